@@ -357,8 +357,10 @@ class SpiralIterator {
     resolution_ = m.resolution;
     bufferSize_ = m.size;
     startIndex_ = m.startIndex;
-    m.getIndex(center_, indexCenter_);  // buffer index
-    if (wrapCorrect_) indexCenter_ = getIndexFromBufferIndex(indexCenter_, bufferSize_, startIndex_);
+    m.getIndex(center_, indexCenter_);  // upstream: BUFFER index (wrapped into range when startIndex != 0)
+    if (wrapCorrect_)                   // repaired mode: the raw unwrapped index (no wrap, may be out of range,
+      getIndexFromPosition(indexCenter_, center_, mapLength_, mapPosition_, resolution_, bufferSize_,
+                           Idx2{0, 0});  // exactly what upstream computes when startIndex == (0,0))
     nRings_ = static_cast<unsigned int>(std::ceil(radius_ / resolution_));
     if (checkIfIndexInRange(indexCenter_, bufferSize_))
       pointsRing_.push_back(indexCenter_);

@@ -1,0 +1,629 @@
+// libfhp C-ABI (include/fhp.h): context, map ingest, parameter derivation, geometry tables, launch plumbing.
+// No CPU fallback lives here: every compute entry point launches the sm_100a kernels or fails.
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fhp_host.h"
+
+using namespace fhp;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct fhp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  mutable std::string err;
+  std::mutex mu;  // one plan at a time per ctx (the reference class is not re-entrant either)
+  // map
+  bool haveMap = false;
+  MapDev M{};
+  std::vector<std::string> layerNames;
+  std::vector<const float*> layerPtrs;  // device
+  std::vector<float*> owned;            // device buffers we allocated
+  // geometry tables cache
+  bool haveGeo = false;
+  float geoFoot = 0, geoSearch = 0;
+  GeoDev G{};
+  // scratch
+  DevBuf dPars, dQ, dOutN, dOutC, dSt, dErr, dA, dB, dC2, dD;
+  long long launches = 0;
+  unsigned pendingErrCheck = 0;
+};
+
+namespace {
+
+int fail(const fhp_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) return fail(ctx, FHP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+void free_owned(fhp_ctx* ctx) {
+  for (float* p : ctx->owned) cudaFree(p);
+  ctx->owned.clear();
+}
+
+int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
+  if (!d || d->rows <= 0 || d->cols <= 0 || !(d->resolution > 0) || d->n_layers < 0 ||
+      d->start_row < 0 || d->start_col < 0 || d->start_row >= d->rows || d->start_col >= d->cols)
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid map description");
+  MapDev& M = ctx->M;
+  M.rows = d->rows;
+  M.cols = d->cols;
+  M.start0 = d->start_row;
+  M.start1 = d->start_col;
+  M.res = d->resolution;
+  M.lenx = d->length_x;
+  M.leny = d->length_y;
+  M.posx = d->pos_x;
+  M.posy = d->pos_y;
+  M.halfx = 0.5 * M.lenx;                        // getVectorToOrigin
+  M.halfy = 0.5 * M.leny;
+  M.fcx = M.posx + (M.halfx - 0.5 * M.res);      // mapPosition + getVectorToFirstCell
+  M.fcy = M.posy + (M.halfy - 0.5 * M.res);
+  ctx->haveGeo = false;
+  return FHP_OK;
+}
+
+int bind_layers(fhp_ctx* ctx) {
+  ctx->M.trav = nullptr;
+  ctx->M.elev = nullptr;
+  for (size_t i = 0; i < ctx->layerNames.size(); ++i) {
+    if (ctx->layerNames[i] == "traversability") ctx->M.trav = ctx->layerPtrs[i];
+    if (ctx->layerNames[i] == "elevation") ctx->M.elev = ctx->layerPtrs[i];
+  }
+  if (!ctx->M.trav || !ctx->M.elev) {
+    ctx->haveMap = false;
+    return fail(ctx, FHP_ERR_MISSING_LAYER, "map needs layers \"traversability\" and \"elevation\"");
+  }
+  ctx->haveMap = true;
+  return FHP_OK;
+}
+
+// Derive what FootholdPlanner::initialize computes from the rosparams (FP.cpp:317-421), with the reference's
+// float / double member types (FootholdPlanner.hpp:609-697).
+void derive_params(const fhp_params& p, ParDev& o) {
+  const float lengthBase = p.kin_length;                 // FP.cpp:340
+  const float widthBase = p.kin_width + p.kin_l1 * 2;    // FP.cpp:341 (float arithmetic)
+  const float skew = p.skew;
+  o.stancex[0] = lengthBase * 0.5;   o.stancey[0] = -widthBase * 0.5;  // RF  FP.cpp:350-351
+  o.stancex[1] = -lengthBase * 0.5;  o.stancey[1] = -widthBase * 0.5;  // RH
+  o.stancex[2] = -lengthBase * 0.5;  o.stancey[2] = widthBase * 0.5;   // LH
+  o.stancex[3] = lengthBase * 0.5;   o.stancey[3] = widthBase * 0.5;   // LF
+  if (p.gait == FHP_GAIT_CUSTOM) {
+    for (int f = 0; f < 4; ++f) {
+      o.biasx[f] = p.bias[f][0];
+      o.biasy[f] = p.bias[f][1];
+    }
+  } else if (p.gait == FHP_GAIT_WALK) {  // extension, see include/fhp.h
+    const double sl = p.step_length;
+    o.biasx[0] = 0.5 * lengthBase + 0.375 * sl;   o.biasy[0] = -0.5 * widthBase;
+    o.biasx[1] = -0.5 * lengthBase + 0.125 * sl;  o.biasy[1] = -0.5 * widthBase;
+    o.biasx[2] = -0.5 * lengthBase - 0.375 * sl;  o.biasy[2] = 0.5 * widthBase;
+    o.biasx[3] = 0.5 * lengthBase - 0.125 * sl;   o.biasy[3] = 0.5 * widthBase;
+  } else if (p.rf_first) {  // FP.cpp:403-411
+    o.biasx[0] = 0.5 * lengthBase + skew;   o.biasy[0] = -0.5 * widthBase;
+    o.biasx[1] = -0.5 * lengthBase - skew;  o.biasy[1] = -0.5 * widthBase;
+    o.biasx[2] = -0.5 * lengthBase + skew;  o.biasy[2] = 0.5 * widthBase;
+    o.biasx[3] = 0.5 * lengthBase - skew;   o.biasy[3] = 0.5 * widthBase;
+  } else {  // FP.cpp:412-421
+    o.biasx[0] = 0.5 * lengthBase - skew;   o.biasy[0] = -0.5 * widthBase;
+    o.biasx[1] = -0.5 * lengthBase + skew;  o.biasy[1] = -0.5 * widthBase;
+    o.biasx[2] = -0.5 * lengthBase - skew;  o.biasy[2] = 0.5 * widthBase;
+    o.biasx[3] = 0.5 * lengthBase + skew;   o.biasy[3] = 0.5 * widthBase;
+  }
+  o.stepLength = p.step_length;
+  o.halfStep = p.step_length / 2;     // float / int -> float (FP.cpp:2693)
+  o.R = p.search_radius;
+  o.halfR = 0.5 * p.search_radius;    // 0.5*radius (FP.cpp:2502)
+  o.rectLx = p.search_radius * 2;     // float (FP.cpp:1616)
+  o.rectLy = p.search_radius;
+  o.r = p.foot_radius;
+  o.r2 = std::pow(o.r, 2);            // CircleIterator: pow(radius, 2)
+  o.R2 = o.R * o.R;                   // SpiralIterator: radius * radius
+  o.h = p.h;
+  o.drift = p.drift_per_cycle;
+  o.thrD = p.thr_default;
+  o.thrC = p.thr_candidate;
+  o.spiralMode = p.spiral_mode;
+  o.pad = 0;
+}
+
+int sgn(int v) { return (v > 0) - (v < 0); }
+
+// Tables that depend only on (footRadius, searchRadius, resolution): the SpiralIterator visiting order and the
+// cell-centred foot-disc stencil.
+int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
+  if (ctx->haveGeo && ctx->geoFoot == footRadius && ctx->geoSearch == searchRadius) return FHP_OK;
+  const MapDev& M = ctx->M;
+  GeoDev& G = ctx->G;
+  std::memset(&G, 0, sizeof(G));
+  const double R = searchRadius, r = footRadius, res = M.res;
+  if (!(R >= 0) || !(r >= 0)) return fail(ctx, FHP_ERR_INVALID_ARG, "radii must be non-negative");
+  const double nr = std::ceil(R / res);  // SpiralIterator: nRings_ = ceil(radius_/resolution_)
+  if (nr > 15) return fail(ctx, FHP_ERR_UNSUPPORTED, "searchRadius/resolution > 15 rings is outside the window tables");
+  G.nRings = static_cast<int>(nr);
+
+  // ---- foot-disc stencil around a cell centre: offsets whose centre distance is <= footRadius.
+  // The reference decides each cell with (pos(u+s) - pos(u))^2 summed in double; that equals |s|*res up to a
+  // rounding error bounded by `tol`.  Offsets further than tol from the boundary are classified here once;
+  // an offset inside the band cannot be classified without the per-cell rounding and is refused.
+  const double Mmax = std::fmax(std::fabs(M.posx) + M.halfx, std::fabs(M.posy) + M.halfy) + 1.0;
+  const double tol = 64.0 * DBL_EPSILON * Mmax * (r + res);
+  const int span = static_cast<int>(std::floor(r / res)) + 2;
+  int ra = 0, ns = 0;
+  for (int sa = -span; sa <= span; ++sa)
+    for (int sb = -span; sb <= span; ++sb) {
+      const double d2 = static_cast<double>(sa * sa + sb * sb) * (res * res);
+      bool in;
+      if (sa == 0 && sb == 0) {
+        in = true;  // distance is exactly 0
+      } else if (d2 <= r * r - tol) {
+        in = true;
+      } else if (d2 >= r * r + tol) {
+        in = false;
+      } else {
+        return fail(ctx, FHP_ERR_UNSUPPORTED,
+                    "footRadius is within rounding distance of a cell-centre distance (stencil offset ambiguous)");
+      }
+      if (!in) continue;
+      if (ns >= kMaxSten) return fail(ctx, FHP_ERR_UNSUPPORTED, "footRadius/resolution too large for the stencil table");
+      G.sten[ns][0] = static_cast<int8_t>(sa);
+      G.sten[ns][1] = static_cast<int8_t>(sb);
+      ++ns;
+      ra = std::max(ra, std::max(std::abs(sa), std::abs(sb)));
+    }
+  G.nSten = ns;
+  G.ra = ra;
+  G.HW = G.nRings + ra;
+  if (G.HW < 1) G.HW = 1;
+  // the staged window must also contain the foot disc of the (continuous) centre: index distance <= floor(r/res)+1
+  if (G.HW < static_cast<int>(std::floor(r / res)) + 1) G.HW = static_cast<int>(std::floor(r / res)) + 1;
+  G.WIN = 2 * G.HW + 1;
+  if (G.WIN > 32)
+    return fail(ctx, FHP_ERR_UNSUPPORTED, "(searchRadius+footRadius)/resolution needs a window wider than 32 cells");
+  G.pack = G.WIN <= 8 ? 4 : (G.WIN <= 16 ? 2 : 1);
+  G.rpShift = G.pack == 4 ? 3 : (G.pack == 2 ? 4 : 5);
+  G.nIter = (G.WIN + G.pack - 1) / G.pack;
+  G.stride = (3 * G.nIter) | 1;
+
+  // ---- SpiralIterator order: centre, then ring d = 1..nRings generated by the upstream walk and consumed from
+  // the BACK of the ring vector (pointsRing_.back()/pop_back()).
+  std::vector<std::pair<int, int>> table;
+  table.push_back({0, 0});
+  int lastTwo = -1;
+  for (int d = 1; d <= G.nRings; ++d) {
+    if (lastTwo < 0 && (d == G.nRings - 1 || d == G.nRings)) lastTwo = static_cast<int>(table.size());
+    std::vector<std::pair<int, int>> ring;
+    int x = d, y = 0;
+    do {
+      ring.push_back({x, y});
+      const int nx = -sgn(y), ny = sgn(x);
+      if (nx != 0 && static_cast<int>(std::sqrt(static_cast<double>((x + nx) * (x + nx) + y * y))) == d)
+        x += nx;
+      else if (ny != 0 && static_cast<int>(std::sqrt(static_cast<double>(x * x + (y + ny) * (y + ny)))) == d)
+        y += ny;
+      else {
+        x += nx;
+        y += ny;
+      }
+    } while (x != d || y != 0);
+    for (auto it = ring.rbegin(); it != ring.rend(); ++it) table.push_back(*it);
+  }
+  if (lastTwo < 0) lastTwo = static_cast<int>(table.size());
+  if (table.size() > static_cast<size_t>(kMaxCand)) return fail(ctx, FHP_ERR_UNSUPPORTED, "spiral table overflow");
+  G.nCand = static_cast<int>(table.size());
+  G.lastTwoStart = lastTwo;
+  for (int k = 0; k < G.nCand; ++k) {
+    G.spiral[k][0] = static_cast<int8_t>(table[k].first);
+    G.spiral[k][1] = static_cast<int8_t>(table[k].second);
+  }
+  ctx->geoFoot = footRadius;
+  ctx->geoSearch = searchRadius;
+  ctx->haveGeo = true;
+  return FHP_OK;
+}
+
+int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cudaStream_t s) {
+  if (!params || n_params <= 0) return fail(ctx, FHP_ERR_INVALID_ARG, "params missing");
+  for (int i = 1; i < n_params; ++i)
+    if (params[i].foot_radius != params[0].foot_radius || params[i].search_radius != params[0].search_radius)
+      return fail(ctx, FHP_ERR_INVALID_ARG, "all parameter sets of one call must share foot_radius and search_radius");
+  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius);
+  if (rc != FHP_OK) return rc;
+  std::vector<ParDev> h(n_params);
+  for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i]);
+  CU(ctx->dPars.reserve(sizeof(ParDev) * n_params));
+  CU(cudaMemcpyAsync(ctx->dPars.p, h.data(), sizeof(ParDev) * n_params, cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));  // h goes out of scope
+  return FHP_OK;
+}
+
+int check_dev_err(fhp_ctx* ctx) {
+  unsigned e = 0;
+  CU(cudaMemcpy(&e, ctx->dErr.p, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) {
+    unsigned z = 0;
+    cudaMemcpy(ctx->dErr.p, &z, sizeof(z), cudaMemcpyHostToDevice);
+    char b[160];
+    snprintf(b, sizeof b, "kernel reported geometry outside its window tables (bits 0x%x)", e);
+    return fail(ctx, FHP_ERR_UNSUPPORTED, b);
+  }
+  return FHP_OK;
+}
+
+int ensure_err_word(fhp_ctx* ctx) {
+  if (!ctx->dErr.p) {
+    CU(ctx->dErr.reserve(sizeof(unsigned)));
+    CU(cudaMemset(ctx->dErr.p, 0, sizeof(unsigned)));
+  }
+  return FHP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fhp_version(void) { return "libfhp 0.1 (sm_100a)"; }
+
+void fhp_default_params(fhp_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->foot_radius = 0.02f;
+  p->search_radius = 0.1f;
+  p->step_length = 0.18f;
+  p->skew = 0.04f;
+  p->thr_default = 0.9f;
+  p->thr_candidate = 0.7f;
+  p->kin_length = 0.4387f;
+  p->kin_width = 0.175f;
+  p->kin_l1 = 0.037f;
+  p->rf_first = 0;
+  p->gait = FHP_GAIT_TROT;
+  p->spiral_mode = FHP_SPIRAL_WRAP_CORRECT;
+  p->h = 0.01;
+  p->drift_per_cycle = -0.007;
+}
+
+int fhp_create(int device, fhp_ctx** out) {
+  if (!out) return FHP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return FHP_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return FHP_ERR_INVALID_ARG;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return FHP_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "libfhp is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return FHP_ERR_CUDA;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return FHP_ERR_CUDA;
+  }
+  fhp_ctx* ctx = new fhp_ctx();
+  ctx->device = device;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return FHP_ERR_CUDA;
+  }
+  *out = ctx;
+  return FHP_OK;
+}
+
+void fhp_destroy(fhp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_owned(ctx);
+  for (DevBuf* b : {&ctx->dPars, &ctx->dQ, &ctx->dOutN, &ctx->dOutC, &ctx->dSt, &ctx->dErr, &ctx->dA, &ctx->dB, &ctx->dC2,
+                    &ctx->dD})
+    b->release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* fhp_last_error(const fhp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int fhp_set_map(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* layers) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (!layers || !desc || !desc->layer_names) return fail(ctx, FHP_ERR_INVALID_ARG, "null map");
+  int rc = set_geometry(ctx, desc);
+  if (rc != FHP_OK) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_owned(ctx);
+  ctx->layerNames.clear();
+  ctx->layerPtrs.clear();
+  ctx->haveMap = false;
+  const size_t bytes = static_cast<size_t>(desc->rows) * desc->cols * sizeof(float);
+  for (int i = 0; i < desc->n_layers; ++i) {
+    if (!layers[i] || !desc->layer_names[i]) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer");
+    float* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    ctx->owned.push_back(d);
+    CU(cudaMemcpyAsync(d, layers[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->layerNames.push_back(desc->layer_names[i]);
+    ctx->layerPtrs.push_back(d);
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return bind_layers(ctx);
+}
+
+int fhp_set_map_device(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* layers) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (!layers || !desc || !desc->layer_names) return fail(ctx, FHP_ERR_INVALID_ARG, "null map");
+  int rc = set_geometry(ctx, desc);
+  if (rc != FHP_OK) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_owned(ctx);
+  ctx->layerNames.clear();
+  ctx->layerPtrs.clear();
+  ctx->haveMap = false;
+  for (int i = 0; i < desc->n_layers; ++i) {
+    if (!layers[i] || !desc->layer_names[i]) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer");
+    ctx->layerNames.push_back(desc->layer_names[i]);
+    ctx->layerPtrs.push_back(layers[i]);
+  }
+  return bind_layers(ctx);
+}
+
+const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* name) {
+  if (!ctx || !name) return nullptr;
+  for (size_t i = 0; i < ctx->layerNames.size(); ++i)
+    if (ctx->layerNames[i] == name) return ctx->layerPtrs[i];
+  return nullptr;
+}
+
+static int plan_common(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,
+                       int64_t n_queries, int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC,
+                       fhp_query_status* d_st, cudaStream_t s) {
+  int rc = prepare_params(ctx, params, n_params, s);
+  if (rc != FHP_OK) return rc;
+  rc = ensure_err_word(ctx);
+  if (rc != FHP_OK) return rc;
+  PlanArgs A;
+  A.M = ctx->M;
+  A.pars = static_cast<const ParDev*>(ctx->dPars.p);
+  A.nPars = n_params;
+  A.q = d_queries;
+  A.nq = n_queries;
+  A.cycles = gait_cycles;
+  A.outN = d_outN;
+  A.outC = d_outC;
+  A.st = d_st;
+  A.err = static_cast<unsigned*>(ctx->dErr.p);
+  CU(launch_plan(A, ctx->G, d_outC != nullptr, s));
+  if (n_queries > 0) ctx->launches += 1;
+  return FHP_OK;
+}
+
+int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
+             int32_t gait_cycles, fhp_foothold* out_nominal, fhp_foothold* out_centroid, fhp_query_status* status) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 || (n_queries > 0 && (!queries || !out_nominal || !status)))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments (gait_cycles is a uint8 in the service request)");
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan before fhp_set_map");
+  for (int64_t i = 0; i < n_queries; ++i)
+    if (queries[i].param_id < 0 || queries[i].param_id >= n_params)
+      return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
+  CU(cudaSetDevice(ctx->device));
+  if (n_queries == 0) return FHP_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t R = FHP_ROWS_PER_QUERY(gait_cycles);
+  const size_t qB = sizeof(fhp_query) * n_queries, oB = sizeof(fhp_foothold) * R * n_queries,
+               sB = sizeof(fhp_query_status) * n_queries;
+  CU(ctx->dQ.reserve(qB));
+  CU(ctx->dOutN.reserve(oB));
+  if (out_centroid) CU(ctx->dOutC.reserve(oB));
+  CU(ctx->dSt.reserve(sB));
+  CU(cudaMemcpyAsync(ctx->dQ.p, queries, qB, cudaMemcpyHostToDevice, s));
+  int rc = plan_common(ctx, params, n_params, static_cast<const fhp_query*>(ctx->dQ.p), n_queries, gait_cycles,
+                       static_cast<fhp_foothold*>(ctx->dOutN.p),
+                       out_centroid ? static_cast<fhp_foothold*>(ctx->dOutC.p) : nullptr,
+                       static_cast<fhp_query_status*>(ctx->dSt.p), s);
+  if (rc != FHP_OK) return rc;
+  CU(cudaMemcpyAsync(out_nominal, ctx->dOutN.p, oB, cudaMemcpyDeviceToHost, s));
+  if (out_centroid) CU(cudaMemcpyAsync(out_centroid, ctx->dOutC.p, oB, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(status, ctx->dSt.p, sB, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return check_dev_err(ctx);
+}
+
+int fhp_plan_device(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,
+                    int64_t n_queries, int32_t gait_cycles, fhp_foothold* d_out_nominal, fhp_foothold* d_out_centroid,
+                    fhp_query_status* d_status, void* cuda_stream) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 ||
+      (n_queries > 0 && (!d_queries || !d_out_nominal || !d_status)))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments");
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan_device before fhp_set_map");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  ctx->pendingErrCheck = 1;
+  return plan_common(ctx, params, n_params, d_queries, n_queries, gait_cycles, d_out_nominal, d_out_centroid, d_status,
+                     s);
+}
+
+int fhp_synchronize(fhp_ctx* ctx) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->pendingErrCheck && ctx->dErr.p) {
+    ctx->pendingErrCheck = 0;
+    CU(cudaDeviceSynchronize());
+    return check_dev_err(ctx);
+  }
+  return FHP_OK;
+}
+
+static int run_task(fhp_ctx* ctx, int mode, const fhp_params* params, const double* centres, const double* rects,
+                    int64_t n, fhp_foothold* out, uint8_t* valid, int8_t* ccase, float* z) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n < 0 || !params || (n > 0 && !centres)) return fail(ctx, FHP_ERR_INVALID_ARG, "invalid task arguments");
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "no map set");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) return FHP_OK;
+  cudaStream_t s = ctx->stream;
+  int rc = prepare_params(ctx, params, 1, s);
+  if (rc != FHP_OK) return rc;
+  rc = ensure_err_word(ctx);
+  if (rc != FHP_OK) return rc;
+  const size_t cB = sizeof(double) * 2 * n;
+  CU(ctx->dA.reserve(cB));
+  CU(cudaMemcpyAsync(ctx->dA.p, centres, cB, cudaMemcpyHostToDevice, s));
+  if (rects) {
+    CU(ctx->dB.reserve(cB));
+    CU(cudaMemcpyAsync(ctx->dB.p, rects, cB, cudaMemcpyHostToDevice, s));
+  }
+  if (out) CU(ctx->dOutN.reserve(sizeof(fhp_foothold) * n));
+  CU(ctx->dC2.reserve(static_cast<size_t>(n)));      // valid / case bytes
+  CU(ctx->dD.reserve(sizeof(float) * n));             // z
+  TaskArgs A;
+  A.M = ctx->M;
+  A.pars = static_cast<const ParDev*>(ctx->dPars.p);
+  A.centres = static_cast<const double*>(ctx->dA.p);
+  A.rects = rects ? static_cast<const double*>(ctx->dB.p) : nullptr;
+  A.n = n;
+  A.out = static_cast<fhp_foothold*>(ctx->dOutN.p);
+  A.valid = static_cast<uint8_t*>(ctx->dC2.p);
+  A.ccase = static_cast<int8_t*>(ctx->dC2.p);
+  A.z = static_cast<float*>(ctx->dD.p);
+  A.err = static_cast<unsigned*>(ctx->dErr.p);
+  CU(launch_task(mode, A, ctx->G, s));
+  ctx->launches += 1;
+  if (out) CU(cudaMemcpyAsync(out, ctx->dOutN.p, sizeof(fhp_foothold) * n, cudaMemcpyDeviceToHost, s));
+  if (valid) CU(cudaMemcpyAsync(valid, ctx->dC2.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, s));
+  if (ccase) CU(cudaMemcpyAsync(ccase, ctx->dC2.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, s));
+  if (z) CU(cudaMemcpyAsync(z, ctx->dD.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return check_dev_err(ctx);
+}
+
+int fhp_check_foothold(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, const double* rect_centres_xy,
+                       int64_t n, fhp_foothold* out, uint8_t* valid_out) {
+  if (n > 0 && (!rect_centres_xy || !out || !valid_out)) return fail(ctx, FHP_ERR_INVALID_ARG, "null output");
+  return run_task(ctx, 0, params, centres_xy, rect_centres_xy, n, out, valid_out, nullptr, nullptr);
+}
+int fhp_check_centroid(fhp_ctx* ctx, const fhp_params* params, const double* points_xy, int64_t n, fhp_foothold* out,
+                       int8_t* case_out) {
+  if (n > 0 && (!out || !case_out)) return fail(ctx, FHP_ERR_INVALID_ARG, "null output");
+  return run_task(ctx, 1, params, points_xy, nullptr, n, out, nullptr, case_out, nullptr);
+}
+int fhp_mean_height(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, int64_t n, float* z_out) {
+  if (n > 0 && !z_out) return fail(ctx, FHP_ERR_INVALID_ARG, "null output");
+  return run_task(ctx, 2, params, centres_xy, nullptr, n, nullptr, nullptr, nullptr, z_out);
+}
+int fhp_check_default(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, int64_t n, uint8_t* valid_out) {
+  if (n > 0 && !valid_out) return fail(ctx, FHP_ERR_INVALID_ARG, "null output");
+  return run_task(ctx, 3, params, centres_xy, nullptr, n, nullptr, valid_out, nullptr, nullptr);
+}
+
+int64_t fhp_kernel_launches(const fhp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- NCCL map replication (symbols resolved at run time from the NCCL already in the process) ------------------
+typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static void* nccl_sym(const char* name) {
+  void* f = dlsym(RTLD_DEFAULT, name);
+  if (f) return f;
+  static void* h = nullptr;
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+  return h ? dlsym(h, name) : nullptr;
+}
+
+int fhp_broadcast_map(fhp_ctx* ctx, const fhp_map_desc* desc, void* nccl_comm, int root, int rank) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!desc || !nccl_comm || !desc->layer_names) return fail(ctx, FHP_ERR_INVALID_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  nccl_bcast_fn bcast = reinterpret_cast<nccl_bcast_fn>(nccl_sym("ncclBroadcast"));
+  if (!bcast) return fail(ctx, FHP_ERR_NCCL, "ncclBroadcast not found in the process");
+  const size_t count = static_cast<size_t>(desc->rows) * desc->cols;
+  if (rank != root) {
+    int rc = set_geometry(ctx, desc);
+    if (rc != FHP_OK) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_owned(ctx);
+    ctx->layerNames.clear();
+    ctx->layerPtrs.clear();
+    ctx->haveMap = false;
+    for (int i = 0; i < desc->n_layers; ++i) {
+      float* d = nullptr;
+      CU(cudaMalloc(&d, count * sizeof(float)));
+      ctx->owned.push_back(d);
+      ctx->layerNames.push_back(desc->layer_names[i]);
+      ctx->layerPtrs.push_back(d);
+    }
+  } else {
+    if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "root has no map to broadcast");
+    if (static_cast<int>(ctx->layerNames.size()) != desc->n_layers || ctx->M.rows != desc->rows ||
+        ctx->M.cols != desc->cols)
+      return fail(ctx, FHP_ERR_INVALID_ARG, "desc does not match the root's map");
+  }
+  for (int i = 0; i < desc->n_layers; ++i) {
+    // ncclFloat32 == 7
+    int r = bcast(ctx->layerPtrs[i], const_cast<float*>(ctx->layerPtrs[i]), count, 7, root, nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, FHP_ERR_NCCL, "ncclBroadcast failed with code " + std::to_string(r));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return bind_layers(ctx);
+}
+
+}  // extern "C"

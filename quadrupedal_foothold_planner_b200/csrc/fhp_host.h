@@ -1,0 +1,40 @@
+// Host <-> kernel argument structs and launchers shared by fhp_kernels.cu and fhp_capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fhp_types.h"
+
+namespace fhp {
+
+constexpr int kPlanThreads = 128;
+
+struct PlanArgs {
+  MapDev M;
+  const ParDev* pars;
+  int nPars;
+  const fhp_query* q;
+  long long nq;
+  int cycles;
+  fhp_foothold* outN;
+  fhp_foothold* outC;
+  fhp_query_status* st;
+  unsigned* err;  // device word, OR of the kErr* bits of every query
+};
+
+struct TaskArgs {
+  MapDev M;
+  const ParDev* pars;
+  const double* centres;
+  const double* rects;
+  long long n;
+  fhp_foothold* out;
+  uint8_t* valid;
+  int8_t* ccase;
+  float* z;
+  unsigned* err;
+};
+
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream);
+cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream_t stream);
+
+}  // namespace fhp

@@ -1,0 +1,250 @@
+// libfhp kernels (sm_100a).  See fhp_device.cuh for the design of the device functions.
+//
+// plan_kernel: one LANE per (query, leg); the 4 lanes of a quad own the RF,RH,LH,LF feet of one query and carry
+// BOTH chains of the reference's cycle loop (FP.cpp:762-1579) in registers across all gait cycles, so one launch
+// plans every cycle of every query (the sequential gait-cycle dependency never leaves the SM).  A warp = 8
+// queries; the only cross-lane traffic is quad shuffles (stance centroid, 4-way AND) and the warp-cooperative
+// window staging.
+#include "fhp_device.cuh"
+#include "fhp_host.h"
+
+namespace fhp {
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+// FootholdPlanner::getPolygonCenter (FP.cpp:2421-2463), xy only (z never reaches the response).
+__device__ __forceinline__ void polygon_center(double rfx, double rfy, double rhx, double rhy, double lhx, double lhy,
+                                               double lfx, double lfy, double& cx, double& cy) {
+  double x1 = rfx, y1 = rfy, x2 = rhx, y2 = rhy, x3, y3;
+  double sum_x = 0, sum_y = 0, sum_s = 0;
+  x3 = lhx;
+  y3 = lhy;
+  double s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) / 2.0;
+  sum_x += (x1 + x2 + x3) * s;
+  sum_y += (y1 + y2 + y3) * s;
+  sum_s += s;
+  x2 = x3;
+  y2 = y3;
+  x3 = lfx;
+  y3 = lfy;
+  s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) / 2.0;
+  sum_x += (x1 + x2 + x3) * s;
+  sum_y += (y1 + y2 + y3) * s;
+  sum_s += s;
+  cx = sum_x / sum_s / 3.0;
+  cy = sum_y / sum_s / 3.0;
+}
+
+__device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y, double z, int row, int col, int foot,
+                                          int cycle, int kind) {
+  double* d = reinterpret_cast<double*>(dst);
+  d[0] = x;
+  d[1] = y;
+  d[2] = z;
+  unsigned long long idx = static_cast<unsigned int>(row) | (static_cast<unsigned long long>(static_cast<unsigned int>(col)) << 32);
+  unsigned long long ids = static_cast<unsigned long long>(foot & 0xff) | (static_cast<unsigned long long>(cycle & 0xff) << 8) |
+                           (static_cast<unsigned long long>(kind & 0xff) << 16);
+  reinterpret_cast<unsigned long long*>(dst)[3] = idx;
+  reinterpret_cast<unsigned long long*>(dst)[4] = ids;
+}
+
+template <bool WANT_CEN>
+__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const __grid_constant__ PlanArgs A,
+                                                            const __grid_constant__ GeoDev G) {
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warpInBlock = threadIdx.x >> 5;
+  uint32_t* sw = smem + warpInBlock * 32 * G.stride;
+  const long long gwarp = static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock;
+  const long long q = gwarp * 8 + (lane >> 2);
+  const int f = lane & 3;           // RF,RH,LH,LF
+  const int quad0 = lane & ~3;
+  const bool active = q < A.nq;
+  if (gwarp * 8 >= A.nq) return;    // whole warp idle
+  const MapDev& M = A.M;
+
+  fhp_query qu;
+  qu.x = qu.y = qu.z = 0.0;
+  qu.param_id = 0;
+  if (active) {
+    const fhp_query* src = A.q + q;
+    qu.x = src->x;
+    qu.y = src->y;
+    qu.z = src->z;
+    qu.param_id = src->param_id;
+  }
+  const ParDev& P = A.pars[qu.param_id];
+  const long long R = 4 + 4 * static_cast<long long>(A.cycles);
+  fhp_foothold* outN = A.outN + q * R;
+  fhp_foothold* outC = WANT_CEN ? A.outC + q * R : nullptr;
+
+  // initialize() stance (FP.cpp:350-378) and setFirstGait (FP.cpp:2679-2699) for both chains
+  const double stx = P.stancex[f] + qu.x, sty = P.stancey[f] + qu.y, stz = 0.0 + qu.z;
+  double nomx = stx - P.halfStep, nomy = sty;
+  double cenx = nomx, ceny = nomy;
+  if (active) {  // FP.cpp:685-699 (and :713-727 for the centroid message)
+    int r0, c0;
+    cell_of_position(M, stx, sty, r0, c0);
+    write_row(outN + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
+    if (WANT_CEN) write_row(outC + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
+  }
+  double adjY = 0.0;  // ajustedPose_[1] (FP.cpp:759)
+  int nrows = 4, succeed = 0;
+  bool success = false;
+  unsigned err = 0;
+  const double bx = P.biasx[f], by = P.biasy[f];
+  const float thrD = P.thrD, thrC = P.thrC;
+
+  for (int g = 0; g < A.cycles; ++g) {
+    // getFootholdSearchGridMap for both chains (FP.cpp:788, :830 -> :2166-2250)
+    double ccx, ccy, ncx, ncy;
+    polygon_center(shfl_d(cenx, quad0), shfl_d(ceny, quad0), shfl_d(cenx, quad0 + 1), shfl_d(ceny, quad0 + 1),
+                   shfl_d(cenx, quad0 + 2), shfl_d(ceny, quad0 + 2), shfl_d(cenx, quad0 + 3), shfl_d(ceny, quad0 + 3),
+                   ccx, ccy);
+    polygon_center(shfl_d(nomx, quad0), shfl_d(nomy, quad0), shfl_d(nomx, quad0 + 1), shfl_d(nomy, quad0 + 1),
+                   shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
+                   ncx, ncy);
+    const double nextY = qu.y + adjY;                                 // :2201
+    const double px = (ccx + P.stepLength) + bx, py = nextY + by;     // centroid-chain next foothold (:2199,:2414)
+    const double rx = (ncx + P.stepLength) + bx, ry = nextY + by;     // nominal-chain next foothold = rectangle centre
+
+    // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
+    const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
+    const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
+    stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
+
+    bool ok = false;
+    CentroidOut co;
+    NominalOut no;
+    double nz = 0.0, cz = 0.0;
+    if (active) {
+      Planes pl{sw + lane * G.stride, G.pack, G.rpShift};
+      co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);                 // FP.cpp:818-821
+      no = nominal_eval<false>(M, G, P, pl, uc0, uc1, px, py, rx, ry, err);  // FP.cpp:863-903
+      ok = no.ok;
+      if (ok) nz = static_cast<double>(mean_height(M, P, px, py));           // at the CENTRE (FP.cpp:2029)
+      if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, P, co.x, co.y));
+    }
+    // footholdValidation_ = RF & RH & LH & LF (FP.cpp:1323)
+    const unsigned okb = __ballot_sync(kFull, ok);
+    const bool all_ok = ((okb >> quad0) & 0xfu) == 0xfu;
+    if (active) {
+      if (all_ok) {
+        write_row(outN + nrows + f, no.x, no.y, nz, no.row, no.col, f, g, no.kind);  // :1378-1396
+        if (WANT_CEN) {
+          int r0, c0;
+          cell_of_position(M, co.x, co.y, r0, c0);
+          write_row(outC + nrows + f, co.x, co.y, cz, r0, c0, f, g, FHP_KIND_DEFAULT);  // :1444-1462
+        }
+        nrows += 4;
+        succeed = g + 1;   // :1379
+        success = true;    // :1380
+        nomx = no.x;       // :1413-1416
+        nomy = no.y;
+        cenx = co.x;       // :1480-1483
+        ceny = co.y;
+      } else {
+        success = false;   // :1574, no break (:1575)
+      }
+    }
+    adjY += P.drift;       // :1578
+  }
+  if (active && err) atomicOr(A.err, err);
+  unsigned e4 = err;  // OR over the quad
+  e4 |= __shfl_xor_sync(kFull, e4, 1);
+  e4 |= __shfl_xor_sync(kFull, e4, 2);
+  if (active && f == 0) {
+    fhp_query_status s;
+    s.success = success ? 1 : 0;
+    s.gait_cycles = static_cast<uint8_t>(A.cycles);
+    s.gait_cycles_succeed = static_cast<uint8_t>(succeed);
+    s.reserved = static_cast<uint8_t>(e4);
+    s.n_rows = nrows;
+    A.st[q] = s;
+  }
+}
+
+// ---- fine-grained primitives: one lane per task -------------------------------------------------------------------
+// mode 0: checkFoothold, 1: checkFootholdUseCentroidMethod, 2: getFootholdMeanHeight, 3: checkDefaultFoothold
+template <int MODE>
+__global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constant__ TaskArgs A,
+                                                            const __grid_constant__ GeoDev G) {
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warpInBlock = threadIdx.x >> 5;
+  uint32_t* sw = smem + warpInBlock * 32 * G.stride;
+  const long long i = (static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock) * 32 + lane;
+  const bool active = i < A.n;
+  const MapDev& M = A.M;
+  const ParDev& P = A.pars[0];
+  double px = 0, py = 0, rx = 0, ry = 0;
+  if (active) {
+    px = A.centres[2 * i];
+    py = A.centres[2 * i + 1];
+    if (MODE == 0) {
+      rx = A.rects[2 * i];
+      ry = A.rects[2 * i + 1];
+    }
+  }
+  unsigned err = 0;
+  if (MODE == 2) {
+    if (active) A.z[i] = mean_height(M, P, px, py);
+    return;
+  }
+  const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
+  const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
+  stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
+  if (!active) return;
+  Planes pl{sw + lane * G.stride, G.pack, G.rpShift};
+  if (MODE == 0) {
+    NominalOut no = nominal_eval<false>(M, G, P, pl, uc0, uc1, px, py, rx, ry, err);
+    double z = 0.0;
+    if (no.ok) z = static_cast<double>(mean_height(M, P, px, py));
+    write_row(A.out + i, no.x, no.y, z, no.row, no.col, 0, 0, no.kind);
+    A.valid[i] = no.ok ? 1 : 0;
+  } else if (MODE == 1) {
+    CentroidOut co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);
+    double z = 0.0;
+    if (co.ccase >= 0 && co.ccase <= 3) z = static_cast<double>(mean_height(M, P, co.x, co.y));
+    int r0, c0;
+    cell_of_position(M, co.x, co.y, r0, c0);
+    write_row(A.out + i, co.x, co.y, z, r0, c0, 0, 0, FHP_KIND_DEFAULT);
+    A.ccase[i] = static_cast<int8_t>(co.ccase);
+  } else if (MODE == 3) {
+    NominalOut no = nominal_eval<true>(M, G, P, pl, uc0, uc1, px, py, rx, ry, err);
+    A.valid[i] = no.ok ? 1 : 0;
+  }
+  if (err) atomicOr(A.err, err);
+}
+
+// ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream) {
+  if (A.nq <= 0) return cudaSuccess;
+  const int warps = kPlanThreads / 32;
+  const long long nWarps = (A.nq + 7) / 8;
+  const long long blocks = (nWarps + warps - 1) / warps;
+  const size_t shm = static_cast<size_t>(warps) * 32 * G.stride * sizeof(uint32_t);
+  if (wantCen)
+    plan_kernel<true><<<static_cast<unsigned>(blocks), kPlanThreads, shm, stream>>>(A, G);
+  else
+    plan_kernel<false><<<static_cast<unsigned>(blocks), kPlanThreads, shm, stream>>>(A, G);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream_t stream) {
+  if (A.n <= 0) return cudaSuccess;
+  const int warps = kPlanThreads / 32;
+  const long long nWarps = (A.n + 31) / 32;
+  const long long blocks = (nWarps + warps - 1) / warps;
+  const size_t shm = static_cast<size_t>(warps) * 32 * G.stride * sizeof(uint32_t);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  switch (mode) {
+    case 0: task_kernel<0><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+    case 1: task_kernel<1><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+    case 2: task_kernel<2><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+    default: task_kernel<3><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fhp

@@ -1,0 +1,58 @@
+// Plain-data structs shared by the kernels (fhp_device.cuh / fhp_kernels.cu) and the host C-ABI (fhp_capi.cu).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/fhp.h"
+
+namespace fhp {
+
+constexpr int kMaxCand = 1024;  // spiral table entries (nRings <= 15)
+constexpr int kMaxSten = 96;    // foot-disc stencil entries
+constexpr unsigned kFull = 0xffffffffu;
+
+// error bits reported per query (status.reserved) — any non-zero bit fails the whole call loudly
+constexpr unsigned kErrWindow = 1u;   // a cell needed by the reference lies outside the staged window
+constexpr unsigned kErrDiscBig = 2u;  // foot disc window larger than 64 cells
+
+struct MapDev {
+  const float* trav;
+  const float* elev;
+  int rows, cols, start0, start1;
+  double res;
+  double lenx, leny, posx, posy;
+  double halfx, halfy;  // getVectorToOrigin: 0.5*length
+  double fcx, fcy;      // mapPosition + (0.5*length - 0.5*res): the constant term of getPositionFromIndex
+};
+
+struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
+  int nRings;    // ceil(searchRadius / res)                 SpiralIterator ctor
+  int ra;        // foot-disc stencil half width (cells)
+  int HW;        // window half width = nRings + ra
+  int WIN;       // 2*HW + 1 (<= 32)
+  int pack;      // window columns per warp load: 1 (WIN<=32), 2 (WIN<=16), 4 (WIN<=8)
+  int rpShift;   // log2(32/pack): lanes per column group
+  int nIter;     // ceil(WIN / pack) = words per bit-plane
+  int stride;    // shared-memory words per query (3*nIter, padded odd)
+  int nCand;     // spiral table length
+  int lastTwoStart;  // first rank that belongs to ring nRings-1 (distance-filtered rings)
+  int nSten;
+  int8_t sten[kMaxSten][2];
+  int8_t spiral[kMaxCand][2];
+};
+
+struct ParDev {  // one per fhp_params, derived on the host exactly as FootholdPlanner::initialize (FP.cpp:317-421)
+  double biasx[4], biasy[4];      // RF,RH,LH,LF default bias
+  double stancex[4], stancey[4];  // +-lengthBase*0.5, +-widthBase*0.5 (initial stance before adding the pose)
+  double stepLength;              // (double)stepLength_
+  double halfStep;                // (double)(stepLength_/2)  (float division, FP.cpp:2693)
+  double R;                       // (double)searchRadius_
+  double halfR;                   // 0.5*R
+  double rectLx, rectLy;          // (double)(searchRadius_*2), (double)searchRadius_  (FP.cpp:1616-1617)
+  double r, r2, R2;               // (double)footRadius_, pow(r,2), R*R
+  double h, drift;
+  float thrD, thrC;
+  int spiralMode;
+  int pad;
+};
+
+}  // namespace fhp

@@ -1,0 +1,304 @@
+"""Host side of libfhp: a ctypes binding of include/fhp.h (`Fhp`) and a mirror of the reference's
+`foothold_planner::FootholdPlanner` class interface (`FootholdPlanner`) on top of it.
+
+The reference's host language is C++ (ROS1); a ROS node binds the same C-ABI from C++ (see INTEGRATION.md and
+csrc/FootholdPlanner.hpp).  This Python mirror keeps the reference's member names, argument meaning and error
+behaviour so the parity tests read like tests of the reference class.
+
+There is NO CPU fallback: if libfhp.so is missing it is built with nvcc; if no sm_100 GPU is usable every compute
+call raises FhpError(FHP_ERR_CUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import (FOOTHOLD_DTYPE, QUERY_DTYPE, STATUS_DTYPE, HostMap, MapDesc, Params, make_queries, rows_per_query,
+                   yaml_params)
+
+_LIB = None
+
+
+class FhpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfhp error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfhp.so")
+
+
+def load_lib():
+    """dlopen libfhp.so, building it first if the sources are newer (nvcc required for that)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    from . import build as _build
+    path = lib_path()
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.fhp_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.fhp_destroy.argtypes = [vp]
+    L.fhp_destroy.restype = None
+    L.fhp_last_error.argtypes = [vp]
+    L.fhp_last_error.restype = C.c_char_p
+    L.fhp_default_params.argtypes = [C.POINTER(Params)]
+    L.fhp_default_params.restype = None
+    L.fhp_version.restype = C.c_char_p
+    L.fhp_set_map.argtypes = [vp, C.POINTER(MapDesc), vp]
+    L.fhp_set_map_device.argtypes = [vp, C.POINTER(MapDesc), vp]
+    L.fhp_map_layer_device.argtypes = [vp, C.c_char_p]
+    L.fhp_map_layer_device.restype = vp
+    L.fhp_plan.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp]
+    L.fhp_plan_device.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp, vp]
+    L.fhp_synchronize.argtypes = [vp]
+    L.fhp_check_foothold.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.fhp_check_centroid.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.fhp_mean_height.argtypes = [vp, vp, vp, i64, vp]
+    L.fhp_check_default.argtypes = [vp, vp, vp, i64, vp]
+    L.fhp_kernel_launches.argtypes = [vp]
+    L.fhp_kernel_launches.restype = i64
+    L.fhp_broadcast_map.argtypes = [vp, C.POINTER(MapDesc), vp, C.c_int, C.c_int]
+    _LIB = L
+    return L
+
+
+def _ptr(a) -> C.c_void_p:
+    """address of a numpy array / torch tensor / raw int"""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+class Fhp:
+    """One libfhp context = one device + one resident map.  Thin, explicit wrapper of the C-ABI."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_lib()
+        h = C.c_void_p()
+        rc = self.L.fhp_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FhpError(rc, (self.L.fhp_last_error(None) or b"").decode())
+        self.h = h
+        self.device = int(device)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fhp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise FhpError(rc, (self.L.fhp_last_error(self.h) or b"").decode())
+
+    # -- map ingest (FootholdPlanner::gridmapCallback, FP.cpp:504-536)
+    def set_map(self, hmap: HostMap):
+        d, ptrs, keep = hmap.desc()
+        self._check(self.L.fhp_set_map(self.h, C.byref(d), C.cast(ptrs, C.c_void_p)))
+        self.map_geometry = hmap
+
+    def set_map_device(self, geometry: HostMap, names: Sequence[str], device_ptrs: Sequence[int], keepalive=None):
+        """Adopt device-resident layers (no copy).  `geometry` supplies rows/cols/resolution/pos/start only."""
+        d, _, keep = geometry.desc(names=[])
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        d.n_layers = len(names)
+        d.layer_names = C.cast(arr, C.POINTER(C.c_char_p))
+        ptrs = (C.c_void_p * len(names))(*[int(p) for p in device_ptrs])
+        self._check(self.L.fhp_set_map_device(self.h, C.byref(d), C.cast(ptrs, C.c_void_p)))
+        self._keep = (keepalive, arr, ptrs)
+        self.map_geometry = geometry
+
+    def layer_device_ptr(self, name: str) -> int:
+        return int(self.L.fhp_map_layer_device(self.h, name.encode()) or 0)
+
+    # -- plan (FootholdPlanner::globalFootholdPlan, FP.cpp:539-1602)
+    @staticmethod
+    def _params_array(params):
+        params = list(params) if isinstance(params, (list, tuple)) else [params]
+        return (Params * len(params))(*params), len(params)
+
+    def plan(self, params, queries: np.ndarray, gait_cycles: int, centroid: bool = False, out=None):
+        """Host buffers in, host buffers out.  -> (nominal [nq,R], centroid [nq,R] | None, status [nq])"""
+        parr, npar = self._params_array(params)
+        q = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
+        nq = len(q)
+        R = rows_per_query(max(0, min(255, int(gait_cycles))))
+        if out is None:
+            nom = np.zeros((nq, R), dtype=FOOTHOLD_DTYPE)
+            cen = np.zeros((nq, R), dtype=FOOTHOLD_DTYPE) if centroid else None
+            st = np.zeros(nq, dtype=STATUS_DTYPE)
+        else:
+            nom, cen, st = out
+        self._check(self.L.fhp_plan(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q), nq, int(gait_cycles), _ptr(nom),
+                                    _ptr(cen) if centroid else None, _ptr(st)))
+        return nom, cen, st
+
+    def plan_raw(self, parr, npar, q_ptr, nq, gait_cycles, nom_ptr, cen_ptr, st_ptr):
+        """fhp_plan on raw host addresses (pinned torch buffers in bench.py)."""
+        self._check(self.L.fhp_plan(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q_ptr), nq, int(gait_cycles),
+                                    _ptr(nom_ptr), _ptr(cen_ptr), _ptr(st_ptr)))
+
+    def plan_device(self, parr, npar, d_queries, nq, gait_cycles, d_nom, d_cen, d_st, stream=None):
+        """Device-resident buffers (torch CUDA tensors or raw device addresses); asynchronous."""
+        self._check(self.L.fhp_plan_device(self.h, C.cast(parr, C.c_void_p), npar, _ptr(d_queries), nq,
+                                           int(gait_cycles), _ptr(d_nom), _ptr(d_cen), _ptr(d_st), _ptr(stream)))
+
+    def synchronize(self):
+        self._check(self.L.fhp_synchronize(self.h))
+
+    def kernel_launches(self) -> int:
+        return int(self.L.fhp_kernel_launches(self.h))
+
+    # -- fine-grained members
+    def check_foothold(self, params: Params, centres, rect_centres):
+        c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+        r = np.ascontiguousarray(rect_centres, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros(len(c), dtype=FOOTHOLD_DTYPE)
+        valid = np.zeros(len(c), dtype=np.uint8)
+        self._check(self.L.fhp_check_foothold(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), _ptr(r), len(c),
+                                              _ptr(out), _ptr(valid)))
+        return out, valid
+
+    def check_centroid(self, params: Params, points):
+        c = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros(len(c), dtype=FOOTHOLD_DTYPE)
+        case = np.zeros(len(c), dtype=np.int8)
+        self._check(self.L.fhp_check_centroid(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), len(c), _ptr(out),
+                                              _ptr(case)))
+        return out, case
+
+    def mean_height(self, params: Params, centres):
+        c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+        z = np.zeros(len(c), dtype=np.float32)
+        self._check(self.L.fhp_mean_height(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), len(c), _ptr(z)))
+        return z
+
+    def check_default(self, params: Params, centres):
+        c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+        v = np.zeros(len(c), dtype=np.uint8)
+        self._check(self.L.fhp_check_default(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), len(c), _ptr(v)))
+        return v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Mirror of the reference's service / message types and class interface
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class Point:  # geometry_msgs/Point
+    x: float = 0.0
+    y: float = 0.0
+    z: float = 0.0
+
+
+@dataclass
+class Foothold:  # foothold_planner_msgs/Foothold (msg/Foothold.msg:1-3)
+    point: Point = field(default_factory=Point)
+    foot_id: int = 0
+    gait_cycle_id: int = 0
+
+
+@dataclass
+class GlobalFootholds:  # foothold_planner_msgs/GlobalFootholds (msg/GlobalFootholds.msg:1-5)
+    success: bool = False
+    gait_cycles: int = 0
+    gait_cycles_succeed: int = 0
+    footholds: List[Foothold] = field(default_factory=list)
+
+
+@dataclass
+class GlobalFootholdPlanRequest:  # srv/GlobalFootholdPlan.srv:1-5 (the four foot fields are ignored, FP.cpp:546-549)
+    gait_cycles: int = 0
+    FR_current_foothold: Point = field(default_factory=Point)
+    RR_current_foothold: Point = field(default_factory=Point)
+    RL_current_foothold: Point = field(default_factory=Point)
+    FL_current_foothold: Point = field(default_factory=Point)
+
+
+@dataclass
+class GlobalFootholdPlanResponse:  # srv/GlobalFootholdPlan.srv:7
+    footholds: GlobalFootholds = field(default_factory=GlobalFootholds)
+
+
+def rows_to_msg(rows: np.ndarray, status) -> GlobalFootholds:
+    """Response assembly (FP.cpp:1378-1396, :1588): the first n_rows rows of one query -> GlobalFootholds."""
+    msg = GlobalFootholds(bool(status["success"]), int(status["gait_cycles"]), int(status["gait_cycles_succeed"]))
+    for r in rows[: int(status["n_rows"])]:
+        msg.footholds.append(Foothold(Point(float(r["x"]), float(r["y"]), float(r["z"])), int(r["foot_id"]),
+                                      int(r["gait_cycle_id"])))
+    return msg
+
+
+class FootholdPlanner:
+    """Drop-in shaped like foothold_planner::FootholdPlanner (FootholdPlanner.hpp:38-757) for the hot path.
+
+    Constructor parameters are the rosparams the path reads (FP.cpp:249-311); `initial_position` is
+    initial_position/{x,y,z}.  gridmapCallback replaces the topic subscription (FP.cpp:188, :504);
+    globalFootholdPlan is the `plan_global_footholds` service body (FP.cpp:539)."""
+
+    def __init__(self, params: Optional[Params] = None, initial_position=(0.0, 0.0, 0.0), device: int = 0):
+        self.params = params if params is not None else yaml_params()
+        self.initialPose_ = tuple(float(v) for v in initial_position)
+        self.fhp = Fhp(device)
+        self.nominalGlobalFootholdsMsg_ = GlobalFootholds()
+        self.centroidGlobalFootholdsMsg_ = GlobalFootholds()
+
+    # FP.cpp:504-536
+    def gridmapCallback(self, msg: HostMap):
+        self.fhp.set_map(msg)
+
+    # FP.cpp:539-1602; returns the service's bool, fills `response`
+    def globalFootholdPlan(self, request: GlobalFootholdPlanRequest, response: GlobalFootholdPlanResponse) -> bool:
+        cycles = int(request.gait_cycles) & 0xFF  # uint8 in the .srv
+        q = make_queries([self.initialPose_])
+        nom, cen, st = self.fhp.plan(self.params, q, cycles, centroid=True)
+        self.nominalGlobalFootholdsMsg_ = rows_to_msg(nom[0], st[0])
+        self.centroidGlobalFootholdsMsg_ = rows_to_msg(cen[0], st[0])
+        response.footholds = self.nominalGlobalFootholdsMsg_  # FP.cpp:1588
+        return True
+
+    # batched extension of the same service: many initial poses at once
+    def globalFootholdPlanBatch(self, initial_positions, gait_cycles: int, params=None, centroid=False):
+        q = initial_positions if isinstance(initial_positions, np.ndarray) and initial_positions.dtype == QUERY_DTYPE \
+            else make_queries(initial_positions)
+        return self.fhp.plan(self.params if params is None else params, q, int(gait_cycles), centroid=centroid)
+
+    # FP.cpp:2001-2036 — returns (footholdResult Point, footholdValidation)
+    def checkFoothold(self, center, polygon_center):
+        out, valid = self.fhp.check_foothold(self.params, [center], [polygon_center])
+        return Point(float(out[0]["x"]), float(out[0]["y"]), float(out[0]["z"])), bool(valid[0])
+
+    # FP.cpp:2039-2082
+    def checkDefaultFoothold(self, center) -> bool:
+        return bool(self.fhp.check_default(self.params, [center])[0])
+
+    # FP.cpp:1605-1997 — returns (resultFoothold Point, case)
+    def checkFootholdUseCentroidMethod(self, defaultFoothold):
+        out, case = self.fhp.check_centroid(self.params, [defaultFoothold])
+        return Point(float(out[0]["x"]), float(out[0]["y"]), float(out[0]["z"])), int(case[0])
+
+    # FP.cpp:2520-2554
+    def getFootholdMeanHeight(self, center) -> float:
+        return float(self.fhp.mean_height(self.params, [center])[0])

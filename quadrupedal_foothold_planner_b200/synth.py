@@ -117,13 +117,13 @@ def stairs_stones_map(rows=2000, cols=2000, res=0.01, seed=20200802, nan_frac=0.
 
 def rough_map(rows=4000, cols=4000, res=0.02, seed=3, nan_frac=0.01, pos=(0.0, 0.0), start=(1234, 2777),
               with_slope=False, pitch_m=0.5) -> HostMap:
-    """C3/C4/C5: rough terrain from bilinear value noise.  trav = clip(1.25 - 1.1*n1, 0, 1) gives roughly a
-    quarter of the cells below the default threshold 0.9 and ~8 % below the candidate threshold 0.7, in patches
+    """C3/C4/C5: rough terrain from smooth value noise n1 in [0,1).  trav = clip(1.79 - 1.333*n1, 0, 1) puts about
+    a quarter of the cells below the default threshold 0.9 and ~8 % below the candidate threshold 0.7, in patches
     of ~0.5 m; elev = 0.3*n2; `nan_frac` of the cells are NaN (independently per layer)."""
     pitch = max(2, int(round(pitch_m / res)))
     n1 = _value_noise(seed, rows, cols, pitch)
     n2 = _value_noise(seed + 101, rows, cols, pitch * 2)
-    trav = np.clip(1.25 - 1.1 * n1, 0.0, 1.0).astype(np.float32)
+    trav = np.clip(1.79 - 1.333 * n1, 0.0, 1.0).astype(np.float32)
     elev = (0.3 * n2).astype(np.float32)
     layers = {"traversability": trav, "elevation": elev}
     if with_slope:

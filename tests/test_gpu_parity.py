@@ -1,0 +1,169 @@
+"""GPU parity: libfhp (CUDA, through the C-ABI) vs the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+from quadrupedal_foothold_planner_b200 import _abi, synth
+from tests.parity import XYZ_TOL, compare_plans
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(fhp, oracle, hmap, params, q, cycles, centroid=True):
+    fhp.set_map(hmap)
+    got = fhp.plan(params, q, cycles, centroid=centroid)
+    exp = oracle.plan(hmap, params, q, cycles, centroid=centroid)
+    return got, exp
+
+
+def test_c1_flat_closed_form(fhp, oracle):
+    """BASELINE config 1: trot, 8 cycles, one query, flat 500x500 @ 0.02 m — known answer."""
+    m, q, N = synth.config_c1()
+    p = _abi.yaml_params()
+    got, exp = _run_both(fhp, oracle, m, p, q, N)
+    assert compare_plans(got, exp, "C1") == 0.0
+    nom, _, st = got
+    assert st[0]["success"] == 1 and st[0]["gait_cycles_succeed"] == 8 and st[0]["n_rows"] == 36
+    f32 = np.float32
+    L = float(f32(0.4387)); W = float(f32(0.175) + f32(0.037) * f32(2)); s = float(f32(0.04))
+    sl = float(f32(0.18)); hs = float(f32(0.18) / f32(2))
+    bx = [0.5 * L - s, -0.5 * L + s, -0.5 * L - s, 0.5 * L + s]
+    by = [-0.5 * W, -0.5 * W, 0.5 * W, 0.5 * W]
+    for g in range(8):
+        for f in range(4):
+            r = nom[0][4 + 4 * g + f]
+            assert abs(r["x"] - (-4 - hs + sl * (g + 1) + bx[f])) < 1e-12
+            assert abs(r["y"] - (by[f] - 0.007 * g)) < 1e-12
+            assert r["z"] == float(f32(0.01)) and r["foot_id"] == f and r["gait_cycle_id"] == g
+
+
+@pytest.mark.parametrize("start", [(0, 0), (123, 277)])
+@pytest.mark.parametrize("mode", [_abi.FHP_SPIRAL_WRAP_CORRECT, _abi.FHP_SPIRAL_FAITHFUL])
+def test_rough_map_trot(fhp, oracle, start, mode):
+    """C3-shaped: rough terrain @0.02 m with NaNs and a wrapped start index; both spiral modes."""
+    m = synth.rough_map(600, 600, 0.02, seed=3, start=start)
+    q = synth.uniform_queries(512, (-5.0, 2.0), (-5.0, 5.0), seed=4)
+    p = _abi.yaml_params(spiral_mode=mode)
+    got, exp = _run_both(fhp, oracle, m, p, q, 12)
+    d = compare_plans(got, exp, f"rough start={start} mode={mode}")
+    assert d <= XYZ_TOL
+    st = got[2]
+    # the case mix must actually exercise the spiral and failures
+    kinds = got[0]["kind"][np.arange(got[0].shape[1])[None, :] < st["n_rows"][:, None]]
+    assert (kinds == _abi.FHP_KIND_CANDIDATE).sum() > 100 and (kinds == _abi.FHP_KIND_DEFAULT).sum() > 100
+
+
+def test_start_index_invariance(fhp):
+    """plan(map with start s) == plan(same content re-laid-out with start 0) in wrap_correct mode."""
+    m = synth.rough_map(500, 420, 0.02, seed=11, start=(77, 301))
+    q = synth.uniform_queries(256, (-4.0, 1.5), (-3.5, 3.5), seed=5)
+    p = _abi.yaml_params()
+    fhp.set_map(m)
+    a = fhp.plan(p, q, 10, centroid=True)
+    fhp.set_map(m.relaid_start0())
+    b = fhp.plan(p, q, 10, centroid=True)
+    for f in ("x", "y", "z", "foot_id", "gait_cycle_id", "kind"):
+        assert np.array_equal(a[0][f], b[0][f]) and np.array_equal(a[1][f], b[1][f])
+    assert np.array_equal(a[2], b[2])
+
+
+def test_c2_walk_stairs_stones(fhp, oracle):
+    """BASELINE config 2 (reduced query count): walk preset, 32 cycles, stairs/stepping stones @0.01 m."""
+    m, q, N = synth.config_c2(n_queries=128)
+    p = _abi.yaml_params(gait=_abi.FHP_GAIT_WALK)
+    got, exp = _run_both(fhp, oracle, m, p, q, N)
+    assert compare_plans(got, exp, "C2") <= XYZ_TOL
+
+
+def test_multi_param_sets(fhp, oracle):
+    """Per-query parameter sets (the C4 sweep shape): step length / skew / gait vary, radii shared."""
+    m = synth.rough_map(500, 500, 0.02, seed=7, start=(5, 9))
+    ps = [_abi.yaml_params(),
+          _abi.yaml_params(step_length=0.12, skew=0.03, rf_first=1),
+          _abi.yaml_params(step_length=0.24, skew=0.06, gait=_abi.FHP_GAIT_WALK),
+          _abi.yaml_params(gait=_abi.FHP_GAIT_CUSTOM, thr_default=0.8, thr_candidate=0.5,
+                           bias=[[0.2, -0.1], [-0.2, -0.1], [-0.25, 0.1], [0.25, 0.1]])]
+    q = synth.uniform_queries(400, (-4.0, 1.0), (-4.0, 4.0), seed=9)
+    q["param_id"] = np.arange(400) % 4
+    got, exp = _run_both(fhp, oracle, m, ps, q, 8)
+    assert compare_plans(got, exp, "multi-param") <= XYZ_TOL
+
+
+def test_edges_border_nan_blocked(fhp, oracle):
+    """Queries at / beyond the map border, an all-NaN map, an all-blocked map, zero cycles, 255 cycles."""
+    p = _abi.yaml_params()
+    m = synth.rough_map(300, 260, 0.02, seed=21, start=(17, 250))
+    hx, hy = 300 * 0.02 / 2, 260 * 0.02 / 2
+    pts = [[-hx + 0.05, 0, 0], [hx - 0.3, 0, 0], [0, hy - 0.05, 0], [0, -hy + 0.02, 0], [hx + 1.0, 0, 0],
+           [-hx - 0.4, hy + 0.3, 0], [hx - 0.9, -hy + 0.13, 0.25], [1e6, -1e6, 0]]
+    q = _abi.make_queries(pts)
+    got, exp = _run_both(fhp, oracle, m, p, q, 6)
+    assert compare_plans(got, exp, "border") <= XYZ_TOL
+    for fill_t, name in ((np.nan, "all-NaN"), (0.0, "all-blocked")):
+        mm = synth.flat_map(200, 200, 0.02)
+        mm.set_layer("traversability", np.full((200, 200), fill_t, np.float32))
+        qq = synth.uniform_queries(64, (-1.0, 0.2), (-1.0, 1.0), seed=3)
+        got, exp = _run_both(fhp, oracle, mm, p, qq, 5)
+        assert compare_plans(got, exp, name) <= XYZ_TOL
+    mm = synth.flat_map(200, 200, 0.02)
+    qq = synth.uniform_queries(8, (-1.0, 0.2), (-1.0, 1.0), seed=3)
+    got, exp = _run_both(fhp, oracle, mm, p, qq, 0)
+    assert compare_plans(got, exp, "zero cycles") == 0.0 and np.all(got[2]["n_rows"] == 4)
+    mm = synth.rough_map(3000, 200, 0.02, seed=2, start=(0, 0))
+    qq = synth.uniform_queries(8, (-29.0, -28.0), (-1.0, 1.0), seed=3)
+    got, exp = _run_both(fhp, oracle, mm, p, qq, 255)
+    assert compare_plans(got, exp, "255 cycles") <= XYZ_TOL
+
+
+def test_fine_grained_members(fhp, oracle):
+    """checkFoothold / checkFootholdUseCentroidMethod / getFootholdMeanHeight / checkDefaultFoothold."""
+    for res, n, kind in ((0.02, 300, "rough"), (0.01, 500, "rough"), (0.01, 1000, "stairs")):
+        if kind == "rough":
+            m = synth.rough_map(n, n, res, seed=31, start=(41, 7))
+        else:
+            m = synth.stairs_stones_map(n, n, res, start=(3, 999))
+        fhp.set_map(m)
+        p = _abi.yaml_params()
+        half = n * res / 2
+        rng = np.random.default_rng(5)
+        c = rng.uniform(-half - 0.1, half + 0.1, size=(4000, 2))
+        rc = c + rng.uniform(-0.06, 0.06, size=c.shape)
+        g_out, g_valid = fhp.check_foothold(p, c, rc)
+        e_out, e_valid = oracle.check_foothold(m, p, c, rc)
+        assert np.array_equal(g_valid, e_valid)
+        for f in ("row", "col", "kind"):
+            assert np.array_equal(g_out[f], e_out[f]), f
+        for f in ("x", "y", "z"):
+            assert np.max(np.abs(g_out[f] - e_out[f])) <= XYZ_TOL, f
+        g_out, g_case = fhp.check_centroid(p, c)
+        e_out, e_case = oracle.check_centroid(m, p, c)
+        assert np.array_equal(g_case, e_case)
+        assert set(np.unique(e_case)) >= ({0, 1, 2, 3, 4, -1} if kind == "stairs" else {0, 1, 3})
+        for f in ("row", "col"):
+            assert np.array_equal(g_out[f], e_out[f]), f
+        for f in ("x", "y", "z"):
+            assert np.max(np.abs(g_out[f] - e_out[f])) <= XYZ_TOL, f
+        assert np.array_equal(fhp.mean_height(p, c), oracle.mean_height(m, p, c))
+        assert np.array_equal(fhp.check_default(p, c), oracle.check_default(m, p, c))
+
+
+def test_errors_are_loud(fhp):
+    from quadrupedal_foothold_planner_b200.planner import Fhp, FhpError
+    p = _abi.yaml_params()
+    q = _abi.make_queries([[0, 0, 0]])
+    fresh = Fhp(0)
+    with pytest.raises(FhpError) as e:
+        fresh.plan(p, q, 4)
+    assert e.value.code == _abi.FHP_ERR_NO_MAP
+    m = synth.flat_map(100, 100, 0.02)
+    del m.layers["elevation"]
+    with pytest.raises(FhpError) as e:
+        fresh.set_map(m)
+    assert e.value.code == _abi.FHP_ERR_MISSING_LAYER
+    fresh.set_map(synth.flat_map(100, 100, 0.02))
+    with pytest.raises(FhpError) as e:
+        fresh.plan(p, q, 256)
+    assert e.value.code == _abi.FHP_ERR_INVALID_ARG
+    with pytest.raises(FhpError) as e:  # window wider than the tables
+        fresh.plan(_abi.yaml_params(search_radius=0.5), q, 2)
+    assert e.value.code == _abi.FHP_ERR_UNSUPPORTED
+    fresh.close()
