@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — footholds/sec of the batched foothold planner (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[2] "C3" — trot gait, 65,536 queries x 16 gait cycles on a
+4000x4000 @ 0.02 m rough-terrain map with a wrapped circular-buffer start index (1234, 2777); one STEP = one
+fhp_plan over the whole batch = 65,536 x 16 x 4 = 4,194,304 footholds (foothold = one (query, cycle, leg) search
+attempt).  Multi-GPU: the map is replicated once by an NCCL broadcast, queries are sharded, every rank
+plans its own 65,536 queries (weak scaling), no collective in the data path.
+
+value        = footholds/s with queries, map and outputs resident in HBM (CUDA events around K launches, max
+               over ranks).
+e2e          = the same metric through the C-ABI call a host makes (fhp_plan on pinned HOST buffers: H2D of the
+               queries, kernel, D2H of all response rows + statuses inside the timed region).
+roofline     = algorithmic bytes per launch / average launch duration vs the measured HBM copy bandwidth.
+cpu_baseline = the CPU oracle (restatement of the reference's CPU path; the reference cannot be built here) on
+               the host cores of this box, bounded sample, rank 0 at N=1 only.
+The oracle is used ONLY in the cpu_baseline leg and in --impl reference; never in the measured product path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from quadrupedal_foothold_planner_b200 import _abi, synth  # noqa: E402
+
+METRIC = "footholds/sec (batched queries)"
+UNIT = "footholds/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_workload(name: str, rank: int, with_map: bool = True):
+    """-> (HostMap, queries, gait_cycles, params list, description).  with_map=False: geometry only (non-root ranks
+    receive the layers by NCCL broadcast)."""
+    if name == "c3":
+        if with_map:
+            m, q, cycles = synth.config_c3(seed_q=4 + 1000 * rank)
+        else:
+            m = _abi.HostMap(4000, 4000, 0.02, (0.0, 0.0), (1234, 2777))
+            q = synth.uniform_queries(65536, (-40 + 1.0, 40 - 4.5), (-40 + 1.0, 40 - 1.0), seed=4 + 1000 * rank)
+            cycles = 16
+        return m, q, cycles, [_abi.yaml_params()], ("C3: trot, 65536 queries x 16 cycles per GPU, 4000x4000 @0.02 m "
+                                                    "rough map, start index (1234,2777)")
+    if name == "c2":
+        m, q, cycles = synth.config_c2()
+        return m, q, cycles, [_abi.yaml_params(gait=_abi.FHP_GAIT_WALK)], \
+            "C2: walk, 1024 queries x 32 cycles, 2000x2000 @0.01 m stairs/stepping stones"
+    if name == "c1":
+        m, q, cycles = synth.config_c1()
+        return m, q, cycles, [_abi.yaml_params()], "C1: trot, 1 query x 8 cycles, flat 500x500 @0.02 m"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = []
+        smax = 0.0
+        reasons = set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = max(smax, float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_footholds_per_s(hmap, params, queries, cycles, n_threads):
+    """The CPU oracle on a bounded sample.  -> (footholds/s, seconds)"""
+    from oracle import binding as ob  # the ONLY product-side use of oracle/: the reported CPU baseline
+    ob.lib()
+    t0 = time.perf_counter()
+    ob.plan(hmap, params, queries, cycles, n_threads=n_threads, centroid=False)
+    dt = time.perf_counter() - t0
+    return len(queries) * cycles * 4 / dt, dt
+
+
+def algorithmic_bytes(hmap, params, queries, cycles, sample=256):
+    """W_in: unique map-cell bytes the reference algorithm reads per foothold (oracle-instrumented, response-only
+    variant = what fhp_plan computes when out_centroid is NULL), averaged over a query sample."""
+    from oracle import binding as ob
+    ob.lib()
+    sel = queries[:: max(1, len(queries) // sample)][:sample]
+    w, sp = ob.touch_bytes(hmap, params, sel, cycles, with_centroid_height=False)
+    n = len(sel) * cycles * 4
+    return float(w.sum()) / n, float(sp.sum()) / n
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle restatement; the reference itself needs ROS/grid_map/
+    Eigen/NLopt and cannot be built here) on this box's host cores, same metric/config, bounded sample per step."""
+    if rank != 0:
+        return
+    hmap, queries, cycles, params, desc = make_workload(args.workload, 0)
+    cores = os.cpu_count() or 1
+    sample_q = min(len(queries), args.ref_sample)
+    q = queries[:sample_q]
+    for _ in range(args.warmup):
+        oracle_footholds_per_s(hmap, params, q[: max(64, sample_q // 8)], cycles, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_footholds_per_s(hmap, params, q, cycles, cores)
+    dt = time.perf_counter() - t0
+    fh = sample_q * cycles * 4 * args.steps
+    v = fh / dt
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": f"{sample_q} of {len(queries)} queries per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_q} queries x {cycles} cycles per step, all host threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1"])
+    ap.add_argument("--ref-sample", type=int, default=16384, help="queries per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="queries of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)  # profiling runs pass --warmup 1; the driver passes >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from quadrupedal_foothold_planner_b200.planner import Fhp
+    from quadrupedal_foothold_planner_b200 import dist as fdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: libfhp has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- workload: rank 0 builds the map, NCCL replicates it; every rank owns its own query shard
+    t_gen = time.perf_counter()
+    hmap, queries, cycles, params, desc = make_workload(args.workload, rank, with_map=(rank == 0 or args.workload != "c3"))
+    t_gen = time.perf_counter() - t_gen
+    fhp = Fhp(local_rank)
+    names = ["traversability", "elevation"]
+    bcast_ms = None
+    if world > 1:
+        layers, bcast_ms = fdist.replicate_map(hmap if rank == 0 else None, hmap, names, local_rank)
+    else:
+        layers = [torch.from_numpy(np.ascontiguousarray(hmap.layers[n].T)).cuda() for n in names]  # (cols,rows) C == col-major
+    fhp.set_map_device(hmap, names, [t.data_ptr() for t in layers], keepalive=layers)
+
+    nq = len(queries)
+    R = _abi.rows_per_query(cycles)
+    parr, npar = Fhp._params_array(params)
+    footholds_per_step = nq * cycles * 4
+
+    # resident buffers (value) and pinned host buffers (e2e)
+    q_np = np.ascontiguousarray(queries)
+    d_q = torch.from_numpy(q_np.view(np.uint8)).cuda()
+    d_nom = torch.empty(nq * R * _abi.FOOTHOLD_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_st = torch.empty(nq * _abi.STATUS_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    h_q = torch.from_numpy(q_np.view(np.uint8).copy()).pin_memory()
+    h_nom = torch.empty(nq * R * _abi.FOOTHOLD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_st = torch.empty(nq * _abi.STATUS_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        fhp.plan_device(parr, npar, d_q, nq, cycles, d_nom, None, d_st, stream=stream.cuda_stream)
+
+    def step_e2e():
+        fhp.plan_raw(parr, npar, h_q, nq, cycles, h_nom, None, h_st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_resident()
+    fhp.synchronize()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = fhp.kernel_launches()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = fhp.kernel_launches() - launches0
+    fhp.synchronize()
+    ms_per_step = ms_total / args.steps
+    total_fh = sum_over_ranks(float(footholds_per_step))
+    value = total_fh / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-facing C-ABI (pinned host buffers, copies inside the timed region)
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop()
+    e2e_value = total_fh / (e2e_s / e2e_steps)
+
+    # results sanity (and the rows-written count for the algorithmic output bytes)
+    st = h_st.numpy().view(_abi.STATUS_DTYPE)
+    if int(st["reserved"].max()) != 0:
+        raise SystemExit("kernel reported error bits")
+    rows_written = float(st["n_rows"].sum())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        w_in, spiral_frac = algorithmic_bytes(hmap, params, queries, cycles)
+        w_out = rows_written * _abi.FOOTHOLD_DTYPE.itemsize / footholds_per_step + 8.0 / (cycles * 4)
+        w = w_in + w_out
+        # per-GPU launch: footholds_per_step of THIS rank / average launch duration
+        achieved = footholds_per_step * w / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "queries_per_gpu": nq, "gait_cycles": cycles,
+                       "footholds_per_step_per_gpu": footholds_per_step,
+                       "l2": "no explicit flush: per-step working set (map 128 MB + response rows %d MB) exceeds the "
+                             "126 MB L2" % (nq * R * 40 // 2 ** 20),
+                       "map_generation_s": round(t_gen, 2), "map_broadcast_ms": bcast_ms},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_q.numel()),
+                    "d2h_bytes_per_step": int(h_nom.numel() + h_st.numel()), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_foothold": {"read_unique_cells": w_in, "rows_written": w_out},
+                         "spiral_taken_frac": spiral_frac, "kernel": "plan_kernel<false>",
+                         "avg_launch_ms": ms_per_step},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sq = queries[: min(nq, args.cpu_sample)]
+            v, dt = oracle_footholds_per_s(hmap, params, sq, cycles, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{len(sq)} of {nq} queries x {cycles} cycles, {dt:.1f} s, all host threads"}
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

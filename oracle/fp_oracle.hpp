@@ -75,6 +75,9 @@ class Planner {
   // instrumentation: when countTouched is set, globalFootholdPlan accumulates the number of UNIQUE
   // map cells (any layer) read per (cycle, leg) foothold = centroid task + nominal task of that leg.
   bool countTouched = false;
+  // response-only variant: skip the centroid chain's height lookups (their z never reaches the
+  // plan_global_footholds response, FP.cpp:1588) — used only to count the algorithmic bytes of that variant.
+  bool centroidHeight = true;
   int64_t touchedCells = 0;
   int64_t spiralTaken = 0;  // footholds whose default-disc test failed (spiral search executed)
 
@@ -320,7 +323,7 @@ class Planner {
 
     if (wholeRegionValid) {  // :1684-1689
       if (caseOut) *caseOut = 0;
-      resultFoothold.z = getFootholdMeanHeight(gridmap, pos, p.footRadius, p.h);
+      if (centroidHeight) resultFoothold.z = getFootholdMeanHeight(gridmap, pos, p.footRadius, p.h);
       resultFoothold.x = pos.x;
       resultFoothold.y = pos.y;
     } else {
@@ -376,7 +379,7 @@ class Planner {
         // :1816 / :1917 / :1982 — a failed getPosition only logs; the (uninitialised upstream, zero here)
         // position is still used.  newIndex is always inside the window for the three cases above.
         map.getPosition(newIndex, newRegionCentroid);
-        resultFoothold.z = getFootholdMeanHeight(gridmap, newRegionCentroid, p.footRadius, p.h);
+        if (centroidHeight) resultFoothold.z = getFootholdMeanHeight(gridmap, newRegionCentroid, p.footRadius, p.h);
         resultFoothold.x = newRegionCentroid.x;
         resultFoothold.y = newRegionCentroid.y;
       } else if (caseOut) {

@@ -131,7 +131,8 @@ int oracle_plan(const fhp_map_desc* desc, const float* const* layers, const fhp_
 // the number of footholds whose spiral search ran.
 int oracle_plan_touch_bytes(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params,
                             int32_t n_params, const fhp_query* queries, int64_t n_queries, int32_t gait_cycles,
-                            int64_t* unique_cell_bytes_per_query, int64_t* spiral_taken_per_query) {
+                            int64_t* unique_cell_bytes_per_query, int64_t* spiral_taken_per_query,
+                            int32_t with_centroid_height) {
   if (!desc || !layers || !params || !queries || !unique_cell_bytes_per_query) return FHP_ERR_INVALID_ARG;
   gm::GridMap map = make_map(desc, layers);
   if (!map.exists("traversability") || !map.exists("elevation")) return FHP_ERR_MISSING_LAYER;
@@ -139,6 +140,7 @@ int oracle_plan_touch_bytes(const fhp_map_desc* desc, const float* const* layers
     if (queries[q].param_id < 0 || queries[q].param_id >= n_params) return FHP_ERR_INVALID_ARG;
     ref::Planner pl = make_planner(params[queries[q].param_id], queries[q]);
     pl.countTouched = true;
+    pl.centroidHeight = with_centroid_height != 0;
     pl.globalFootholdPlan(map, static_cast<uint8_t>(gait_cycles));
     unique_cell_bytes_per_query[q] = pl.touchedCells * 4;
     if (spiral_taken_per_query) spiral_taken_per_query[q] = pl.spiralTaken;
