@@ -97,6 +97,12 @@ inline bool getPositionFromIndex(Vec2& position, const Idx2& index, const Vec2& 
   position.y = (mapPosition.y + offset.y) + resolution * vy;
   return true;
 }
+// double -> int of a NaN / out-of-int-range value is UB upstream (x86 cvttsd2si yields INT_MIN, i.e. "far out of
+// range").  Policy (shared with the CUDA path): every such index becomes -2^30.
+inline int toIndex(double v) {
+  if (!(std::fabs(v) < 1073741824.0)) return -1073741824;
+  return static_cast<int>(v);
+}
 // getIndexFromPosition: indexVector = (position - offset - mapPosition)/resolution; index = (int)(-indexVector)
 // -> buffer index; returns false (index still written) when the position is outside the map.
 inline bool getIndexFromPosition(Idx2& index, const Vec2& position, const Vec2& mapLength, const Vec2& mapPosition,
@@ -104,7 +110,7 @@ inline bool getIndexFromPosition(Idx2& index, const Vec2& position, const Vec2& 
   Vec2 offset = getVectorToOrigin(mapLength);
   double ivx = ((position.x - offset.x) - mapPosition.x) / resolution;
   double ivy = ((position.y - offset.y) - mapPosition.y) / resolution;
-  Idx2 u{static_cast<int>(-ivx), static_cast<int>(-ivy)};
+  Idx2 u{toIndex(-ivx), toIndex(-ivy)};
   index = getBufferIndexFromIndex(u, bufferSize, bufferStartIndex);
   return checkIfPositionWithinMap(position, mapLength, mapPosition);
 }

@@ -219,7 +219,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
   G.pack = G.WIN <= 8 ? 4 : (G.WIN <= 16 ? 2 : 1);
   G.rpShift = G.pack == 4 ? 3 : (G.pack == 2 ? 4 : 5);
   G.nIter = (G.WIN + G.pack - 1) / G.pack;
-  G.stride = (3 * G.nIter) | 1;
+  G.stride = 4 * G.nIter;
 
   // ---- SpiralIterator order: centre, then ring d = 1..nRings generated by the upstream walk and consumed from
   // the BACK of the ring vector (pointsRing_.back()/pop_back()).
@@ -247,6 +247,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
   if (lastTwo < 0) lastTwo = static_cast<int>(table.size());
   if (table.size() > static_cast<size_t>(kMaxCand)) return fail(ctx, FHP_ERR_UNSUPPORTED, "spiral table overflow");
   G.nCand = static_cast<int>(table.size());
+  G.spiralWords = ((G.nCand * 2 + 15) / 16) * 4;
   G.lastTwoStart = lastTwo;
   for (int k = 0; k < G.nCand; ++k) {
     G.spiral[k][0] = static_cast<int8_t>(table[k].first);

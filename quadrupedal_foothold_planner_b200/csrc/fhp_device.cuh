@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 #include "fhp_types.h"
 
@@ -39,6 +40,9 @@ __device__ __forceinline__ double bound_axis(double p, double len, double mp, do
 // getIndexFromPosition without the start-index wrap: (int)(-(((p - 0.5*len) - mapPos)/res))
 __device__ __forceinline__ int raw_index_axis(double p, double half, double mp, double res) {
   double iv = ((p - half) - mp) / res;
+  // (int) of a NaN / out-of-int-range double is UB upstream (x86 cvttsd2si yields INT_MIN).  Policy shared with the
+  // oracle: every such index becomes -2^30 — far outside any map, and index +- window never overflows.
+  if (!(fabs(iv) < 1073741824.0)) return -1073741824;
   return static_cast<int>(-iv);
 }
 // checkIfPositionWithinMap for one axis
@@ -81,30 +85,36 @@ struct Planes {  // view of one query's staged window in shared memory
   const uint32_t* w;
   int pack, rpShift;
   __device__ __forceinline__ uint32_t col(int plane, int b) const {  // bits over window rows a for column b
-    if (pack == 1) return w[b * 3 + plane];
+    if (pack == 1) return w[b * 4 + plane];
     int k, sh;
     if (pack == 2) {
       k = b >> 1;
       sh = (b & 1) << 4;
-      return (w[k * 3 + plane] >> sh) & 0xffffu;
+      return (w[k * 4 + plane] >> sh) & 0xffffu;
     }
     k = b >> 2;
     sh = (b & 3) << 3;
-    return (w[k * 3 + plane] >> sh) & 0xffu;
+    return (w[k * 4 + plane] >> sh) & 0xffu;
   }
   __device__ __forceinline__ bool bit(int plane, int a, int b) const { return (col(plane, b) >> a) & 1u; }
 };
 enum { PL_D = 0, PL_C = 1, PL_F = 2 };
 
 // Warp-cooperative staging: for every lane j with has_window, read the WIN x WIN traversability window whose
-// unwrapped origin is (w0,w1) of lane j and store its D/C/F bit-planes at smem[j*stride ...].
+// unwrapped origin is (w0,w1) of lane j and store its D/C/F bit-planes at smem[j*stride ...] (4 words per load
+// iteration: D, C, F, pad — one 16-byte store by lane 0).
 // Cells outside the map read as NaN (=> D=C=F=0), which is exactly "not visited" for every iterator.
+// Interior windows that do not cross the circular-buffer seam (the common case) take a path whose per-iteration
+// work is one pointer increment, one coalesced load, three compares and three ballots; bits of rows/columns
+// beyond WIN then hold real neighbouring cells, which no consumer ever reads.
 __device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, uint32_t* smemWarp, int lane,
                                               bool has_window, int w0, int w1, float thrD, float thrC) {
   const unsigned act = __ballot_sync(kFull, has_window);
   const int RP = 1 << G.rpShift;
   const int a = lane & (RP - 1);
   const int h = lane >> G.rpShift;
+  const int colsCovered = G.nIter * G.pack;
+  const float inf = __int_as_float(0x7f800000);
   __syncwarp();
   for (unsigned m = act; m; m &= m - 1) {
     const int j = __ffs(m) - 1;
@@ -112,44 +122,73 @@ __device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, 
     const int jw1 = __shfl_sync(kFull, w1, j);
     const float tD = __shfl_sync(kFull, thrD, j);
     const float tC = __shfl_sync(kFull, thrC, j);
-    const int u0 = jw0 + a;
-    const bool in0 = (a < G.WIN) && u0 >= 0 && u0 < M.rows;
-    const int b0 = wrap_add(u0, M.start0, M.rows);
-    uint32_t myD = 0, myC = 0, myF = 0;
-    for (int k = 0; k < G.nIter; ++k) {
-      const int b = k * G.pack + h;
-      const int u1 = jw1 + b;
-      const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
-      const int b1 = wrap_add(u1, M.start1, M.cols);
-      float v = __int_as_float(0x7fc00000);
-      if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
-      const uint32_t bD = __ballot_sync(kFull, v < tD);
-      const uint32_t bC = __ballot_sync(kFull, v < tC);
-      const uint32_t bF = __ballot_sync(kFull, fabsf(v) < __int_as_float(0x7f800000));
-      if (lane == k) {
-        myD = bD;
-        myC = bC;
-        myF = bF;
+    uint4* dst = reinterpret_cast<uint4*>(smemWarp + j * G.stride);
+    int bb0 = jw0 + M.start0, bb1 = jw1 + M.start1;
+    if (bb0 >= M.rows) bb0 -= M.rows;
+    if (bb1 >= M.cols) bb1 -= M.cols;
+    const bool fast = jw0 >= 0 && jw1 >= 0 && jw0 <= M.rows - RP && jw1 <= M.cols - colsCovered &&
+                      bb0 <= M.rows - RP && bb1 <= M.cols - colsCovered;
+    if (fast) {
+      const float* p = M.trav + static_cast<size_t>(bb1 + h) * M.rows + (bb0 + a);
+      const size_t step = static_cast<size_t>(G.pack) * M.rows;
+#ifdef FHP_DEBUG
+      {
+        long long off0 = static_cast<long long>(bb1 + h) * M.rows + (bb0 + a);
+        long long offN = off0 + static_cast<long long>(G.nIter - 1) * static_cast<long long>(step);
+        if (off0 < 0 || offN >= static_cast<long long>(M.rows) * M.cols)
+          printf("BAD fast: lane %d j %d jw0 %d jw1 %d bb0 %d bb1 %d a %d h %d RP %d colsCov %d rows %d cols %d off0 %lld offN %lld trav %p\n",
+                 lane, j, jw0, jw1, bb0, bb1, a, h, RP, colsCovered, M.rows, M.cols, off0, offN, (const void*)M.trav);
       }
-    }
-    if (lane < G.nIter) {
-      uint32_t* dst = smemWarp + j * G.stride + lane * 3;
-      dst[0] = myD;
-      dst[1] = myC;
-      dst[2] = myF;
+#endif
+      for (int k = 0; k < G.nIter; ++k) {
+        const float v = __ldg(p);
+        p += step;
+        const uint32_t bD = __ballot_sync(kFull, v < tD);
+        const uint32_t bC = __ballot_sync(kFull, v < tC);
+        const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
+        if (lane == 0) dst[k] = make_uint4(bD, bC, bF, 0u);
+      }
+    } else {
+      const int u0 = jw0 + a;
+      const bool in0 = (a < G.WIN) && u0 >= 0 && u0 < M.rows;
+      const int b0 = wrap_add(u0, M.start0, M.rows);
+      for (int k = 0; k < G.nIter; ++k) {
+        const int b = k * G.pack + h;
+        const int u1 = jw1 + b;
+        const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
+        const int b1 = wrap_add(u1, M.start1, M.cols);
+        float v = __int_as_float(0x7fc00000);
+        if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
+        const uint32_t bD = __ballot_sync(kFull, v < tD);
+        const uint32_t bC = __ballot_sync(kFull, v < tC);
+        const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
+        if (lane == 0) dst[k] = make_uint4(bD, bC, bF, 0u);
+      }
     }
   }
   __syncwarp();
 }
 
+// CircleIterator::findSubmapParameters: bounded corners -> unwrapped index window [tl, br] of the foot disc
+struct DiscWin {
+  int tl0, tl1, br0, br1;
+};
+__device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, double cy, double r) {
+  DiscWin d;
+  const double tlx = bound_axis(cx + r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + r, M.leny, M.posy, M.halfy);
+  const double brx = bound_axis(cx - r, M.lenx, M.posx, M.halfx), bry = bound_axis(cy - r, M.leny, M.posy, M.halfy);
+  d.tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res);
+  d.tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res);
+  d.br0 = raw_index_axis(brx, M.halfx, M.posx, M.res);
+  d.br1 = raw_index_axis(bry, M.halfy, M.posy, M.res);
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------------ a9 mean height
 // FootholdPlanner::getFootholdMeanHeight (FP.cpp:2520-2554) over grid_map::CircleIterator (row-major over the
 // bounded window in unwrapped index space, cells with squared distance <= r^2).
-__device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy) {
-  const double tlx = bound_axis(cx + P.r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + P.r, M.leny, M.posy, M.halfy);
-  const double brx = bound_axis(cx - P.r, M.lenx, M.posx, M.halfx), bry = bound_axis(cy - P.r, M.leny, M.posy, M.halfy);
-  const int tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res), tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res);
-  const int br0 = raw_index_axis(brx, M.halfx, M.posx, M.res), br1 = raw_index_axis(bry, M.halfy, M.posy, M.res);
+__device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw) {
+  const int tl0 = dw.tl0, tl1 = dw.tl1, br0 = dw.br0, br1 = dw.br1;
   float iHeight = 0.0f, meanHeight = 0.0f;
   int i = 0;
   for (int u0 = tl0; u0 <= br0; ++u0) {
@@ -172,6 +211,9 @@ __device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, d
     meanHeight = iHeight;
   }
   return static_cast<float>(static_cast<double>(meanHeight) + P.h);
+}
+__device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy) {
+  return mean_height(M, P, cx, cy, disc_window(M, cx, cy, P.r));
 }
 
 // ------------------------------------------------------------------------------------------------ a4 centroid
@@ -286,9 +328,77 @@ struct NominalOut {
   int row, col;  // buffer index of the chosen cell (or of the centre's cell), (-1,-1) outside the map
 };
 
-// One foot-disc candidate evaluated straight from global memory (used only for faithful-mode candidates that
-// wrap to the far side of the circular buffer): checkCirclePolygonFoothold (FP.cpp:2117-2163).
-__device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, const ParDev& P, int q0, int q1, double xlo,
+// Polygon::isInside for the reference's axis-aligned rectangle (getSearchPolygon, FP.cpp:2496-2517) reduces to the
+// half-open box  xlo <= x < xhi  &&  ylo <= y < yhi  on the cell centre.
+struct Box {
+  double xlo, xhi, ylo, yhi;
+};
+__device__ __forceinline__ Box search_box(const ParDev& P, double rx, double ry) {
+  Box b;
+  b.xhi = rx + P.R;
+  b.xlo = rx - P.R;
+  b.yhi = ry + P.halfR;
+  b.ylo = ry - P.halfR;
+  return b;
+}
+
+// FootholdPlanner::checkDefaultFoothold (FP.cpp:2039-2082): CircleIterator(centre, footRadius) on the staged planes.
+__device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl, int w0,
+                                             int w1, double cx, double cy, const DiscWin& dw, unsigned& err) {
+  int visited = 0;
+  bool below = false;
+  for (int u0 = dw.tl0; u0 <= dw.br0; ++u0) {
+    const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+    const double dx2 = dx * dx;
+    for (int u1 = dw.tl1; u1 <= dw.br1; ++u1) {
+      const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+      if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
+      ++visited;
+      const int a = u0 - w0, b = u1 - w1;
+      if (a < 0 || b < 0 || a >= G.WIN || b >= G.WIN) {
+        err |= kErrWindow;
+        continue;
+      }
+      const uint32_t bits = pl.col(PL_D, b) & pl.col(PL_F, b);
+      below |= (bits >> a) & 1u;
+    }
+  }
+  return (visited > 0) && !below;
+}
+
+// Which window rows / columns have their cell centre inside the box, with the reference's position arithmetic.
+__device__ __forceinline__ void box_masks(const MapDev& M, const GeoDev& G, const Box& bx, int w0, int w1,
+                                          uint32_t& rowsBox, uint32_t& colsBox) {
+  rowsBox = 0;
+  colsBox = 0;
+  for (int a = 0; a < G.WIN; ++a) {
+    const double X = pos_axis(M.fcx, M.res, w0 + a);
+    if (X >= bx.xlo && X < bx.xhi) rowsBox |= 1u << a;
+    const double Y = pos_axis(M.fcy, M.res, w1 + a);
+    if (Y >= bx.ylo && Y < bx.yhi) colsBox |= 1u << a;
+  }
+}
+
+// checkCirclePolygonFoothold (FP.cpp:2117-2163) for the candidate at window coordinates (qa,qb), on the planes:
+// every finite cell of the foot disc must be >= candidateFootholdThreshold and inside the box.
+__device__ __forceinline__ bool candidate_on_planes(const GeoDev& G, const Planes& pl, int qa, int qb, uint32_t rowsBox,
+                                                    uint32_t colsBox) {
+  bool good = true;
+  for (int s = 0; s < G.nSten && good; ++s) {
+    const int a = qa + G.sten[s][0], b = qb + G.sten[s][1];
+    // a,b are inside the window by construction (|d| <= nRings, |sten| <= ra); cells outside the map have
+    // F = 0 and are skipped like the iterator skips them
+    const uint32_t F = pl.col(PL_F, b), C = pl.col(PL_C, b);
+    const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
+    const uint32_t bad = F & (C | ~box);
+    good = !((bad >> a) & 1u);
+  }
+  return good;
+}
+
+// One candidate evaluated straight from global memory (faithful-mode candidates that wrap to the far side of the
+// circular buffer): checkCirclePolygonFoothold (FP.cpp:2117-2163).
+__device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, float thrC, int q0, int q1, double xlo,
                                             double xhi, double ylo, double yhi) {
   for (int s = 0; s < G.nSten; ++s) {
     const int u0 = q0 + G.sten[s][0], u1 = q1 + G.sten[s][1];
@@ -297,130 +407,153 @@ __device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, co
     if (!(fabsf(v) < __int_as_float(0x7f800000))) continue;
     const double X = pos_axis(M.fcx, M.res, u0), Y = pos_axis(M.fcy, M.res, u1);
     const bool inside = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
-    if (v < P.thrC || !inside) return false;
+    if (v < thrC || !inside) return false;
   }
   return true;
 }
 
+__device__ __forceinline__ void spiral_entry(const uint16_t* sSpiral, int k, int& d0, int& d1) {
+  const unsigned e = sSpiral[k];
+  d0 = static_cast<int>(static_cast<int8_t>(e & 0xffu));
+  d1 = static_cast<int>(static_cast<int8_t>(e >> 8));
+}
+
+// checkCandidateFoothold (FP.cpp:2085-2114) over grid_map::SpiralIterator — warp-cooperative rank scan.
+// For every lane j with `need`, the 32 lanes test candidates rank base..base+31 of query j at once (in-range
+// check, last-two-rings distance filter, foot-disc/polygon test on j's staged planes) and the first set bit of the
+// ballot is the first valid cell in spiral order; the scan stops at the first 32-block that has one.
+// Handles wrap_correct mode, and faithful mode when the start index is (0,0) (identical there).
+__device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
+                                                 const uint32_t* smemWarp, int lane, bool need, int uc0, int uc1,
+                                                 double cx, double cy, double R2, uint32_t rowsBox, uint32_t colsBox,
+                                                 bool& found, int& fq0, int& fq1) {
+  const unsigned needMask = __ballot_sync(kFull, need);
+  for (unsigned m = needMask; m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    const int juc0 = __shfl_sync(kFull, uc0, j), juc1 = __shfl_sync(kFull, uc1, j);
+    const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
+    const Planes pj{smemWarp + j * G.stride, G.pack, G.rpShift};
+    bool haveC = false;
+    double jcx = 0, jcy = 0, jR2 = 0;
+    for (int base = 0; base < G.nCand; base += 32) {
+      const int k = base + lane;
+      bool cand = k < G.nCand;
+      int d0, d1;
+      spiral_entry(sSpiral, cand ? k : 0, d0, d1);
+      const int q0 = juc0 + d0, q1 = juc1 + d1;
+      cand = cand && in_map(M, q0, q1);                // checkIfIndexInRange(pointInMap)
+      if (base + 32 > G.lastTwoStart) {                // rings nRings-1, nRings: distance filter (uniform branch)
+        if (!haveC) {
+          jcx = __shfl_sync(kFull, cx, j);
+          jcy = __shfl_sync(kFull, cy, j);
+          jR2 = __shfl_sync(kFull, R2, j);
+          haveC = true;
+        }
+        if (cand && k >= G.lastTwoStart) {
+          const double dx = pos_axis(M.fcx, M.res, q0) - jcx, dy = pos_axis(M.fcy, M.res, q1) - jcy;
+          cand = (dx * dx + dy * dy <= jR2);
+        }
+      }
+      const bool good = cand && candidate_on_planes(G, pj, d0 + G.HW, d1 + G.HW, jrows, jcols);
+      const unsigned g = __ballot_sync(kFull, good);
+      if (g) {
+        const int src = __ffs(g) - 1;
+        const int wq0 = __shfl_sync(kFull, q0, src), wq1 = __shfl_sync(kFull, q1, src);
+        if (lane == j) {
+          found = true;
+          fq0 = wq0;
+          fq1 = wq1;
+        }
+        break;
+      }
+    }
+  }
+}
+
+// The same scan for FHP_SPIRAL_FAITHFUL with a non-zero start index (bug-compatible with upstream):
+// the centre index is the BUFFER index, ring neighbours are taken in buffer space without wrapping, and the
+// distance filter evaluates positions as if the start index were 0.  Per-lane scalar loop (compatibility path).
+__device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
+                                                  const Planes& pl, float thrC, int uc0, int uc1, double cx, double cy,
+                                                  double R2, const Box& bx, uint32_t rowsBox, uint32_t colsBox,
+                                                  bool& found, int& fq0, int& fq1) {
+  int cb0 = uc0 + M.start0, cb1 = uc1 + M.start1;  // getBufferIndexFromIndex + wrapIndexToRange
+  if (cb0 < 0) cb0 += ((-cb0 / M.rows) + 1) * M.rows;
+  cb0 %= M.rows;
+  if (cb1 < 0) cb1 += ((-cb1 / M.cols) + 1) * M.cols;
+  cb1 %= M.cols;
+  for (int k = 0; k < G.nCand; ++k) {
+    int d0, d1;
+    spiral_entry(sSpiral, k, d0, d1);
+    const int bi0 = cb0 + d0, bi1 = cb1 + d1;  // buffer index, NOT wrapped
+    if (!in_map(M, bi0, bi1)) continue;
+    if (k >= G.lastTwoStart) {  // upstream evaluates the position as if the start index were 0
+      const double dx = pos_axis(M.fcx, M.res, bi0) - cx, dy = pos_axis(M.fcy, M.res, bi1) - cy;
+      if (!(dx * dx + dy * dy <= R2)) continue;
+    }
+    int q0 = bi0 - M.start0, q1 = bi1 - M.start1;  // getIndexFromBufferIndex
+    if (q0 < 0) q0 += M.rows;
+    if (q1 < 0) q1 += M.cols;
+    const bool far = (q0 != uc0 + d0) || (q1 != uc1 + d1);
+    const bool good = far ? candidate_slow(M, G, thrC, q0, q1, bx.xlo, bx.xhi, bx.ylo, bx.yhi)
+                          : candidate_on_planes(G, pl, d0 + G.HW, d1 + G.HW, rowsBox, colsBox);
+    if (good) {
+      found = true;
+      fq0 = q0;
+      fq1 = q1;
+      return;
+    }
+  }
+}
+
 // FootholdPlanner::checkFoothold (FP.cpp:2001-2036) = checkDefaultFoothold (:2039-2082), then
 // checkCandidateFoothold (:2085-2114) over grid_map::SpiralIterator with checkCirclePolygonFoothold (:2117-2163).
-// (cx,cy): search centre; (rx,ry): centre of the search rectangle (getSearchPolygon, FP.cpp:2496-2517);
-// (uc0,uc1): raw unwrapped index of the centre; (w0,w1) = (uc0-HW, uc1-HW): staged window origin.
+// WARP-COLLECTIVE: every lane of the warp must call it (inactive lanes pass active = false).
+// (cx,cy): search centre; (rx,ry): centre of the search rectangle; (uc0,uc1): raw unwrapped index of the centre;
+// the staged window origin is (uc0-HW, uc1-HW).
 template <bool DEFAULT_ONLY>
-__device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl,
-                                                   int uc0, int uc1, double cx, double cy, double rx, double ry,
-                                                   unsigned& err) {
+__device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P,
+                                                   const uint16_t* sSpiral, const uint32_t* smemWarp, int lane,
+                                                   bool active, int uc0, int uc1, double cx, double cy, double rx,
+                                                   double ry, const DiscWin& dw, unsigned& err) {
   NominalOut o;
   o.x = cx;  // FP.cpp:2016-2017
   o.y = cy;
   o.ok = false;
   o.kind = FHP_KIND_DEFAULT;
+  o.row = o.col = -1;
   const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
-  const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
-                             in_map(M, uc0, uc1);
-  o.row = centre_in_map ? wrap_add(uc0, M.start0, M.rows) : -1;
-  o.col = centre_in_map ? wrap_add(uc1, M.start1, M.cols) : -1;
-
-  // ---- checkDefaultFoothold: CircleIterator(centre, footRadius)
-  {
-    const double tlx = bound_axis(cx + P.r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + P.r, M.leny, M.posy, M.halfy);
-    const double brx = bound_axis(cx - P.r, M.lenx, M.posx, M.halfx), bry = bound_axis(cy - P.r, M.leny, M.posy, M.halfy);
-    const int tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res), tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res);
-    const int br0 = raw_index_axis(brx, M.halfx, M.posx, M.res), br1 = raw_index_axis(bry, M.halfy, M.posy, M.res);
-    int visited = 0;
-    bool below = false;
-    for (int u0 = tl0; u0 <= br0; ++u0) {
-      const double dx = pos_axis(M.fcx, M.res, u0) - cx;
-      const double dx2 = dx * dx;
-      for (int u1 = tl1; u1 <= br1; ++u1) {
-        const double dy = pos_axis(M.fcy, M.res, u1) - cy;
-        if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
-        ++visited;
-        const int a = u0 - w0, b = u1 - w1;
-        if (a < 0 || b < 0 || a >= G.WIN || b >= G.WIN) {
-          err |= kErrWindow;
-          continue;
-        }
-        const uint32_t bits = pl.col(PL_D, b) & pl.col(PL_F, b);
-        below |= (bits >> a) & 1u;
-      }
-    }
-    o.ok = (visited > 0) && !below;
+  const Planes pl{smemWarp + lane * G.stride, G.pack, G.rpShift};
+  if (active) {
+    const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
+                               in_map(M, uc0, uc1);
+    o.row = centre_in_map ? wrap_add(uc0, M.start0, M.rows) : -1;
+    o.col = centre_in_map ? wrap_add(uc1, M.start1, M.cols) : -1;
+    o.ok = default_eval(M, G, P, pl, w0, w1, cx, cy, dw, err);
   }
-  if (o.ok || DEFAULT_ONLY) return o;
+  if (DEFAULT_ONLY) return o;
 
-  // ---- checkCandidateFoothold: SpiralIterator(centre, searchRadius)
-  o.kind = FHP_KIND_CANDIDATE;
-  const double xhi = rx + P.R, xlo = rx - P.R, yhi = ry + P.halfR, ylo = ry - P.halfR;
-  // Polygon::isInside for the axis-aligned rectangle == half-open box on the cell centre;
-  // evaluate it once per window row / column with the reference's position arithmetic.
-  uint32_t rowsBox = 0, colsBox = 0;
-  for (int a = 0; a < G.WIN; ++a) {
-    const double X = pos_axis(M.fcx, M.res, w0 + a);
-    if (X >= xlo && X < xhi) rowsBox |= 1u << a;
-    const double Y = pos_axis(M.fcy, M.res, w1 + a);
-    if (Y >= ylo && Y < yhi) colsBox |= 1u << a;
-  }
+  const bool need = active && !o.ok;
   const bool faithful = (P.spiralMode == FHP_SPIRAL_FAITHFUL) && !(M.start0 == 0 && M.start1 == 0);
-  // faithful: upstream's centre index is the BUFFER index (getIndex), neighbours are taken in buffer space
-  int cb0 = uc0, cb1 = uc1;
-  if (faithful) {
-    cb0 = uc0 + M.start0;
-    cb1 = uc1 + M.start1;
-    // wrapIndexToRange
-    if (cb0 < 0) cb0 += ((-cb0 / M.rows) + 1) * M.rows;
-    cb0 %= M.rows;
-    if (cb1 < 0) cb1 += ((-cb1 / M.cols) + 1) * M.cols;
-    cb1 %= M.cols;
+  uint32_t rowsBox = 0, colsBox = 0;
+  Box bx = {0, 0, 0, 0};
+  if (need) {
+    o.kind = FHP_KIND_CANDIDATE;
+    bx = search_box(P, rx, ry);
+    box_masks(M, G, bx, w0, w1, rowsBox, colsBox);
   }
-  for (int k = 0; k < G.nCand; ++k) {
-    const int d0 = G.spiral[k][0], d1 = G.spiral[k][1];
-    int q0, q1;  // unwrapped index of the candidate cell
-    bool far = false;
-    if (!faithful) {
-      q0 = uc0 + d0;
-      q1 = uc1 + d1;
-      if (!in_map(M, q0, q1)) continue;  // checkIfIndexInRange(pointInMap)
-      if (k >= G.lastTwoStart) {         // rings nRings-1, nRings: distance filter on the cell centre
-        const double dx = pos_axis(M.fcx, M.res, q0) - cx, dy = pos_axis(M.fcy, M.res, q1) - cy;
-        if (!(dx * dx + dy * dy <= P.R2)) continue;
-      }
-    } else {
-      const int bi0 = cb0 + d0, bi1 = cb1 + d1;  // buffer index, NOT wrapped
-      if (!in_map(M, bi0, bi1)) continue;
-      if (k >= G.lastTwoStart) {  // upstream evaluates the position as if the start index were 0
-        const double dx = pos_axis(M.fcx, M.res, bi0) - cx, dy = pos_axis(M.fcy, M.res, bi1) - cy;
-        if (!(dx * dx + dy * dy <= P.R2)) continue;
-      }
-      q0 = bi0 - M.start0;
-      if (q0 < 0) q0 += M.rows;
-      q1 = bi1 - M.start1;
-      if (q1 < 0) q1 += M.cols;
-      far = (q0 != uc0 + d0) || (q1 != uc1 + d1);
-    }
-    bool good = true;
-    if (far) {
-      good = candidate_slow(M, G, P, q0, q1, xlo, xhi, ylo, yhi);
-    } else {
-      const int qa = d0 + G.HW, qb = d1 + G.HW;  // window coordinates of the candidate
-      for (int s = 0; s < G.nSten && good; ++s) {
-        const int a = qa + G.sten[s][0], b = qb + G.sten[s][1];
-        // a,b are inside the window by construction (|d| <= nRings, |sten| <= ra); cells outside the map
-        // have F = 0 and are skipped like the iterator skips them
-        const uint32_t F = pl.col(PL_F, b), C = pl.col(PL_C, b);
-        const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
-        const uint32_t bad = F & (C | ~box);
-        good = !((bad >> a) & 1u);
-      }
-    }
-    if (good) {
-      o.ok = true;
-      o.x = pos_axis(M.fcx, M.res, q0);  // gridmap.getPosition(index) (FP.cpp:2105-2107)
-      o.y = pos_axis(M.fcy, M.res, q1);
-      o.row = wrap_add(q0, M.start0, M.rows);
-      o.col = wrap_add(q1, M.start1, M.cols);
-      break;
-    }
+  bool found = false;
+  int fq0 = 0, fq1 = 0;
+  spiral_scan_coop(M, G, sSpiral, smemWarp, lane, need && !faithful, uc0, uc1, cx, cy, P.R2, rowsBox, colsBox, found,
+                   fq0, fq1);
+  if (need && faithful)
+    spiral_scan_faithful(M, G, sSpiral, pl, P.thrC, uc0, uc1, cx, cy, P.R2, bx, rowsBox, colsBox, found, fq0, fq1);
+  if (found) {
+    o.ok = true;
+    o.x = pos_axis(M.fcx, M.res, fq0);  // gridmap.getPosition(index) (FP.cpp:2105-2107)
+    o.y = pos_axis(M.fcy, M.res, fq1);
+    o.row = wrap_add(fq0, M.start0, M.rows);
+    o.col = wrap_add(fq1, M.start1, M.cols);
   }
   return o;
 }

@@ -48,19 +48,31 @@ __device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y,
   reinterpret_cast<unsigned long long*>(dst)[4] = ids;
 }
 
+// Block-wide copy of the SpiralIterator table into shared memory (ranks are looked up with a per-lane index in the
+// cooperative scan; the constant bank would serialise those).  Returns the table; ends with __syncthreads.
+__device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, uint32_t* smem) {
+  uint16_t* t = reinterpret_cast<uint16_t*>(smem);
+  for (int k = threadIdx.x; k < G.nCand; k += blockDim.x)
+    t[k] = static_cast<uint16_t>(static_cast<uint8_t>(G.spiral[k][0])) |
+           static_cast<uint16_t>(static_cast<uint16_t>(static_cast<uint8_t>(G.spiral[k][1])) << 8);
+  __syncthreads();
+  return t;
+}
+
 template <bool WANT_CEN>
 __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
-  uint32_t* sw = smem + warpInBlock * 32 * G.stride;
+  const uint16_t* sSpiral = load_spiral_table(G, smem);
+  uint32_t* sw = smem + G.spiralWords + warpInBlock * 32 * G.stride;
   const long long gwarp = static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock;
   const long long q = gwarp * 8 + (lane >> 2);
   const int f = lane & 3;           // RF,RH,LH,LF
   const int quad0 = lane & ~3;
   const bool active = q < A.nq;
-  if (gwarp * 8 >= A.nq) return;    // whole warp idle
+  if (gwarp * 8 >= A.nq) return;    // whole warp idle (after the block-wide table load)
   const MapDev& M = A.M;
 
   fhp_query qu;
@@ -113,16 +125,21 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const __grid_constan
     const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
     stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
 
-    bool ok = false;
     CentroidOut co;
-    NominalOut no;
+    co.x = co.y = 0.0;
+    co.ccase = -1;
     double nz = 0.0, cz = 0.0;
+    DiscWin dw = {0, 0, -1, -1};
     if (active) {
       Planes pl{sw + lane * G.stride, G.pack, G.rpShift};
-      co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);                 // FP.cpp:818-821
-      no = nominal_eval<false>(M, G, P, pl, uc0, uc1, px, py, rx, ry, err);  // FP.cpp:863-903
-      ok = no.ok;
-      if (ok) nz = static_cast<double>(mean_height(M, P, px, py));           // at the CENTRE (FP.cpp:2029)
+      co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
+      dw = disc_window(M, px, py, P.r);
+    }
+    const NominalOut no =
+        nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, px, py, rx, ry, dw, err);  // FP.cpp:863-903
+    const bool ok = no.ok;
+    if (active) {
+      if (ok) nz = static_cast<double>(mean_height(M, P, px, py, dw));  // at the CENTRE (FP.cpp:2029)
       if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, P, co.x, co.y));
     }
     // footholdValidation_ = RF & RH & LH & LF (FP.cpp:1323)
@@ -169,10 +186,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const __grid_constan
 template <int MODE>
 __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constant__ TaskArgs A,
                                                             const __grid_constant__ GeoDev G) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
-  uint32_t* sw = smem + warpInBlock * 32 * G.stride;
+  const uint16_t* sSpiral = load_spiral_table(G, smem);
+  uint32_t* sw = smem + G.spiralWords + warpInBlock * 32 * G.stride;
   const long long i = (static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock) * 32 + lane;
   const bool active = i < A.n;
   const MapDev& M = A.M;
@@ -194,15 +212,26 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
   const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
-  if (!active) return;
   Planes pl{sw + lane * G.stride, G.pack, G.rpShift};
-  if (MODE == 0) {
-    NominalOut no = nominal_eval<false>(M, G, P, pl, uc0, uc1, px, py, rx, ry, err);
-    double z = 0.0;
-    if (no.ok) z = static_cast<double>(mean_height(M, P, px, py));
-    write_row(A.out + i, no.x, no.y, z, no.row, no.col, 0, 0, no.kind);
-    A.valid[i] = no.ok ? 1 : 0;
-  } else if (MODE == 1) {
+  if (MODE == 0 || MODE == 3) {
+    DiscWin dw = {0, 0, -1, -1};
+    if (active) dw = disc_window(M, px, py, P.r);
+    NominalOut no;
+    if (MODE == 0)
+      no = nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, px, py, rx, ry, dw, err);
+    else
+      no = nominal_eval<true>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, px, py, rx, ry, dw, err);
+    if (active) {
+      if (MODE == 0) {
+        double z = 0.0;
+        if (no.ok) z = static_cast<double>(mean_height(M, P, px, py, dw));
+        write_row(A.out + i, no.x, no.y, z, no.row, no.col, 0, 0, no.kind);
+      }
+      A.valid[i] = no.ok ? 1 : 0;
+    }
+  }
+  if (!active) return;
+  if (MODE == 1) {
     CentroidOut co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);
     double z = 0.0;
     if (co.ccase >= 0 && co.ccase <= 3) z = static_cast<double>(mean_height(M, P, co.x, co.y));
@@ -210,9 +239,6 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     cell_of_position(M, co.x, co.y, r0, c0);
     write_row(A.out + i, co.x, co.y, z, r0, c0, 0, 0, FHP_KIND_DEFAULT);
     A.ccase[i] = static_cast<int8_t>(co.ccase);
-  } else if (MODE == 3) {
-    NominalOut no = nominal_eval<true>(M, G, P, pl, uc0, uc1, px, py, rx, ry, err);
-    A.valid[i] = no.ok ? 1 : 0;
   }
   if (err) atomicOr(A.err, err);
 }
@@ -223,7 +249,14 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
   const int warps = kPlanThreads / 32;
   const long long nWarps = (A.nq + 7) / 8;
   const long long blocks = (nWarps + warps - 1) / warps;
-  const size_t shm = static_cast<size_t>(warps) * 32 * G.stride * sizeof(uint32_t);
+  const size_t shm = (static_cast<size_t>(G.spiralWords) + static_cast<size_t>(warps) * 32 * G.stride) * sizeof(uint32_t);
+  if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
+    cudaError_t e = wantCen ? cudaFuncSetAttribute(plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(shm))
+                            : cudaFuncSetAttribute(plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(shm));
+    if (e != cudaSuccess) return e;
+  }
   if (wantCen)
     plan_kernel<true><<<static_cast<unsigned>(blocks), kPlanThreads, shm, stream>>>(A, G);
   else
@@ -236,8 +269,18 @@ cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream
   const int warps = kPlanThreads / 32;
   const long long nWarps = (A.n + 31) / 32;
   const long long blocks = (nWarps + warps - 1) / warps;
-  const size_t shm = static_cast<size_t>(warps) * 32 * G.stride * sizeof(uint32_t);
+  const size_t shm = (static_cast<size_t>(G.spiralWords) + static_cast<size_t>(warps) * 32 * G.stride) * sizeof(uint32_t);
   const unsigned nb = static_cast<unsigned>(blocks);
+  if (shm > 48 * 1024) {
+    cudaError_t e;
+    switch (mode) {
+      case 0: e = cudaFuncSetAttribute(task_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+      case 1: e = cudaFuncSetAttribute(task_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+      case 2: e = cudaFuncSetAttribute(task_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+      default: e = cudaFuncSetAttribute(task_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+    }
+    if (e != cudaSuccess) return e;
+  }
   switch (mode) {
     case 0: task_kernel<0><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
     case 1: task_kernel<1><<<nb, kPlanThreads, shm, stream>>>(A, G); break;

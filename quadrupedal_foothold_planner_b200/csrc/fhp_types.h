@@ -32,7 +32,8 @@ struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int pack;      // window columns per warp load: 1 (WIN<=32), 2 (WIN<=16), 4 (WIN<=8)
   int rpShift;   // log2(32/pack): lanes per column group
   int nIter;     // ceil(WIN / pack) = words per bit-plane
-  int stride;    // shared-memory words per query (3*nIter, padded odd)
+  int stride;    // shared-memory words per query (4 per load iteration: D, C, F, pad)
+  int spiralWords;  // 32-bit words reserved at the start of shared memory for the spiral table (16-byte multiple)
   int nCand;     // spiral table length
   int lastTwoStart;  // first rank that belongs to ring nRings-1 (distance-filtered rings)
   int nSten;
