@@ -59,8 +59,11 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
   return t;
 }
 
+#ifndef FHP_PLAN_MIN_BLOCKS
+#define FHP_PLAN_MIN_BLOCKS 5
+#endif
 template <bool WANT_CEN>
-__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const __grid_constant__ PlanArgs A,
+__global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;

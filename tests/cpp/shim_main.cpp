@@ -1,0 +1,49 @@
+// Drives the C++ host shim (FootholdPlannerGpu.hpp) exactly like a ROS node would: map update, then the
+// plan_global_footholds service body.  Reads a raw map file written by the test, prints the response rows.
+//   shim_main <map.bin> <rows> <cols> <res> <start_row> <start_col> <x> <y> <z> <gait_cycles>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "FootholdPlannerGpu.hpp"
+
+int main(int argc, char** argv) {
+  if (argc != 11) return 2;
+  const int rows = atoi(argv[2]), cols = atoi(argv[3]);
+  const double res = atof(argv[4]);
+  std::vector<float> trav(static_cast<size_t>(rows) * cols), elev(trav.size());
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) return 3;
+  if (fread(&trav[0], 4, trav.size(), f) != trav.size() || fread(&elev[0], 4, elev.size(), f) != elev.size()) return 4;
+  fclose(f);
+  foothold_planner::FootholdPlannerGpu planner(0);
+  foothold_planner::GridMapView m;
+  m.rows = rows;
+  m.cols = cols;
+  m.resolution = res;
+  m.length_x = rows * res;
+  m.length_y = cols * res;
+  m.pos_x = 0;
+  m.pos_y = 0;
+  m.start_row = atoi(argv[5]);
+  m.start_col = atoi(argv[6]);
+  m.layer_names.push_back("traversability");
+  m.layer_names.push_back("elevation");
+  m.layer_data.push_back(&trav[0]);
+  m.layer_data.push_back(&elev[0]);
+  planner.gridmapCallback(m);
+  planner.initialPose_[0] = atof(argv[7]);
+  planner.initialPose_[1] = atof(argv[8]);
+  planner.initialPose_[2] = atof(argv[9]);
+  foothold_planner::GlobalFootholdPlanRequest req;
+  req.gait_cycles = static_cast<uint8_t>(atoi(argv[10]));
+  foothold_planner::GlobalFootholdPlanResponse resp;
+  if (!planner.globalFootholdPlan(req, resp)) return 5;
+  printf("%d %d %d %zu\n", resp.footholds.success ? 1 : 0, resp.footholds.gait_cycles, resp.footholds.gait_cycles_succeed,
+         resp.footholds.footholds.size());
+  for (size_t i = 0; i < resp.footholds.footholds.size(); ++i) {
+    const foothold_planner::Foothold& h = resp.footholds.footholds[i];
+    printf("%.17g %.17g %.17g %d %d\n", h.point.x, h.point.y, h.point.z, h.foot_id, h.gait_cycle_id);
+  }
+  return 0;
+}

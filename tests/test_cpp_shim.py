@@ -1,0 +1,45 @@
+"""The C++ host shim a ROS node would link (csrc/FootholdPlannerGpu.hpp): compiled with g++ against libfhp.so and
+run as a separate process on the GPU; its response must equal the oracle's."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from quadrupedal_foothold_planner_b200 import _abi, planner, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path):
+    planner.load_lib()
+    exe = str(tmp_path / "shim_main")
+    pkg = os.path.join(ROOT, "quadrupedal_foothold_planner_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "csrc"),
+                           os.path.join(ROOT, "tests", "cpp", "shim_main.cpp"), "-o", exe, "-L", pkg, "-lfhp",
+                           "-Wl,-rpath," + pkg])
+    return exe
+
+
+def test_cpp_shim_links(tmp_path):
+    assert os.path.exists(_build(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cpp_shim_matches_oracle(tmp_path, oracle):
+    exe = _build(tmp_path)
+    m = synth.rough_map(400, 300, 0.02, seed=13, start=(31, 250))
+    path = str(tmp_path / "map.bin")
+    with open(path, "wb") as f:
+        f.write(np.asfortranarray(m.layers["traversability"]).tobytes(order="F"))
+        f.write(np.asfortranarray(m.layers["elevation"]).tobytes(order="F"))
+    for pose in ([-2.5, 0.3, 0.0], [-1.0, -1.2, 0.125]):
+        out = subprocess.check_output([exe, path, "400", "300", "0.02", "31", "250", repr(pose[0]), repr(pose[1]),
+                                       repr(pose[2]), "9"], text=True).strip().splitlines()
+        nom, _, st = oracle.plan(m, _abi.yaml_params(), _abi.make_queries([pose]), 9)
+        s, gc, gs, n = (int(v) for v in out[0].split())
+        assert (s, gc, gs, n) == (st[0]["success"], 9, st[0]["gait_cycles_succeed"], st[0]["n_rows"])
+        for line, row in zip(out[1:], nom[0][:n]):
+            x, y, z, foot, cyc = line.split()
+            assert abs(float(x) - row["x"]) <= 1e-5 and abs(float(y) - row["y"]) <= 1e-5 and abs(float(z) - row["z"]) <= 1e-5
+            assert (int(foot), int(cyc)) == (row["foot_id"], row["gait_cycle_id"])
