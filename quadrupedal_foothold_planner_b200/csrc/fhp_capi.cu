@@ -91,6 +91,8 @@ int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
   M.leny = d->length_y;
   M.posx = d->pos_x;
   M.posy = d->pos_y;
+  M.fastOk = (static_cast<long long>(d->rows) * d->cols < (1LL << 31)) ? 1 : 0;
+  M.pad0 = 0;
   M.halfx = 0.5 * M.lenx;                        // getVectorToOrigin
   M.halfy = 0.5 * M.leny;
   M.fcx = M.posx + (M.halfx - 0.5 * M.res);      // mapPosition + getVectorToFirstCell

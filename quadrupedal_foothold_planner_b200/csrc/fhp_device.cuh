@@ -104,66 +104,115 @@ enum { PL_D = 0, PL_C = 1, PL_F = 2 };
 // unwrapped origin is (w0,w1) of lane j and store its D/C/F bit-planes at smem[j*stride ...] (4 words per load
 // iteration: D, C, F, pad — one 16-byte store by lane 0).
 // Cells outside the map read as NaN (=> D=C=F=0), which is exactly "not visited" for every iterator.
-// Interior windows that do not cross the circular-buffer seam (the common case) take a path whose per-iteration
-// work is one pointer increment, one coalesced load, three compares and three ballots; bits of rows/columns
-// beyond WIN then hold real neighbouring cells, which no consumer ever reads.
+//
+// Interior windows that do not cross the circular-buffer seam (the common case) go through a software pipeline:
+// the loads of the NEXT window (up to kStageChunk coalesced column loads per lane) are issued before the ballots
+// of the current one, so the L2/HBM latency of a window is covered by the bit-plane reduction of its predecessor.
+// Bits of rows/columns beyond WIN then hold real neighbouring cells, which no consumer ever reads.
+// Windows touching the map border or the seam take the generic per-cell path.
+constexpr int kStageChunk = 8;
+
+__device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint4* dst, int lane, int k0, const float (&v)[kStageChunk],
+                                                    float tD, float tC) {
+  const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int i = 0; i < kStageChunk; ++i) {
+    if (k0 + i < G.nIter) {
+      const uint32_t bD = __ballot_sync(kFull, v[i] < tD);
+      const uint32_t bC = __ballot_sync(kFull, v[i] < tC);
+      const uint32_t bF = __ballot_sync(kFull, fabsf(v[i]) < inf);
+      if (lane == 0) dst[k0 + i] = make_uint4(bD, bC, bF, 0u);
+    }
+  }
+}
+
 __device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, uint32_t* smemWarp, int lane,
                                               bool has_window, int w0, int w1, float thrD, float thrC) {
-  const unsigned act = __ballot_sync(kFull, has_window);
   const int RP = 1 << G.rpShift;
   const int a = lane & (RP - 1);
   const int h = lane >> G.rpShift;
   const int colsCovered = G.nIter * G.pack;
-  const float inf = __int_as_float(0x7f800000);
+  // every lane classifies ITS OWN window and computes its buffer origin (|w| <= 2^30 + HW: no overflow)
+  int bb0 = w0 + M.start0, bb1 = w1 + M.start1;
+  if (bb0 >= M.rows) bb0 -= M.rows;
+  if (bb1 >= M.cols) bb1 -= M.cols;
+  const bool myFast = has_window && M.fastOk && w0 >= 0 && w1 >= 0 && w0 <= M.rows - RP && w1 <= M.cols - colsCovered &&
+                      bb0 <= M.rows - RP && bb1 <= M.cols - colsCovered;
+  const int org = myFast ? bb1 * M.rows + bb0 : 0;  // rows*cols < 2^31 is part of fastOk
+  unsigned fastMask = __ballot_sync(kFull, myFast);
+  const unsigned slowMask = __ballot_sync(kFull, has_window && !myFast);
+  const unsigned act = fastMask | slowMask;
+  if (act == 0) {
+    __syncwarp();
+    return;
+  }
+  const int first = __ffs(act) - 1;
+  const float tD0 = __shfl_sync(kFull, thrD, first), tC0 = __shfl_sync(kFull, thrC, first);
+  const bool uni = __all_sync(kFull, !has_window || (thrD == tD0 && thrC == tC0));
   __syncwarp();
-  for (unsigned m = act; m; m &= m - 1) {
+
+  if (fastMask) {
+    const int nChunks = (G.nIter + kStageChunk - 1) / kStageChunk;
+    const long long step = static_cast<long long>(G.pack) * M.rows;
+    const float* laneBase = M.trav + static_cast<long long>(h) * M.rows + a;
+    float nxt[kStageChunk], cur[kStageChunk];
+    int jn = __ffs(fastMask) - 1, cn = 0;
+    {
+      const float* p = laneBase + __shfl_sync(kFull, org, jn);
+#pragma unroll
+      for (int i = 0; i < kStageChunk; ++i) nxt[i] = (i < G.nIter) ? __ldg(p + i * step) : 0.0f;
+    }
+    for (;;) {
+      const int j = jn, c = cn;
+#pragma unroll
+      for (int i = 0; i < kStageChunk; ++i) cur[i] = nxt[i];
+      bool more = true;
+      if (cn + 1 < nChunks) {
+        cn += 1;
+      } else {
+        fastMask &= fastMask - 1;
+        if (fastMask) {
+          jn = __ffs(fastMask) - 1;
+          cn = 0;
+        } else {
+          more = false;
+        }
+      }
+      if (more) {  // prefetch the next unit before reducing the current one
+        const float* p = laneBase + __shfl_sync(kFull, org, jn) + static_cast<long long>(cn) * kStageChunk * step;
+        const int k0n = cn * kStageChunk;
+#pragma unroll
+        for (int i = 0; i < kStageChunk; ++i) nxt[i] = (k0n + i < G.nIter) ? __ldg(p + i * step) : 0.0f;
+      }
+      const float tD = uni ? tD0 : __shfl_sync(kFull, thrD, j);
+      const float tC = uni ? tC0 : __shfl_sync(kFull, thrC, j);
+      stage_chunk_ballots(G, reinterpret_cast<uint4*>(smemWarp + j * G.stride), lane, c * kStageChunk, cur, tD, tC);
+      if (!more) break;
+    }
+  }
+
+  const float inf = __int_as_float(0x7f800000);
+  for (unsigned m = slowMask; m; m &= m - 1) {
     const int j = __ffs(m) - 1;
     const int jw0 = __shfl_sync(kFull, w0, j);
     const int jw1 = __shfl_sync(kFull, w1, j);
     const float tD = __shfl_sync(kFull, thrD, j);
     const float tC = __shfl_sync(kFull, thrC, j);
     uint4* dst = reinterpret_cast<uint4*>(smemWarp + j * G.stride);
-    int bb0 = jw0 + M.start0, bb1 = jw1 + M.start1;
-    if (bb0 >= M.rows) bb0 -= M.rows;
-    if (bb1 >= M.cols) bb1 -= M.cols;
-    const bool fast = jw0 >= 0 && jw1 >= 0 && jw0 <= M.rows - RP && jw1 <= M.cols - colsCovered &&
-                      bb0 <= M.rows - RP && bb1 <= M.cols - colsCovered;
-    if (fast) {
-      const float* p = M.trav + static_cast<size_t>(bb1 + h) * M.rows + (bb0 + a);
-      const size_t step = static_cast<size_t>(G.pack) * M.rows;
-#ifdef FHP_DEBUG
-      {
-        long long off0 = static_cast<long long>(bb1 + h) * M.rows + (bb0 + a);
-        long long offN = off0 + static_cast<long long>(G.nIter - 1) * static_cast<long long>(step);
-        if (off0 < 0 || offN >= static_cast<long long>(M.rows) * M.cols)
-          printf("BAD fast: lane %d j %d jw0 %d jw1 %d bb0 %d bb1 %d a %d h %d RP %d colsCov %d rows %d cols %d off0 %lld offN %lld trav %p\n",
-                 lane, j, jw0, jw1, bb0, bb1, a, h, RP, colsCovered, M.rows, M.cols, off0, offN, (const void*)M.trav);
-      }
-#endif
-      for (int k = 0; k < G.nIter; ++k) {
-        const float v = __ldg(p);
-        p += step;
-        const uint32_t bD = __ballot_sync(kFull, v < tD);
-        const uint32_t bC = __ballot_sync(kFull, v < tC);
-        const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
-        if (lane == 0) dst[k] = make_uint4(bD, bC, bF, 0u);
-      }
-    } else {
-      const int u0 = jw0 + a;
-      const bool in0 = (a < G.WIN) && u0 >= 0 && u0 < M.rows;
-      const int b0 = wrap_add(u0, M.start0, M.rows);
-      for (int k = 0; k < G.nIter; ++k) {
-        const int b = k * G.pack + h;
-        const int u1 = jw1 + b;
-        const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
-        const int b1 = wrap_add(u1, M.start1, M.cols);
-        float v = __int_as_float(0x7fc00000);
-        if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
-        const uint32_t bD = __ballot_sync(kFull, v < tD);
-        const uint32_t bC = __ballot_sync(kFull, v < tC);
-        const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
-        if (lane == 0) dst[k] = make_uint4(bD, bC, bF, 0u);
-      }
+    const int u0 = jw0 + a;
+    const bool in0 = (a < G.WIN) && u0 >= 0 && u0 < M.rows;
+    const int b0 = wrap_add(u0, M.start0, M.rows);
+    for (int k = 0; k < G.nIter; ++k) {
+      const int b = k * G.pack + h;
+      const int u1 = jw1 + b;
+      const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
+      const int b1 = wrap_add(u1, M.start1, M.cols);
+      float v = __int_as_float(0x7fc00000);
+      if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
+      const uint32_t bD = __ballot_sync(kFull, v < tD);
+      const uint32_t bC = __ballot_sync(kFull, v < tC);
+      const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
+      if (lane == 0) dst[k] = make_uint4(bD, bC, bF, 0u);
     }
   }
   __syncwarp();
@@ -419,20 +468,52 @@ __device__ __forceinline__ void spiral_entry(const uint16_t* sSpiral, int k, int
 }
 
 // checkCandidateFoothold (FP.cpp:2085-2114) over grid_map::SpiralIterator — warp-cooperative rank scan.
-// For every lane j with `need`, the 32 lanes test candidates rank base..base+31 of query j at once (in-range
-// check, last-two-rings distance filter, foot-disc/polygon test on j's staged planes) and the first set bit of the
-// ballot is the first valid cell in spiral order; the scan stops at the first 32-block that has one.
+// For every lane j with `need`:
+//   1. lane b (< WIN) builds the "bad cell" mask of window column b from j's staged planes: a finite cell is bad when
+//      it is below candidateFootholdThreshold or its centre is outside the search rectangle (FP.cpp:2138); NaN and
+//      out-of-map cells are never bad (the CircleIterator skips them).  The masks are then dilated by the foot-disc
+//      stencil, so bit a of column b says "the foot disc centred on cell (a,b) contains a bad cell", and cells whose
+//      own index is outside the map are marked too (checkIfIndexInRange in SpiralIterator::generateRing).
+//   2. the 32 lanes test candidates rank base..base+31 at once: table lookup, one shuffle to fetch the column mask,
+//      one bit test, plus the exact last-two-rings distance filter; the first set bit of the ballot is the first
+//      valid cell in spiral order and the scan stops at the first 32-block that has one.
 // Handles wrap_correct mode, and faithful mode when the start index is (0,0) (identical there).
 __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
                                                  const uint32_t* smemWarp, int lane, bool need, int uc0, int uc1,
                                                  double cx, double cy, double R2, uint32_t rowsBox, uint32_t colsBox,
                                                  bool& found, int& fq0, int& fq1) {
   const unsigned needMask = __ballot_sync(kFull, need);
+  const uint32_t winMask = G.WIN >= 32 ? 0xffffffffu : ((1u << G.WIN) - 1u);
   for (unsigned m = needMask; m; m &= m - 1) {
     const int j = __ffs(m) - 1;
     const int juc0 = __shfl_sync(kFull, uc0, j), juc1 = __shfl_sync(kFull, uc1, j);
     const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
     const Planes pj{smemWarp + j * G.stride, G.pack, G.rpShift};
+    // 1. column masks (lane = window column)
+    uint32_t bad = 0;
+    if (lane < G.WIN) {
+      const uint32_t F = pj.col(PL_F, lane), C = pj.col(PL_C, lane);
+      const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
+      bad = F & (C | ~box) & winMask;
+    }
+    uint32_t dil = 0;
+    for (int s = 0; s < G.nSten; ++s) {
+      const int s0 = G.sten[s][0], s1 = G.sten[s][1];
+      const int srcCol = lane + s1;
+      uint32_t nb = __shfl_sync(kFull, bad, srcCol & 31);
+      if (srcCol < 0 || srcCol >= G.WIN) nb = 0;
+      dil |= (s0 >= 0) ? (nb >> s0) : (nb << (-s0));
+    }
+    // candidate cells outside the map: rows (bits) and this lane's column
+    {
+      const int lo = max(0, G.HW - juc0), hi = min(G.WIN - 1, M.rows - 1 - juc0 + G.HW);  // window rows inside the map
+      uint32_t rowsIn = 0;
+      if (hi >= lo) rowsIn = (hi - lo >= 31 ? 0xffffffffu : ((1u << (hi - lo + 1)) - 1u)) << lo;
+      const int q1 = juc1 + lane - G.HW;
+      const bool colIn = q1 >= 0 && q1 < M.cols;
+      dil = colIn ? (dil | ~rowsIn) : 0xffffffffu;
+    }
+    // 2. rank scan
     bool haveC = false;
     double jcx = 0, jcy = 0, jR2 = 0;
     for (int base = 0; base < G.nCand; base += 32) {
@@ -440,9 +521,10 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
       bool cand = k < G.nCand;
       int d0, d1;
       spiral_entry(sSpiral, cand ? k : 0, d0, d1);
-      const int q0 = juc0 + d0, q1 = juc1 + d1;
-      cand = cand && in_map(M, q0, q1);                // checkIfIndexInRange(pointInMap)
-      if (base + 32 > G.lastTwoStart) {                // rings nRings-1, nRings: distance filter (uniform branch)
+      const int qa = d0 + G.HW, qb = d1 + G.HW;
+      const uint32_t e = __shfl_sync(kFull, dil, qb);
+      cand = cand && !((e >> qa) & 1u);
+      if (base + 32 > G.lastTwoStart) {  // rings nRings-1, nRings: distance filter (uniform branch)
         if (!haveC) {
           jcx = __shfl_sync(kFull, cx, j);
           jcy = __shfl_sync(kFull, cy, j);
@@ -450,19 +532,18 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
           haveC = true;
         }
         if (cand && k >= G.lastTwoStart) {
-          const double dx = pos_axis(M.fcx, M.res, q0) - jcx, dy = pos_axis(M.fcy, M.res, q1) - jcy;
+          const double dx = pos_axis(M.fcx, M.res, juc0 + d0) - jcx, dy = pos_axis(M.fcy, M.res, juc1 + d1) - jcy;
           cand = (dx * dx + dy * dy <= jR2);
         }
       }
-      const bool good = cand && candidate_on_planes(G, pj, d0 + G.HW, d1 + G.HW, jrows, jcols);
-      const unsigned g = __ballot_sync(kFull, good);
+      const unsigned g = __ballot_sync(kFull, cand);
       if (g) {
         const int src = __ffs(g) - 1;
-        const int wq0 = __shfl_sync(kFull, q0, src), wq1 = __shfl_sync(kFull, q1, src);
+        const int wd0 = __shfl_sync(kFull, d0, src), wd1 = __shfl_sync(kFull, d1, src);
         if (lane == j) {
           found = true;
-          fq0 = wq0;
-          fq1 = wq1;
+          fq0 = juc0 + wd0;
+          fq1 = juc1 + wd1;
         }
         break;
       }

@@ -18,6 +18,8 @@ struct MapDev {
   const float* trav;
   const float* elev;
   int rows, cols, start0, start1;
+  int fastOk;  // rows*cols < 2^31: 32-bit linear cell offsets are safe in the pipelined staging path
+  int pad0;
   double res;
   double lenx, leny, posx, posy;
   double halfx, halfy;  // getVectorToOrigin: 0.5*length
