@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "fhp_host.h"
 
 using namespace fhp;
@@ -54,6 +56,9 @@ struct fhp_ctx {
   bool haveGeo = false;
   float geoFoot = 0, geoSearch = 0;
   GeoDev G{};
+  // TMA descriptor of the traversability layer (box = one staged window); rebuilt with the geometry tables
+  alignas(64) CUtensorMap tmapTrav;
+  bool disableTma = false;  // FHP_DISABLE_TMA=1: force the LDG staging path (tests cover both)
   // scratch
   DevBuf dPars, dQ, dOutN, dOutC, dSt, dErr, dA, dB, dC2, dD;
   long long launches = 0;
@@ -167,6 +172,38 @@ void derive_params(const fhp_params& p, ParDev& o) {
 
 int sgn(int v) { return (v > 0) - (v < 0); }
 
+// 2-D tiled tensor map over the column-major traversability layer: dim0 = rows (contiguous), dim1 = cols; box =
+// (32/pack rows) x (nIter*pack cols) = one staged window; out-of-bounds elements are filled with NaN.
+// Returns false (=> LDG staging path) when TMA's layout rules are not met: row pitch not a multiple of 16 bytes,
+// base pointer not 16-byte aligned, or the driver entry point is unavailable.
+bool build_tma(fhp_ctx* ctx) {
+  if (ctx->disableTma) return false;
+  const MapDev& M = ctx->M;
+  const GeoDev& G = ctx->G;
+  if (!M.trav || (M.rows % 4) != 0 || (reinterpret_cast<uintptr_t>(M.trav) & 15u) != 0) return false;
+  if (G.WIN + 3 > 32 / G.pack) return false;  // the row-alignment shift (<= 3) must fit in the box
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn)
+      return false;
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(M.rows), static_cast<cuuint64_t>(M.cols)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(M.rows) * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(32 / G.pack), static_cast<cuuint32_t>(G.nIter * G.pack)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(&ctx->tmapTrav, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(M.trav), gdim, gstride, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+  return r == CUDA_SUCCESS;
+}
+
 // Tables that depend only on (footRadius, searchRadius, resolution): the SpiralIterator visiting order and the
 // cell-centred foot-disc stencil.
 int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
@@ -255,6 +292,17 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
     G.spiral[k][0] = static_cast<int8_t>(table[k].first);
     G.spiral[k][1] = static_cast<int8_t>(table[k].second);
   }
+  // ---- shared-memory layout of a plan_kernel block and the TMA descriptor
+  const int warps = kPlanThreads / 32;
+  const int planesEnd = G.spiralWords + warps * 32 * G.stride;
+  G.boxWords = 32 * G.nIter;
+  G.tmaBShift = 0;
+  while (G.tmaBShift < 3 && (2 << (G.tmaBShift + 1)) * G.boxWords * 4 <= 8192) ++G.tmaBShift;
+  G.tmaB = 1 << G.tmaBShift;
+  G.mbarOff = planesEnd;                                   // multiple of 4 words -> 8-byte aligned
+  G.boxOff = ((G.mbarOff + warps * 4 + 31) / 32) * 32;     // 128-byte aligned
+  G.useTma = build_tma(ctx) ? 1 : 0;
+  G.smemWords = G.useTma ? G.boxOff + warps * 2 * G.tmaB * G.boxWords : planesEnd;
   ctx->geoFoot = footRadius;
   ctx->geoSearch = searchRadius;
   ctx->haveGeo = true;
@@ -352,6 +400,9 @@ int fhp_create(int device, fhp_ctx** out) {
   }
   fhp_ctx* ctx = new fhp_ctx();
   ctx->device = device;
+  std::memset(&ctx->tmapTrav, 0, sizeof(ctx->tmapTrav));
+  const char* dt = std::getenv("FHP_DISABLE_TMA");
+  ctx->disableTma = dt && dt[0] == '1';
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
@@ -437,6 +488,7 @@ static int plan_common(fhp_ctx* ctx, const fhp_params* params, int32_t n_params,
   rc = ensure_err_word(ctx);
   if (rc != FHP_OK) return rc;
   PlanArgs A;
+  A.tmap = ctx->tmapTrav;
   A.M = ctx->M;
   A.pars = static_cast<const ParDev*>(ctx->dPars.p);
   A.nPars = n_params;

@@ -80,21 +80,39 @@ __device__ __forceinline__ void cell_of_position(const MapDev& M, double x, doub
   col = wrap_add(u1, M.start1, M.cols);
 }
 
+// ------------------------------------------------------------------------------------------------ shared memory
+// Explicit shared-space accesses on 32-bit addresses (the compiler otherwise falls back to generic 64-bit
+// addressing once a shared pointer has travelled through a struct).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ bit planes
-struct Planes {  // view of one query's staged window in shared memory
-  const uint32_t* w;
+struct Planes {  // view of one query's staged window in shared memory (shared-space byte address)
+  uint32_t w;
   int pack, rpShift;
   __device__ __forceinline__ uint32_t col(int plane, int b) const {  // bits over window rows a for column b
-    if (pack == 1) return w[b * 4 + plane];
+    if (pack == 1) return lds_u32(w + static_cast<uint32_t>(b * 4 + plane) * 4u);
     int k, sh;
     if (pack == 2) {
       k = b >> 1;
       sh = (b & 1) << 4;
-      return (w[k * 4 + plane] >> sh) & 0xffffu;
+      return (lds_u32(w + static_cast<uint32_t>(k * 4 + plane) * 4u) >> sh) & 0xffffu;
     }
     k = b >> 2;
     sh = (b & 3) << 3;
-    return (w[k * 4 + plane] >> sh) & 0xffu;
+    return (lds_u32(w + static_cast<uint32_t>(k * 4 + plane) * 4u) >> sh) & 0xffu;
   }
   __device__ __forceinline__ bool bit(int plane, int a, int b) const { return (col(plane, b) >> a) & 1u; }
 };
@@ -112,7 +130,7 @@ enum { PL_D = 0, PL_C = 1, PL_F = 2 };
 // Windows touching the map border or the seam take the generic per-cell path.
 constexpr int kStageChunk = 8;
 
-__device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint4* dst, int lane, int k0, const float (&v)[kStageChunk],
+__device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint32_t dst, int lane, int k0, const float (&v)[kStageChunk],
                                                     float tD, float tC) {
   const float inf = __int_as_float(0x7f800000);
 #pragma unroll
@@ -121,12 +139,44 @@ __device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint4* dst,
       const uint32_t bD = __ballot_sync(kFull, v[i] < tD);
       const uint32_t bC = __ballot_sync(kFull, v[i] < tC);
       const uint32_t bF = __ballot_sync(kFull, fabsf(v[i]) < inf);
-      if (lane == 0) dst[k0 + i] = make_uint4(bD, bC, bF, 0u);
+      if (lane == 0) sts_v4(dst + static_cast<uint32_t>(k0 + i) * 16u, bD, bC, bF, 0u);
     }
   }
 }
 
-__device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, uint32_t* smemWarp, int lane,
+// Generic per-cell staging (windows touching the map border or the circular-buffer seam).
+__device__ __noinline__ void stage_slow(const MapDev& M, const GeoDev& G, uint32_t smemWarp, int lane, unsigned slowMask,
+                                        int w0, int w1, float thrD, float thrC) {
+  const int RP = 1 << G.rpShift;
+  const int a = lane & (RP - 1);
+  const int h = lane >> G.rpShift;
+  const float inf = __int_as_float(0x7f800000);
+  for (unsigned m = slowMask; m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    const int jw0 = __shfl_sync(kFull, w0, j);
+    const int jw1 = __shfl_sync(kFull, w1, j);
+    const float tD = __shfl_sync(kFull, thrD, j);
+    const float tC = __shfl_sync(kFull, thrC, j);
+    const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
+    const int u0 = jw0 + a;
+    const bool in0 = u0 >= 0 && u0 < M.rows;  // all RP rows: the TMA path may have shifted the origin down by <= 3
+    const int b0 = wrap_add(u0, M.start0, M.rows);
+    for (int k = 0; k < G.nIter; ++k) {
+      const int b = k * G.pack + h;
+      const int u1 = jw1 + b;
+      const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
+      const int b1 = wrap_add(u1, M.start1, M.cols);
+      float v = __int_as_float(0x7fc00000);
+      if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
+      const uint32_t bD = __ballot_sync(kFull, v < tD);
+      const uint32_t bC = __ballot_sync(kFull, v < tC);
+      const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
+      if (lane == 0) sts_v4(dst + static_cast<uint32_t>(k) * 16u, bD, bC, bF, 0u);
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, uint32_t smemWarp, int lane,
                                               bool has_window, int w0, int w1, float thrD, float thrC) {
   const int RP = 1 << G.rpShift;
   const int a = lane & (RP - 1);
@@ -186,35 +236,155 @@ __device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, 
       }
       const float tD = uni ? tD0 : __shfl_sync(kFull, thrD, j);
       const float tC = uni ? tC0 : __shfl_sync(kFull, thrC, j);
-      stage_chunk_ballots(G, reinterpret_cast<uint4*>(smemWarp + j * G.stride), lane, c * kStageChunk, cur, tD, tC);
+      stage_chunk_ballots(G, smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, lane, c * kStageChunk, cur, tD, tC);
       if (!more) break;
     }
   }
 
-  const float inf = __int_as_float(0x7f800000);
-  for (unsigned m = slowMask; m; m &= m - 1) {
-    const int j = __ffs(m) - 1;
-    const int jw0 = __shfl_sync(kFull, w0, j);
-    const int jw1 = __shfl_sync(kFull, w1, j);
-    const float tD = __shfl_sync(kFull, thrD, j);
-    const float tC = __shfl_sync(kFull, thrC, j);
-    uint4* dst = reinterpret_cast<uint4*>(smemWarp + j * G.stride);
-    const int u0 = jw0 + a;
-    const bool in0 = (a < G.WIN) && u0 >= 0 && u0 < M.rows;
-    const int b0 = wrap_add(u0, M.start0, M.rows);
-    for (int k = 0; k < G.nIter; ++k) {
-      const int b = k * G.pack + h;
-      const int u1 = jw1 + b;
-      const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
-      const int b1 = wrap_add(u1, M.start1, M.cols);
-      float v = __int_as_float(0x7fc00000);
-      if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
-      const uint32_t bD = __ballot_sync(kFull, v < tD);
-      const uint32_t bC = __ballot_sync(kFull, v < tC);
-      const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
-      if (lane == 0) dst[k] = make_uint4(bD, bC, bF, 0u);
+  stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ TMA staging
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// One 2-D tiled TMA load: box (boxDim of the tensor map) at element coordinates (c0 = row, c1 = col) of the
+// column-major layer -> shared memory; completion is signalled on the mbarrier as transferred bytes.  Elements
+// outside the tensor are filled with NaN by the tensor map (CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA).
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// Box (floats in shared memory) -> D/C/F bit-planes.  Load iteration k of the window is box word k*32 + lane: a
+// linear, conflict-free read.  Unrolled by 4 without per-iteration predicates (every ballot is a convergence
+// point, so a predicated body would cost a branch pair per iteration).
+__device__ __forceinline__ void convert_one(uint32_t src, uint32_t dst, int lane, float tD, float tC) {
+  const float v = lds_f32(src);
+  const uint32_t bD = __ballot_sync(kFull, v < tD);
+  const uint32_t bC = __ballot_sync(kFull, v < tC);
+  const uint32_t bF = __ballot_sync(kFull, fabsf(v) < __int_as_float(0x7f800000));
+  if (lane == 0) sts_v4(dst, bD, bC, bF, 0u);
+}
+__device__ __forceinline__ void convert_box(int nIter, uint32_t src, uint32_t dst, int lane, float tD, float tC) {
+  int k = 0;
+  for (; k + 4 <= nIter; k += 4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      convert_one(src + static_cast<uint32_t>(k + i) * 128u, dst + static_cast<uint32_t>(k + i) * 16u, lane, tD, tC);
+  }
+  for (; k < nIter; ++k) convert_one(src + static_cast<uint32_t>(k) * 128u, dst + static_cast<uint32_t>(k) * 16u, lane, tD, tC);
+}
+
+struct TmaWarp {       // per-warp TMA staging state (lives in registers across the whole plan)
+  uint32_t bar[2];     // shared-space addresses of the two mbarriers (one per round buffer)
+  uint32_t boxAddr;    // shared-space address of the warp's box buffers: [2][tmaB][boxWords] floats
+  uint32_t parity[2];
+};
+
+// TMA variant of stage_windows (plan_kernel): every eligible window is fetched by ONE cp.async.bulk.tensor (issued by
+// an elected lane with the window's broadcast coordinates) into the warp's shared-memory box buffers,
+// two rounds of tmaB windows in flight (mbarrier per buffer).  The box lands as [col][row] floats, i.e. exactly
+// the order in which the cooperative reduction wants it: load iteration k of the window is box word k*32 + lane,
+// a conflict-free linear read.  Eligible = the window does not wrap around the circular-buffer seam and, when the
+// start index is non-zero, lies inside the map (with start index (0,0) buffer coordinates equal map coordinates,
+// so the tensor map's NaN out-of-bounds fill IS grid_map's "cell outside the map is not visited").
+__device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev& G, const void* tmap, TmaWarp& T,
+                                                  uint32_t smemWarp, int lane, bool has_window, int w0, int w1,
+                                                  float thrD, float thrC) {
+  const int RP = 1 << G.rpShift;
+  const int colsCovered = G.nIter * G.pack;
+  const bool start0 = (M.start0 == 0) && (M.start1 == 0);
+  // a window with no cell inside the map stages as all-"not visited": the owning lane just clears its planes
+  const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -RP || w1 <= -colsCovered);
+  int c0 = w0, c1 = w1;
+  bool elig = has_window && !empty;
+  if (!start0) {
+    c0 = w0 + M.start0;
+    c1 = w1 + M.start1;
+    if (c0 >= M.rows) c0 -= M.rows;
+    if (c1 >= M.cols) c1 -= M.cols;
+    elig = elig && w0 >= 0 && w1 >= 0 && w0 <= M.rows - RP && w1 <= M.cols - colsCovered && c0 <= M.rows - RP &&
+           c1 <= M.cols - colsCovered;
+  }
+  const unsigned fastMask = __ballot_sync(kFull, elig);
+  const unsigned slowMask = __ballot_sync(kFull, has_window && !elig && !empty);
+  const unsigned act = __ballot_sync(kFull, has_window);
+  if (act == 0) {
+    __syncwarp();
+    return;
+  }
+  const int first = __ffs(act) - 1;
+  const float tD0 = __shfl_sync(kFull, thrD, first), tC0 = __shfl_sync(kFull, thrC, first);
+  const bool uni = __all_sync(kFull, !has_window || (thrD == tD0 && thrC == tC0));
+  __syncwarp();  // every lane is done reading the planes of the previous leg/cycle
+  if (empty) {
+    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
+    for (int k = 0; k < G.nIter; ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
+  }
+
+  const int nFast = __popc(fastMask);
+  if (nFast) {
+    const int B = 1 << G.tmaBShift;
+    const int nRounds = (nFast + B - 1) >> G.tmaBShift;
+    const uint32_t boxBytes = static_cast<uint32_t>(G.boxWords) * 4u;
+    const float inf = __int_as_float(0x7f800000);
+    unsigned remIssue = fastMask;
+    // UTMALDG is a warp-uniform instruction: ONE elected lane issues each box with broadcast coordinates.
+    auto issue = [&](int r) {
+      const int buf = r & 1;
+      const int cnt = min(B, nFast - (r << G.tmaBShift));
+      if (lane == 0) mbar_expect_tx(T.bar[buf], static_cast<uint32_t>(cnt) * boxBytes);
+      uint32_t dstBox = T.boxAddr + static_cast<uint32_t>(buf << G.tmaBShift) * boxBytes;
+      for (int sidx = 0; sidx < cnt; ++sidx) {
+        const int j = __ffs(remIssue) - 1;
+        remIssue &= remIssue - 1;
+        const int jc0 = __shfl_sync(kFull, c0, j), jc1 = __shfl_sync(kFull, c1, j);
+        if (lane == 0) tma_load_box(dstBox, tmap, jc0, jc1, T.bar[buf]);
+        dstBox += boxBytes;
+      }
+    };
+    // the box buffers were last read through the generic proxy; order those reads before the async-proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue(0);
+    unsigned rem = fastMask;
+    for (int r = 0; r < nRounds; ++r) {
+      const int buf = r & 1;
+      if (r + 1 < nRounds) issue(r + 1);
+      while (!mbar_try_wait(T.bar[buf], T.parity[buf])) {
+      }
+      T.parity[buf] ^= 1u;
+      const int cnt = min(B, nFast - (r << G.tmaBShift));
+      uint32_t src = T.boxAddr + static_cast<uint32_t>(buf << G.tmaBShift) * boxBytes + static_cast<uint32_t>(lane) * 4u;
+      for (int sidx = 0; sidx < cnt; ++sidx) {
+        const int j = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const float tD = uni ? tD0 : __shfl_sync(kFull, thrD, j);
+        const float tC = uni ? tC0 : __shfl_sync(kFull, thrC, j);
+        const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
+        convert_box(G.nIter, src, dst, lane, tD, tC);
+        src += boxBytes;
+      }
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
+  if (slowMask) stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
   __syncwarp();
 }
 
@@ -298,7 +468,7 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
 
   // window coordinates of the submap inside the staged planes
   const int a0 = tl0 - w0, a1 = br0 - w0, c0 = tl1 - w1, c1 = br1 - w1;
-  if (a0 < 0 || c0 < 0 || a1 >= G.WIN || c1 >= G.WIN || n0 < 1 || n1 < 1 || n0 > 32) {
+  if (a0 < 0 || c0 < 0 || a1 >= min(32, G.WIN + 3) || c1 >= G.WIN || n0 < 1 || n1 < 1 || n0 > 32) {
     err |= kErrWindow;
     return o;
   }
@@ -404,7 +574,7 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
       if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
       ++visited;
       const int a = u0 - w0, b = u1 - w1;
-      if (a < 0 || b < 0 || a >= G.WIN || b >= G.WIN) {
+      if (a < 0 || b < 0 || a >= min(32, G.WIN + 3) || b >= G.WIN) {
         err |= kErrWindow;
         continue;
       }
@@ -420,11 +590,14 @@ __device__ __forceinline__ void box_masks(const MapDev& M, const GeoDev& G, cons
                                           uint32_t& rowsBox, uint32_t& colsBox) {
   rowsBox = 0;
   colsBox = 0;
-  for (int a = 0; a < G.WIN; ++a) {
+  const int nr = min(32, G.WIN + 3);  // the TMA path shifts the window origin down by up to 3 rows
+  for (int a = 0; a < nr; ++a) {
     const double X = pos_axis(M.fcx, M.res, w0 + a);
     if (X >= bx.xlo && X < bx.xhi) rowsBox |= 1u << a;
-    const double Y = pos_axis(M.fcy, M.res, w1 + a);
-    if (Y >= bx.ylo && Y < bx.yhi) colsBox |= 1u << a;
+    if (a < G.WIN) {
+      const double Y = pos_axis(M.fcy, M.res, w1 + a);
+      if (Y >= bx.ylo && Y < bx.yhi) colsBox |= 1u << a;
+    }
   }
 }
 
@@ -479,22 +652,22 @@ __device__ __forceinline__ void spiral_entry(const uint16_t* sSpiral, int k, int
 //      valid cell in spiral order and the scan stops at the first 32-block that has one.
 // Handles wrap_correct mode, and faithful mode when the start index is (0,0) (identical there).
 __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
-                                                 const uint32_t* smemWarp, int lane, bool need, int uc0, int uc1,
-                                                 double cx, double cy, double R2, uint32_t rowsBox, uint32_t colsBox,
-                                                 bool& found, int& fq0, int& fq1) {
+                                                 uint32_t smemWarp, int lane, bool need, int uc0, int uc1,
+                                                 int w0, double cx, double cy, double R2, uint32_t rowsBox,
+                                                 uint32_t colsBox, bool& found, int& fq0, int& fq1) {
   const unsigned needMask = __ballot_sync(kFull, need);
-  const uint32_t winMask = G.WIN >= 32 ? 0xffffffffu : ((1u << G.WIN) - 1u);
   for (unsigned m = needMask; m; m &= m - 1) {
     const int j = __ffs(m) - 1;
     const int juc0 = __shfl_sync(kFull, uc0, j), juc1 = __shfl_sync(kFull, uc1, j);
+    const int ha = juc0 - __shfl_sync(kFull, w0, j);  // window row of the centre cell (HW, plus the TMA alignment shift)
     const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
-    const Planes pj{smemWarp + j * G.stride, G.pack, G.rpShift};
+    const Planes pj{smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift};
     // 1. column masks (lane = window column)
     uint32_t bad = 0;
     if (lane < G.WIN) {
       const uint32_t F = pj.col(PL_F, lane), C = pj.col(PL_C, lane);
       const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
-      bad = F & (C | ~box) & winMask;
+      bad = F & (C | ~box);
     }
     uint32_t dil = 0;
     for (int s = 0; s < G.nSten; ++s) {
@@ -506,7 +679,7 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
     }
     // candidate cells outside the map: rows (bits) and this lane's column
     {
-      const int lo = max(0, G.HW - juc0), hi = min(G.WIN - 1, M.rows - 1 - juc0 + G.HW);  // window rows inside the map
+      const int lo = max(0, ha - juc0), hi = min(31, M.rows - 1 - juc0 + ha);  // window rows inside the map
       uint32_t rowsIn = 0;
       if (hi >= lo) rowsIn = (hi - lo >= 31 ? 0xffffffffu : ((1u << (hi - lo + 1)) - 1u)) << lo;
       const int q1 = juc1 + lane - G.HW;
@@ -521,7 +694,7 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
       bool cand = k < G.nCand;
       int d0, d1;
       spiral_entry(sSpiral, cand ? k : 0, d0, d1);
-      const int qa = d0 + G.HW, qb = d1 + G.HW;
+      const int qa = d0 + ha, qb = d1 + G.HW;
       const uint32_t e = __shfl_sync(kFull, dil, qb);
       cand = cand && !((e >> qa) & 1u);
       if (base + 32 > G.lastTwoStart) {  // rings nRings-1, nRings: distance filter (uniform branch)
@@ -555,9 +728,9 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
 // the centre index is the BUFFER index, ring neighbours are taken in buffer space without wrapping, and the
 // distance filter evaluates positions as if the start index were 0.  Per-lane scalar loop (compatibility path).
 __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
-                                                  const Planes& pl, float thrC, int uc0, int uc1, double cx, double cy,
-                                                  double R2, const Box& bx, uint32_t rowsBox, uint32_t colsBox,
-                                                  bool& found, int& fq0, int& fq1) {
+                                                  const Planes& pl, float thrC, int uc0, int uc1, int w0, double cx,
+                                                  double cy, double R2, const Box& bx, uint32_t rowsBox,
+                                                  uint32_t colsBox, bool& found, int& fq0, int& fq1) {
   int cb0 = uc0 + M.start0, cb1 = uc1 + M.start1;  // getBufferIndexFromIndex + wrapIndexToRange
   if (cb0 < 0) cb0 += ((-cb0 / M.rows) + 1) * M.rows;
   cb0 %= M.rows;
@@ -577,7 +750,7 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
     if (q1 < 0) q1 += M.cols;
     const bool far = (q0 != uc0 + d0) || (q1 != uc1 + d1);
     const bool good = far ? candidate_slow(M, G, thrC, q0, q1, bx.xlo, bx.xhi, bx.ylo, bx.yhi)
-                          : candidate_on_planes(G, pl, d0 + G.HW, d1 + G.HW, rowsBox, colsBox);
+                          : candidate_on_planes(G, pl, d0 + (uc0 - w0), d1 + G.HW, rowsBox, colsBox);
     if (good) {
       found = true;
       fq0 = q0;
@@ -591,20 +764,19 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
 // checkCandidateFoothold (:2085-2114) over grid_map::SpiralIterator with checkCirclePolygonFoothold (:2117-2163).
 // WARP-COLLECTIVE: every lane of the warp must call it (inactive lanes pass active = false).
 // (cx,cy): search centre; (rx,ry): centre of the search rectangle; (uc0,uc1): raw unwrapped index of the centre;
-// the staged window origin is (uc0-HW, uc1-HW).
+// (w0,w1): unwrapped origin of the staged window (uc-HW, minus the TMA row-alignment shift).
 template <bool DEFAULT_ONLY>
 __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P,
-                                                   const uint16_t* sSpiral, const uint32_t* smemWarp, int lane,
-                                                   bool active, int uc0, int uc1, double cx, double cy, double rx,
-                                                   double ry, const DiscWin& dw, unsigned& err) {
+                                                   const uint16_t* sSpiral, uint32_t smemWarp, int lane,
+                                                   bool active, int uc0, int uc1, int w0, int w1, double cx, double cy,
+                                                   double rx, double ry, const DiscWin& dw, unsigned& err) {
   NominalOut o;
   o.x = cx;  // FP.cpp:2016-2017
   o.y = cy;
   o.ok = false;
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
-  const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
-  const Planes pl{smemWarp + lane * G.stride, G.pack, G.rpShift};
+  const Planes pl{smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift};
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
                                in_map(M, uc0, uc1);
@@ -625,10 +797,10 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
   }
   bool found = false;
   int fq0 = 0, fq1 = 0;
-  spiral_scan_coop(M, G, sSpiral, smemWarp, lane, need && !faithful, uc0, uc1, cx, cy, P.R2, rowsBox, colsBox, found,
-                   fq0, fq1);
+  spiral_scan_coop(M, G, sSpiral, smemWarp, lane, need && !faithful, uc0, uc1, w0, cx, cy, P.R2, rowsBox, colsBox,
+                   found, fq0, fq1);
   if (need && faithful)
-    spiral_scan_faithful(M, G, sSpiral, pl, P.thrC, uc0, uc1, cx, cy, P.R2, bx, rowsBox, colsBox, found, fq0, fq1);
+    spiral_scan_faithful(M, G, sSpiral, pl, P.thrC, uc0, uc1, w0, cx, cy, P.R2, bx, rowsBox, colsBox, found, fq0, fq1);
   if (found) {
     o.ok = true;
     o.x = pos_axis(M.fcx, M.res, fq0);  // gridmap.getPosition(index) (FP.cpp:2105-2107)

@@ -1,5 +1,6 @@
 // Host <-> kernel argument structs and launchers shared by fhp_kernels.cu and fhp_capi.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "fhp_types.h"
@@ -9,6 +10,7 @@ namespace fhp {
 constexpr int kPlanThreads = 128;
 
 struct PlanArgs {
+  alignas(64) CUtensorMap tmap;  // traversability layer, box = one staged window (valid iff G.useTma)
   MapDev M;
   const ParDev* pars;
   int nPars;

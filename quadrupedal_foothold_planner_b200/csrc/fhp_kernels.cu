@@ -65,11 +65,23 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 template <bool WANT_CEN>
 __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem_raw[];
+  // 128-byte aligned base (TMA destinations must be 128-byte aligned; the launcher adds the slack)
+  uint32_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) / 4u;
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
-  const uint16_t* sSpiral = load_spiral_table(G, smem);
-  uint32_t* sw = smem + G.spiralWords + warpInBlock * 32 * G.stride;
+  TmaWarp T;
+  T.bar[0] = smem_u32(smem + G.mbarOff + warpInBlock * 4);
+  T.bar[1] = T.bar[0] + 8;
+  T.boxAddr = smem_u32(smem + G.boxOff) + static_cast<uint32_t>(warpInBlock * 2 * G.tmaB * G.boxWords) * 4u;
+  T.parity[0] = T.parity[1] = 0;
+  if (G.useTma && lane == 0) {
+    mbar_init(T.bar[0], 1);
+    mbar_init(T.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint16_t* sSpiral = load_spiral_table(G, smem);  // ends with __syncthreads (also publishes the mbarriers)
+  const uint32_t sw = smem_u32(smem + G.spiralWords + warpInBlock * 32 * G.stride);
   const long long gwarp = static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock;
   const long long q = gwarp * 8 + (lane >> 2);
   const int f = lane & 3;           // RF,RH,LH,LF
@@ -125,8 +137,17 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
 
     // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
     const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
-    const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
-    stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
+    int w0 = uc0 - G.HW;
+    const int w1 = uc1 - G.HW;
+    if (G.useTma) {  // TMA needs the box's innermost (row) coordinate 16-byte aligned: shift the origin down to a
+      int c0 = w0 + M.start0;  // multiple of 4 buffer rows (rows % 4 == 0, so the wrap keeps the alignment)
+      if (c0 >= M.rows) c0 -= M.rows;
+      w0 -= c0 & 3;
+    }
+    if (G.useTma)
+      stage_windows_tma(M, G, &A.tmap, T, sw, lane, active, w0, w1, thrD, thrC);
+    else
+      stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
 
     CentroidOut co;
     co.x = co.y = 0.0;
@@ -134,12 +155,12 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     double nz = 0.0, cz = 0.0;
     DiscWin dw = {0, 0, -1, -1};
     if (active) {
-      Planes pl{sw + lane * G.stride, G.pack, G.rpShift};
+      Planes pl{sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift};
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
       dw = disc_window(M, px, py, P.r);
     }
     const NominalOut no =
-        nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, px, py, rx, ry, dw, err);  // FP.cpp:863-903
+        nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
     const bool ok = no.ok;
     if (active) {
       if (ok) nz = static_cast<double>(mean_height(M, P, px, py, dw));  // at the CENTRE (FP.cpp:2029)
@@ -193,7 +214,7 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
   const uint16_t* sSpiral = load_spiral_table(G, smem);
-  uint32_t* sw = smem + G.spiralWords + warpInBlock * 32 * G.stride;
+  const uint32_t sw = smem_u32(smem + G.spiralWords + warpInBlock * 32 * G.stride);
   const long long i = (static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock) * 32 + lane;
   const bool active = i < A.n;
   const MapDev& M = A.M;
@@ -215,15 +236,15 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
   const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
-  Planes pl{sw + lane * G.stride, G.pack, G.rpShift};
+  Planes pl{sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift};
   if (MODE == 0 || MODE == 3) {
     DiscWin dw = {0, 0, -1, -1};
     if (active) dw = disc_window(M, px, py, P.r);
     NominalOut no;
     if (MODE == 0)
-      no = nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, px, py, rx, ry, dw, err);
+      no = nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
     else
-      no = nominal_eval<true>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, px, py, rx, ry, dw, err);
+      no = nominal_eval<true>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
     if (active) {
       if (MODE == 0) {
         double z = 0.0;
@@ -252,7 +273,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
   const int warps = kPlanThreads / 32;
   const long long nWarps = (A.nq + 7) / 8;
   const long long blocks = (nWarps + warps - 1) / warps;
-  const size_t shm = (static_cast<size_t>(G.spiralWords) + static_cast<size_t>(warps) * 32 * G.stride) * sizeof(uint32_t);
+  const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = wantCen ? cudaFuncSetAttribute(plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(shm))

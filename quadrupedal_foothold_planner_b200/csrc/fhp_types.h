@@ -36,6 +36,15 @@ struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int nIter;     // ceil(WIN / pack) = words per bit-plane
   int stride;    // shared-memory words per query (4 per load iteration: D, C, F, pad)
   int spiralWords;  // 32-bit words reserved at the start of shared memory for the spiral table (16-byte multiple)
+  // TMA staging (plan_kernel): each window is fetched as one 2-D box of boxWords floats (32 rows*cols per load
+  // iteration) into shared memory; tmaB windows per round, two rounds in flight per warp.
+  int useTma;       // 1: the tensor map in the kernel arguments is valid for this map/geometry
+  int tmaB;         // windows per TMA round (power of two)
+  int tmaBShift;    // log2(tmaB)
+  int boxWords;     // 32 * nIter
+  int mbarOff;      // word offset of the per-warp mbarrier pairs (from the 128-byte aligned shared base)
+  int boxOff;       // word offset of the per-warp box buffers (multiple of 32 words)
+  int smemWords;    // total dynamic shared memory words for a kPlanThreads block (without alignment slack)
   int nCand;     // spiral table length
   int lastTwoStart;  // first rank that belongs to ring nRings-1 (distance-filtered rings)
   int nSten;

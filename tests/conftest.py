@@ -19,10 +19,17 @@ def oracle():
     return oracle_binding
 
 
-@pytest.fixture(scope="session")
-def fhp():
-    """One libfhp context on cuda:0 (GPU tests only)."""
+@pytest.fixture(scope="session", params=["tma", "ldg"])
+def fhp(request):
+    """One libfhp context on cuda:0 per window-staging path (GPU tests only): "tma" = 2-D TMA box loads (default),
+    "ldg" = FHP_DISABLE_TMA=1, the pipelined LDG path that also serves maps TMA cannot describe."""
     from quadrupedal_foothold_planner_b200.planner import Fhp
+    old = os.environ.get("FHP_DISABLE_TMA")
+    os.environ["FHP_DISABLE_TMA"] = "1" if request.param == "ldg" else "0"
     ctx = Fhp(0)
+    if old is None:
+        del os.environ["FHP_DISABLE_TMA"]
+    else:
+        os.environ["FHP_DISABLE_TMA"] = old
     yield ctx
     ctx.close()
