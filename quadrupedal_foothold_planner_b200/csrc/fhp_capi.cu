@@ -44,6 +44,7 @@ struct DevBuf {
 struct fhp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second lane of the host-buffer pipeline in fhp_plan
   mutable std::string err;
   std::mutex mu;  // one plan at a time per ctx (the reference class is not re-entrant either)
   // map
@@ -92,6 +93,7 @@ int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
   M.start0 = d->start_row;
   M.start1 = d->start_col;
   M.res = d->resolution;
+  M.rinv = 1.0 / d->resolution;
   M.lenx = d->length_x;
   M.leny = d->length_y;
   M.posx = d->pos_x;
@@ -404,6 +406,7 @@ int fhp_create(int device, fhp_ctx** out) {
   const char* dt = std::getenv("FHP_DISABLE_TMA");
   ctx->disableTma = dt && dt[0] == '1';
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -422,6 +425,7 @@ void fhp_destroy(fhp_ctx* ctx) {
                     &ctx->dD})
     b->release();
   cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
 }
 
@@ -480,13 +484,9 @@ const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* name) {
   return nullptr;
 }
 
-static int plan_common(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,
-                       int64_t n_queries, int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC,
-                       fhp_query_status* d_st, cudaStream_t s) {
-  int rc = prepare_params(ctx, params, n_params, s);
-  if (rc != FHP_OK) return rc;
-  rc = ensure_err_word(ctx);
-  if (rc != FHP_OK) return rc;
+static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_queries, int64_t n_queries,
+                       int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC, fhp_query_status* d_st,
+                       cudaStream_t s) {
   PlanArgs A;
   A.tmap = ctx->tmapTrav;
   A.M = ctx->M;
@@ -502,6 +502,16 @@ static int plan_common(fhp_ctx* ctx, const fhp_params* params, int32_t n_params,
   CU(launch_plan(A, ctx->G, d_outC != nullptr, s));
   if (n_queries > 0) ctx->launches += 1;
   return FHP_OK;
+}
+
+static int plan_common(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,
+                       int64_t n_queries, int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC,
+                       fhp_query_status* d_st, cudaStream_t s) {
+  int rc = prepare_params(ctx, params, n_params, s);
+  if (rc != FHP_OK) return rc;
+  rc = ensure_err_word(ctx);
+  if (rc != FHP_OK) return rc;
+  return plan_launch(ctx, n_params, d_queries, n_queries, gait_cycles, d_outN, d_outC, d_st, s);
 }
 
 int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
@@ -524,16 +534,34 @@ int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp
   CU(ctx->dOutN.reserve(oB));
   if (out_centroid) CU(ctx->dOutC.reserve(oB));
   CU(ctx->dSt.reserve(sB));
-  CU(cudaMemcpyAsync(ctx->dQ.p, queries, qB, cudaMemcpyHostToDevice, s));
-  int rc = plan_common(ctx, params, n_params, static_cast<const fhp_query*>(ctx->dQ.p), n_queries, gait_cycles,
-                       static_cast<fhp_foothold*>(ctx->dOutN.p),
-                       out_centroid ? static_cast<fhp_foothold*>(ctx->dOutC.p) : nullptr,
-                       static_cast<fhp_query_status*>(ctx->dSt.p), s);
+  // Host-buffer pipeline: the batch is cut into chunks that alternate between two streams, so the kernel of
+  // chunk i+1 runs while the response rows of chunk i travel back over PCIe (the D2H of the rows is the
+  // longest leg of a large batch).  Small batches are a single chunk = one launch.
+  int rc = prepare_params(ctx, params, n_params, s);
   if (rc != FHP_OK) return rc;
-  CU(cudaMemcpyAsync(out_nominal, ctx->dOutN.p, oB, cudaMemcpyDeviceToHost, s));
-  if (out_centroid) CU(cudaMemcpyAsync(out_centroid, ctx->dOutC.p, oB, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(status, ctx->dSt.p, sB, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  rc = ensure_err_word(ctx);
+  if (rc != FHP_OK) return rc;
+  const int64_t wave = plan_wave_queries(ctx->G, out_centroid != nullptr);
+  int64_t nChunks = (n_queries + wave - 1) / wave;  // wave-sized chunks: a partial wave costs as much as a full one
+  if (nChunks < 1) nChunks = 1;
+  const int64_t per = ((n_queries + nChunks - 1) / nChunks + 31) / 32 * 32;  // whole blocks per chunk
+  const fhp_query* dq = static_cast<const fhp_query*>(ctx->dQ.p);
+  fhp_foothold* dN = static_cast<fhp_foothold*>(ctx->dOutN.p);
+  fhp_foothold* dC = out_centroid ? static_cast<fhp_foothold*>(ctx->dOutC.p) : nullptr;
+  fhp_query_status* dS = static_cast<fhp_query_status*>(ctx->dSt.p);
+  int lane = 0;
+  for (int64_t lo = 0; lo < n_queries; lo += per, lane ^= 1) {
+    const int64_t n = std::min<int64_t>(per, n_queries - lo);
+    cudaStream_t cs = lane ? ctx->stream2 : ctx->stream;
+    CU(cudaMemcpyAsync(const_cast<fhp_query*>(dq) + lo, queries + lo, sizeof(fhp_query) * n, cudaMemcpyHostToDevice, cs));
+    rc = plan_launch(ctx, n_params, dq + lo, n, gait_cycles, dN + lo * R, dC ? dC + lo * R : nullptr, dS + lo, cs);
+    if (rc != FHP_OK) return rc;
+    CU(cudaMemcpyAsync(out_nominal + lo * R, dN + lo * R, sizeof(fhp_foothold) * R * n, cudaMemcpyDeviceToHost, cs));
+    if (dC) CU(cudaMemcpyAsync(out_centroid + lo * R, dC + lo * R, sizeof(fhp_foothold) * R * n, cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(status + lo, dS + lo, sizeof(fhp_query_status) * n, cudaMemcpyDeviceToHost, cs));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream2));
   return check_dev_err(ctx);
 }
 
@@ -558,6 +586,7 @@ int fhp_synchronize(fhp_ctx* ctx) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream2));
   if (ctx->pendingErrCheck && ctx->dErr.p) {
     ctx->pendingErrCheck = 0;
     CU(cudaDeviceSynchronize());

@@ -37,13 +37,27 @@ __device__ __forceinline__ double bound_axis(double p, double len, double mp, do
   }
   return (shifted + mp) - half;
 }
-// getIndexFromPosition without the start-index wrap: (int)(-(((p - 0.5*len) - mapPos)/res))
-__device__ __forceinline__ int raw_index_axis(double p, double half, double mp, double res) {
-  double iv = ((p - half) - mp) / res;
+// IEEE double division as ONE out-of-line subroutine: the inline expansion is ~35 instructions per site, and the
+// instruction footprint of the scalar phases is what limits this kernel (profiles/).
+__device__ __noinline__ double div_rn(double a, double b) { return a / b; }
+
+// getIndexFromPosition without the start-index wrap: (int)(-(((p - 0.5*len) - mapPos)/res)).
+// Fast path: multiply by the correctly rounded reciprocal; the product differs from the IEEE quotient by at most a
+// few ulp, so the truncated integer can only differ when the value sits within that distance of an integer —
+// then (and only then) the exact division decides.  `rinv` = 1/res (MapDev::rinv).
+__device__ __forceinline__ int raw_index_axis(double p, double half, double mp, double res, double rinv) {
+  const double x = (p - half) - mp;
+  double t = -(x * rinv);
   // (int) of a NaN / out-of-int-range double is UB upstream (x86 cvttsd2si yields INT_MIN).  Policy shared with the
-  // oracle: every such index becomes -2^30 — far outside any map, and index +- window never overflows.
-  if (!(fabs(iv) < 1073741824.0)) return -1073741824;
-  return static_cast<int>(-iv);
+  // CPU restatement: every such index becomes -2^30 — far outside any map, and index +- window never overflows.
+  if (!(fabs(t) < 1073741000.0)) {
+    t = -div_rn(x, res);
+    if (!(fabs(t) < 1073741824.0)) return -1073741824;
+    return static_cast<int>(t);
+  }
+  const double fr = t - rint(t);
+  if (fabs(fr) < 1e-6) t = -div_rn(x, res);  // |t| < 2^30: quotient error < 2^30 * 4 ulp ~ 1e-6 is a safe band
+  return static_cast<int>(t);
 }
 // checkIfPositionWithinMap for one axis
 __device__ __forceinline__ bool within_axis(double p, double len, double mp, double half) {
@@ -71,7 +85,7 @@ __device__ __forceinline__ void cell_of_position(const MapDev& M, double x, doub
     row = col = -1;
     return;
   }
-  int u0 = raw_index_axis(x, M.halfx, M.posx, M.res), u1 = raw_index_axis(y, M.halfy, M.posy, M.res);
+  int u0 = raw_index_axis(x, M.halfx, M.posx, M.res, M.rinv), u1 = raw_index_axis(y, M.halfy, M.posy, M.res, M.rinv);
   if (!in_map(M, u0, u1)) {  // unreachable for finite geometry; keep the contract total
     row = col = -1;
     return;
@@ -99,20 +113,23 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // ------------------------------------------------------------------------------------------------ bit planes
-struct Planes {  // view of one query's staged window in shared memory (shared-space byte address)
-  uint32_t w;
+struct Planes {  // view of one query's staged window in shared memory
+  const uint32_t* w;
   int pack, rpShift;
+  // from a shared-space byte address: plain loads (the compiler may keep words in registers between barriers)
+  __device__ __forceinline__ Planes(uint32_t addr, int pack_, int rpShift_)
+      : w(static_cast<const uint32_t*>(__cvta_shared_to_generic(addr))), pack(pack_), rpShift(rpShift_) {}
   __device__ __forceinline__ uint32_t col(int plane, int b) const {  // bits over window rows a for column b
-    if (pack == 1) return lds_u32(w + static_cast<uint32_t>(b * 4 + plane) * 4u);
+    if (pack == 1) return w[b * 4 + plane];
     int k, sh;
     if (pack == 2) {
       k = b >> 1;
       sh = (b & 1) << 4;
-      return (lds_u32(w + static_cast<uint32_t>(k * 4 + plane) * 4u) >> sh) & 0xffffu;
+      return (w[k * 4 + plane] >> sh) & 0xffffu;
     }
     k = b >> 2;
     sh = (b & 3) << 3;
-    return (lds_u32(w + static_cast<uint32_t>(k * 4 + plane) * 4u) >> sh) & 0xffu;
+    return (w[k * 4 + plane] >> sh) & 0xffu;
   }
   __device__ __forceinline__ bool bit(int plane, int a, int b) const { return (col(plane, b) >> a) & 1u; }
 };
@@ -288,7 +305,10 @@ __device__ __forceinline__ void convert_box(int nIter, uint32_t src, uint32_t ds
     for (int i = 0; i < 4; ++i)
       convert_one(src + static_cast<uint32_t>(k + i) * 128u, dst + static_cast<uint32_t>(k + i) * 16u, lane, tD, tC);
   }
-  for (; k < nIter; ++k) convert_one(src + static_cast<uint32_t>(k) * 128u, dst + static_cast<uint32_t>(k) * 16u, lane, tD, tC);
+  const int rem = nIter - k;  // 0..3, straight-line (a loop would add a divergence check per ballot)
+  if (rem >= 1) convert_one(src + static_cast<uint32_t>(k) * 128u, dst + static_cast<uint32_t>(k) * 16u, lane, tD, tC);
+  if (rem >= 2) convert_one(src + static_cast<uint32_t>(k + 1) * 128u, dst + static_cast<uint32_t>(k + 1) * 16u, lane, tD, tC);
+  if (rem >= 3) convert_one(src + static_cast<uint32_t>(k + 2) * 128u, dst + static_cast<uint32_t>(k + 2) * 16u, lane, tD, tC);
 }
 
 struct TmaWarp {       // per-warp TMA staging state (lives in registers across the whole plan)
@@ -361,11 +381,11 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
     };
     // the box buffers were last read through the generic proxy; order those reads before the async-proxy writes
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue(0);
     unsigned rem = fastMask;
-    for (int r = 0; r < nRounds; ++r) {
-      const int buf = r & 1;
+    for (int r = -1; r < nRounds; ++r) {  // round r+1 is issued before round r is reduced (one copy of each body)
       if (r + 1 < nRounds) issue(r + 1);
+      if (r < 0) continue;
+      const int buf = r & 1;
       while (!mbar_try_wait(T.bar[buf], T.parity[buf])) {
       }
       T.parity[buf] ^= 1u;
@@ -376,8 +396,7 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
         rem &= rem - 1;
         const float tD = uni ? tD0 : __shfl_sync(kFull, thrD, j);
         const float tC = uni ? tC0 : __shfl_sync(kFull, thrC, j);
-        const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
-        convert_box(G.nIter, src, dst, lane, tD, tC);
+        convert_box(G.nIter, src, smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, lane, tD, tC);
         src += boxBytes;
       }
       __syncwarp();
@@ -396,17 +415,17 @@ __device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, doubl
   DiscWin d;
   const double tlx = bound_axis(cx + r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + r, M.leny, M.posy, M.halfy);
   const double brx = bound_axis(cx - r, M.lenx, M.posx, M.halfx), bry = bound_axis(cy - r, M.leny, M.posy, M.halfy);
-  d.tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res);
-  d.tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res);
-  d.br0 = raw_index_axis(brx, M.halfx, M.posx, M.res);
-  d.br1 = raw_index_axis(bry, M.halfy, M.posy, M.res);
+  d.tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res, M.rinv);
+  d.tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res, M.rinv);
+  d.br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv);
+  d.br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
   return d;
 }
 
 // ------------------------------------------------------------------------------------------------ a9 mean height
 // FootholdPlanner::getFootholdMeanHeight (FP.cpp:2520-2554) over grid_map::CircleIterator (row-major over the
 // bounded window in unwrapped index space, cells with squared distance <= r^2).
-__device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw) {
+__device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw) {
   const int tl0 = dw.tl0, tl1 = dw.tl1, br0 = dw.br0, br1 = dw.br1;
   float iHeight = 0.0f, meanHeight = 0.0f;
   int i = 0;
@@ -452,11 +471,11 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
   const double tlx = bound_axis(px + 0.5 * P.rectLx, M.lenx, M.posx, M.halfx);
   const double tly = bound_axis(py + 0.5 * P.rectLy, M.leny, M.posy, M.halfy);
   if (!(within_axis(tlx, M.lenx, M.posx, M.halfx) && within_axis(tly, M.leny, M.posy, M.halfy))) return o;
-  const int tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res), tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res);
+  const int tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res, M.rinv), tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res, M.rinv);
   const double brx = bound_axis(px - 0.5 * P.rectLx, M.lenx, M.posx, M.halfx);
   const double bry = bound_axis(py - 0.5 * P.rectLy, M.leny, M.posy, M.halfy);
   if (!(within_axis(brx, M.lenx, M.posx, M.halfx) && within_axis(bry, M.leny, M.posy, M.halfy))) return o;
-  const int br0 = raw_index_axis(brx, M.halfx, M.posx, M.res), br1 = raw_index_axis(bry, M.halfy, M.posy, M.res);
+  const int br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv), br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
   if (!in_map(M, tl0, tl1)) return o;  // getPositionFromIndex(topLeftCorner) range check
   const double cornx = pos_axis(M.fcx, M.res, tl0) + 0.5 * M.res;
   const double corny = pos_axis(M.fcy, M.res, tl1) + 0.5 * M.res;
@@ -661,7 +680,7 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
     const int juc0 = __shfl_sync(kFull, uc0, j), juc1 = __shfl_sync(kFull, uc1, j);
     const int ha = juc0 - __shfl_sync(kFull, w0, j);  // window row of the centre cell (HW, plus the TMA alignment shift)
     const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
-    const Planes pj{smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift};
+    const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
     // 1. column masks (lane = window column)
     uint32_t bad = 0;
     if (lane < G.WIN) {
@@ -776,7 +795,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
   o.ok = false;
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
-  const Planes pl{smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift};
+  const Planes pl(smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
                                in_map(M, uc0, uc1);

@@ -37,6 +37,7 @@ struct TaskArgs {
 };
 
 cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream);
+long long plan_wave_queries(const GeoDev& G, bool wantCen);
 cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream_t stream);
 
 }  // namespace fhp

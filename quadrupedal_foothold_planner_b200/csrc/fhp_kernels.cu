@@ -19,7 +19,7 @@ __device__ __forceinline__ void polygon_center(double rfx, double rfy, double rh
   double sum_x = 0, sum_y = 0, sum_s = 0;
   x3 = lhx;
   y3 = lhy;
-  double s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) / 2.0;
+  double s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) * 0.5;  // x/2.0 == x*0.5 exactly
   sum_x += (x1 + x2 + x3) * s;
   sum_y += (y1 + y2 + y3) * s;
   sum_s += s;
@@ -27,12 +27,12 @@ __device__ __forceinline__ void polygon_center(double rfx, double rfy, double rh
   y2 = y3;
   x3 = lfx;
   y3 = lfy;
-  s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) / 2.0;
+  s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) * 0.5;
   sum_x += (x1 + x2 + x3) * s;
   sum_y += (y1 + y2 + y3) * s;
   sum_s += s;
-  cx = sum_x / sum_s / 3.0;
-  cy = sum_y / sum_s / 3.0;
+  cx = div_rn(div_rn(sum_x, sum_s), 3.0);
+  cy = div_rn(div_rn(sum_y, sum_s), 3.0);
 }
 
 __device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y, double z, int row, int col, int foot,
@@ -62,7 +62,7 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
 #endif
-template <bool WANT_CEN>
+template <bool WANT_CEN, bool USE_TMA>
 __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem_raw[];
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
   T.bar[1] = T.bar[0] + 8;
   T.boxAddr = smem_u32(smem + G.boxOff) + static_cast<uint32_t>(warpInBlock * 2 * G.tmaB * G.boxWords) * 4u;
   T.parity[0] = T.parity[1] = 0;
-  if (G.useTma && lane == 0) {
+  if (USE_TMA && lane == 0) {
     mbar_init(T.bar[0], 1);
     mbar_init(T.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,15 +136,15 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     const double rx = (ncx + P.stepLength) + bx, ry = nextY + by;     // nominal-chain next foothold = rectangle centre
 
     // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
-    const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
+    const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
     int w0 = uc0 - G.HW;
     const int w1 = uc1 - G.HW;
-    if (G.useTma) {  // TMA needs the box's innermost (row) coordinate 16-byte aligned: shift the origin down to a
+    if (USE_TMA) {  // TMA needs the box's innermost (row) coordinate 16-byte aligned: shift the origin down to a
       int c0 = w0 + M.start0;  // multiple of 4 buffer rows (rows % 4 == 0, so the wrap keeps the alignment)
       if (c0 >= M.rows) c0 -= M.rows;
       w0 -= c0 & 3;
     }
-    if (G.useTma)
+    if (USE_TMA)
       stage_windows_tma(M, G, &A.tmap, T, sw, lane, active, w0, w1, thrD, thrC);
     else
       stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     double nz = 0.0, cz = 0.0;
     DiscWin dw = {0, 0, -1, -1};
     if (active) {
-      Planes pl{sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift};
+      Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
       dw = disc_window(M, px, py, P.r);
     }
@@ -233,10 +233,10 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     if (active) A.z[i] = mean_height(M, P, px, py);
     return;
   }
-  const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res);
+  const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
   const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
-  Planes pl{sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift};
+  Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
   if (MODE == 0 || MODE == 3) {
     DiscWin dw = {0, 0, -1, -1};
     if (active) dw = disc_window(M, px, py, P.r);
@@ -274,18 +274,31 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
   const long long nWarps = (A.nq + 7) / 8;
   const long long blocks = (nWarps + warps - 1) / warps;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
+  void (*kern)(const PlanArgs, const GeoDev) =
+      G.useTma ? (wantCen ? plan_kernel<true, true> : plan_kernel<false, true>)
+               : (wantCen ? plan_kernel<true, false> : plan_kernel<false, false>);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
-    cudaError_t e = wantCen ? cudaFuncSetAttribute(plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   static_cast<int>(shm))
-                            : cudaFuncSetAttribute(plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   static_cast<int>(shm));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
   }
-  if (wantCen)
-    plan_kernel<true><<<static_cast<unsigned>(blocks), kPlanThreads, shm, stream>>>(A, G);
-  else
-    plan_kernel<false><<<static_cast<unsigned>(blocks), kPlanThreads, shm, stream>>>(A, G);
+  kern<<<static_cast<unsigned>(blocks), kPlanThreads, shm, stream>>>(A, G);
   return cudaGetLastError();
+}
+
+// Queries one full wave of plan_kernel blocks holds on the current device (occupancy x SM count x 32 queries per block):
+// the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
+// a wave takes as long as a full one).
+long long plan_wave_queries(const GeoDev& G, bool wantCen) {
+  void (*kern)(const PlanArgs, const GeoDev) =
+      G.useTma ? (wantCen ? plan_kernel<true, true> : plan_kernel<false, true>)
+               : (wantCen ? plan_kernel<true, false> : plan_kernel<false, false>);
+  const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
+  if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
+  int perSm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, kPlanThreads, shm) != cudaSuccess || perSm < 1) perSm = 1;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  return static_cast<long long>(perSm) * sms * (kPlanThreads / 4);
 }
 
 cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream_t stream) {

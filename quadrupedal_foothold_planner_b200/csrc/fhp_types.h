@@ -21,6 +21,7 @@ struct MapDev {
   int fastOk;  // rows*cols < 2^31: 32-bit linear cell offsets are safe in the pipelined staging path
   int pad0;
   double res;
+  double rinv;          // 1/res, correctly rounded (fast path of the position -> index conversion)
   double lenx, leny, posx, posy;
   double halfx, halfy;  // getVectorToOrigin: 0.5*length
   double fcx, fcy;      // mapPosition + (0.5*length - 0.5*res): the constant term of getPositionFromIndex
