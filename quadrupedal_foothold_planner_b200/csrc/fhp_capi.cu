@@ -56,6 +56,7 @@ struct fhp_ctx {
   // geometry tables cache
   bool haveGeo = false;
   float geoFoot = 0, geoSearch = 0;
+  bool geoTrim = false;
   GeoDev G{};
   // TMA descriptor of the traversability layer (box = one staged window); rebuilt with the geometry tables
   alignas(64) CUtensorMap tmapTrav;
@@ -208,8 +209,9 @@ bool build_tma(fhp_ctx* ctx) {
 
 // Tables that depend only on (footRadius, searchRadius, resolution): the SpiralIterator visiting order and the
 // cell-centred foot-disc stencil.
-int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
-  if (ctx->haveGeo && ctx->geoFoot == footRadius && ctx->geoSearch == searchRadius) return FHP_OK;
+int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim) {
+  if (ctx->haveGeo && ctx->geoFoot == footRadius && ctx->geoSearch == searchRadius && ctx->geoTrim == allowTrim)
+    return FHP_OK;
   const MapDev& M = ctx->M;
   GeoDev& G = ctx->G;
   std::memset(&G, 0, sizeof(G));
@@ -250,7 +252,14 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
     }
   G.nSten = ns;
   G.ra = ra;
-  G.HW = G.nRings + ra;
+  // Rings whose every cell is farther than searchRadius from ANY centre that maps to the centre cell can never pass
+  // SpiralIterator's last-two-rings distance filter: ring d holds offsets with |offset| >= d cells and the centre is
+  // within sqrt(2)/2 cell of its cell centre (farther, and on the far side, when it lies outside the map).  Not
+  // valid for the bug-compatible mode with a shifted start index, whose filter uses unrelated positions.
+  int ringsEff = G.nRings;
+  if (allowTrim)
+    while (ringsEff > 0 && (static_cast<double>(ringsEff) - 0.70711 - 1e-6) * res > R) --ringsEff;
+  G.HW = ringsEff + ra;
   if (G.HW < 1) G.HW = 1;
   // the staged window must also contain the foot disc of the (continuous) centre: index distance <= floor(r/res)+1
   if (G.HW < static_cast<int>(std::floor(r / res)) + 1) G.HW = static_cast<int>(std::floor(r / res)) + 1;
@@ -267,7 +276,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
   std::vector<std::pair<int, int>> table;
   table.push_back({0, 0});
   int lastTwo = -1;
-  for (int d = 1; d <= G.nRings; ++d) {
+  for (int d = 1; d <= ringsEff; ++d) {
     if (lastTwo < 0 && (d == G.nRings - 1 || d == G.nRings)) lastTwo = static_cast<int>(table.size());
     std::vector<std::pair<int, int>> ring;
     int x = d, y = 0;
@@ -293,6 +302,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
   for (int k = 0; k < G.nCand; ++k) {
     G.spiral[k][0] = static_cast<int8_t>(table[k].first);
     G.spiral[k][1] = static_cast<int8_t>(table[k].second);
+    G.candRows[table[k].second + G.HW] |= 1u << (table[k].first + G.HW);
   }
   // ---- shared-memory layout of a plan_kernel block and the TMA descriptor
   const int warps = kPlanThreads / 32;
@@ -307,6 +317,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius) {
   G.smemWords = G.useTma ? G.boxOff + warps * 2 * G.tmaB * G.boxWords : planesEnd;
   ctx->geoFoot = footRadius;
   ctx->geoSearch = searchRadius;
+  ctx->geoTrim = allowTrim;
   ctx->haveGeo = true;
   return FHP_OK;
 }
@@ -316,7 +327,10 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   for (int i = 1; i < n_params; ++i)
     if (params[i].foot_radius != params[0].foot_radius || params[i].search_radius != params[0].search_radius)
       return fail(ctx, FHP_ERR_INVALID_ARG, "all parameter sets of one call must share foot_radius and search_radius");
-  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius);
+  bool allowTrim = true;  // see build_geo: ring trimming is exact unless the bug-compatible spiral meets a shifted start
+  for (int i = 0; i < n_params; ++i)
+    if (params[i].spiral_mode == FHP_SPIRAL_FAITHFUL && !(ctx->M.start0 == 0 && ctx->M.start1 == 0)) allowTrim = false;
+  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim);
   if (rc != FHP_OK) return rc;
   std::vector<ParDev> h(n_params);
   for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i]);

@@ -454,6 +454,21 @@ __device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, d
   return mean_height(M, P, cx, cy, disc_window(M, cx, cy, P.r));
 }
 
+// Rare path of the centroid method: whole-window test and edge rows counted from global memory (submap rows
+// tl0..tl0+n0-1, columns tl1..tl1+n1-1, all inside the map by construction of getSubmapInformation).
+__device__ __noinline__ unsigned long long centroid_rows_slow(const MapDev& M, float thrD, int tl0, int tl1, int n0,
+                                                              int n1) {
+  uint32_t any = 0, edgeRel = 0;
+  for (int i = 0; i < n0; ++i) {
+    int cnt = 0;
+    for (int c = 0; c < n1; ++c)
+      if (in_map(M, tl0 + i, tl1 + c) && load_cell(M, M.trav, tl0 + i, tl1 + c) < thrD) ++cnt;
+    if (cnt > 0) any |= 1u << i;
+    if (2 * cnt > n1) edgeRel |= 1u << i;  // cnt > n1 * 0.5
+  }
+  return static_cast<unsigned long long>(any) | (static_cast<unsigned long long>(edgeRel) << 32);
+}
+
 // ------------------------------------------------------------------------------------------------ a4 centroid
 struct CentroidOut {
   double x, y;  // result xy ((0,0) when the submap failed or no case matched)
@@ -485,37 +500,38 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
   const double spx = cornx - shx, spy = corny - shy;  // submap position
   if (!(within_axis(px, slx, spx, shx) && within_axis(py, sly, spy, shy))) return o;  // requested centre in submap
 
-  // window coordinates of the submap inside the staged planes
-  const int a0 = tl0 - w0, a1 = br0 - w0, c0 = tl1 - w1, c1 = br1 - w1;
-  if (a0 < 0 || c0 < 0 || a1 >= min(32, G.WIN + 3) || c1 >= G.WIN || n0 < 1 || n1 < 1 || n0 > 32) {
+  if (n0 < 1 || n1 < 1 || n0 > 32) {
     err |= kErrWindow;
     return o;
   }
-  const uint32_t rowmask = (n0 >= 32 ? 0xffffffffu : ((1u << n0) - 1u)) << a0;
-
-  // whole-window test (FP.cpp:1649-1658) and per-row counts of cells below the threshold (:1722-1750) as a
-  // bit-sliced vertical counter over the window columns (policy C.1: the phantom column is not counted)
-  uint32_t any = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-  for (int c = c0; c <= c1; ++c) {
-    uint32_t x = pl.col(PL_D, c) & rowmask;
-    any |= x;
-    uint32_t t;
-    t = s0 & x; s0 ^= x; x = t;
-    t = s1 & x; s1 ^= x; x = t;
-    t = s2 & x; s2 ^= x; x = t;
-    t = s3 & x; s3 ^= x; x = t;
-    s4 ^= x;
-  }
-  if (any == 0) {  // wholeRegionValid (:1684-1689)
-    o.x = px;
-    o.y = py;
-    o.ccase = 0;
-    return o;
-  }
-  // row is an "edge" when count > (rightCol+1)*0.5  <=>  count > floor(n1/2) for integers (:1743)
-  const int T = n1 >> 1;
-  uint32_t gt = 0, eq = 0xffffffffu;
-  {
+  // window coordinates of the submap inside the staged planes
+  const int a0 = tl0 - w0, a1 = br0 - w0, c0 = tl1 - w1, c1 = br1 - w1;
+  uint32_t any, edgeRel;  // bit i <-> submap row i: any cell below the threshold / row is an "edge"
+  if (a0 < 0 || c0 < 0 || a1 >= min(32, G.WIN + 3) || c1 >= G.WIN) {
+    // the submap sticks out of the staged window (its size is one cell larger when the corner's lattice phase is
+    // within ~1e-7 of a cell boundary): count straight from global memory
+    const unsigned long long pk = centroid_rows_slow(M, P.thrD, tl0, tl1, n0, n1);
+    any = static_cast<uint32_t>(pk);
+    edgeRel = static_cast<uint32_t>(pk >> 32);
+  } else {
+    const uint32_t rowmask = (n0 >= 32 ? 0xffffffffu : ((1u << n0) - 1u)) << a0;
+    // whole-window test (FP.cpp:1649-1658) and per-row counts of cells below the threshold (:1722-1750) as a
+    // bit-sliced vertical counter over the window columns (policy C.1: the phantom column is not counted)
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+    any = 0;
+    for (int c = c0; c <= c1; ++c) {
+      uint32_t x = pl.col(PL_D, c) & rowmask;
+      any |= x;
+      uint32_t t;
+      t = s0 & x; s0 ^= x; x = t;
+      t = s1 & x; s1 ^= x; x = t;
+      t = s2 & x; s2 ^= x; x = t;
+      t = s3 & x; s3 ^= x; x = t;
+      s4 ^= x;
+    }
+    // row is an "edge" when count > (rightCol+1)*0.5  <=>  count > floor(n1/2) for integers (:1743)
+    const int T = n1 >> 1;
+    uint32_t gt = 0, eq = 0xffffffffu;
     const uint32_t sv[5] = {s0, s1, s2, s3, s4};
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
@@ -523,12 +539,18 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
       gt |= eq & sv[i] & ~ti;
       eq &= ~(sv[i] ^ ti);
     }
+    edgeRel = (gt & rowmask) >> a0;
   }
-  const uint32_t edge = gt & rowmask;
+  if (any == 0) {  // wholeRegionValid (:1684-1689)
+    o.x = px;
+    o.y = py;
+    o.ccase = 0;
+    return o;
+  }
   int minRow = 0, maxRow = 0;
-  if (edge) {
-    minRow = (__ffs(edge) - 1) - a0;
-    maxRow = (31 - __clz(edge)) - a0;
+  if (edgeRel) {
+    minRow = __ffs(edgeRel) - 1;
+    maxRow = 31 - __clz(edgeRel);
   }
   const int topRow = 0, bottomRow = n0 - 1, rightCol = n1 - 1;
   int newRow, newCol;
@@ -688,13 +710,16 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
       const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
       bad = F & (C | ~box);
     }
-    uint32_t dil = 0;
-    for (int s = 0; s < G.nSten; ++s) {
-      const int s0 = G.sten[s][0], s1 = G.sten[s][1];
-      const int srcCol = lane + s1;
-      uint32_t nb = __shfl_sync(kFull, bad, srcCol & 31);
-      if (srcCol < 0 || srcCol >= G.WIN) nb = 0;
-      dil |= (s0 >= 0) ? (nb >> s0) : (nb << (-s0));
+    uint32_t dil = bad;
+    if (G.nSten > 1) {  // dilate by the foot-disc stencil (a single-cell stencil needs nothing)
+      dil = 0;
+      for (int s = 0; s < G.nSten; ++s) {
+        const int s0 = G.sten[s][0], s1 = G.sten[s][1];
+        const int srcCol = lane + s1;
+        uint32_t nb = __shfl_sync(kFull, bad, srcCol & 31);
+        if (srcCol < 0 || srcCol >= G.WIN) nb = 0;
+        dil |= (s0 >= 0) ? (nb >> s0) : (nb << (-s0));
+      }
     }
     // candidate cells outside the map: rows (bits) and this lane's column
     {
@@ -704,6 +729,12 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
       const int q1 = juc1 + lane - G.HW;
       const bool colIn = q1 >= 0 && q1 < M.cols;
       dil = colIn ? (dil | ~rowsIn) : 0xffffffffu;
+    }
+    // quick reject: no cell of the spiral footprint is acceptable even before the distance filter (a query that is
+    // stuck on an untraversable patch re-scans the same window every remaining cycle)
+    {
+      const uint32_t footprint = (lane < G.WIN) ? (G.candRows[lane] << (ha - G.HW)) : 0u;
+      if (__ballot_sync(kFull, (footprint & ~dil) != 0u) == 0u) continue;
     }
     // 2. rank scan
     bool haveC = false;

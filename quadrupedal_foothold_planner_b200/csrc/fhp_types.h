@@ -49,6 +49,7 @@ struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int nCand;     // spiral table length
   int lastTwoStart;  // first rank that belongs to ring nRings-1 (distance-filtered rings)
   int nSten;
+  uint32_t candRows[32];  // per window column: bit (d0+HW) set for every spiral-table offset (d0, column-HW)
   int8_t sten[kMaxSten][2];
   int8_t spiral[kMaxCand][2];
 };

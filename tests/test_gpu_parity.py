@@ -167,3 +167,35 @@ def test_errors_are_loud(fhp):
         fresh.plan(_abi.yaml_params(search_radius=0.5), q, 2)
     assert e.value.code == _abi.FHP_ERR_UNSUPPORTED
     fresh.close()
+
+
+def test_centroid_submap_one_cell_larger(fhp, oracle):
+    """when a submap corner's lattice phase is within ~1e-7 cell of a boundary the window is 12x6 /
+    11x7 instead of 11x6 and sticks out of the trimmed staged window -> the kernel's global-memory fallback."""
+    m = synth.rough_map(400, 400, 0.02, seed=17, start=(9, 391))
+    fhp.set_map(m)
+    p = _abi.yaml_params()
+    f32 = np.float32
+    Lx, Ly = float(f32(0.1) * f32(2)), float(f32(0.1))
+    pts = []
+    for k in range(-150, 150, 7):
+        for d in (-3e-9, -1e-9, 0.0, 1e-9, 3e-9):
+            pts.append((k * 0.02 - 0.5 * Lx + d, 0.013 + 0.02 * (k % 11)))
+            pts.append((0.011 + 0.02 * (k % 13), k * 0.02 - 0.5 * Ly + d))
+            pts.append((k * 0.02 + 0.5 * Lx + d, k * 0.02 + 0.5 * Ly - d))
+    pts = np.array(pts)
+    sizes = {tuple(oracle.submap_info(m, x, y, Lx, Ly)[1][2:]) for x, y in pts}
+    assert (12, 6) in sizes or (12, 7) in sizes, sizes
+    assert (11, 7) in sizes or (12, 7) in sizes, sizes
+    g_out, g_case = fhp.check_centroid(p, pts)
+    e_out, e_case = oracle.check_centroid(m, p, pts)
+    assert np.array_equal(g_case, e_case)
+    for f in ("row", "col"):
+        assert np.array_equal(g_out[f], e_out[f]), f
+    for f in ("x", "y", "z"):
+        assert np.max(np.abs(g_out[f] - e_out[f])) <= XYZ_TOL, f
+    # and through the plan: stance centres chosen so the first cycle's windows hit the enlarged case
+    q = _abi.make_queries([[x - 0.09, y, 0.0] for x, y in pts[:200]])
+    got = fhp.plan(p, q, 3, centroid=True)
+    exp = oracle.plan(m, p, q, 3, centroid=True)
+    assert compare_plans(got, exp, "enlarged submap") <= XYZ_TOL
