@@ -308,8 +308,10 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   const int warps = kPlanThreads / 32;
   const int planesEnd = G.spiralWords + warps * 32 * G.stride;
   G.boxWords = 32 * G.nIter;
+  int boxBudget = 8192;  // bytes of box buffers per warp (two rounds in flight)
+  if (const char* e = std::getenv("FHP_TMA_BOX_BUDGET")) boxBudget = std::max(1024, atoi(e));
   G.tmaBShift = 0;
-  while (G.tmaBShift < 3 && (2 << (G.tmaBShift + 1)) * G.boxWords * 4 <= 8192) ++G.tmaBShift;
+  while (G.tmaBShift < 3 && (2 << (G.tmaBShift + 1)) * G.boxWords * 4 <= boxBudget) ++G.tmaBShift;
   G.tmaB = 1 << G.tmaBShift;
   G.mbarOff = planesEnd;                                   // multiple of 4 words -> 8-byte aligned
   G.boxOff = ((G.mbarOff + warps * 4 + 31) / 32) * 32;     // 128-byte aligned

@@ -7,7 +7,10 @@
 
 namespace fhp {
 
-constexpr int kPlanThreads = 128;
+#ifndef FHP_PLAN_THREADS
+#define FHP_PLAN_THREADS 128
+#endif
+constexpr int kPlanThreads = FHP_PLAN_THREADS;
 
 struct PlanArgs {
   alignas(64) CUtensorMap tmap;  // traversability layer, box = one staged window (valid iff G.useTma)

@@ -59,6 +59,9 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
   return t;
 }
 
+#ifndef FHP_SYNC_LEVEL
+#define FHP_SYNC_LEVEL 2
+#endif
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
 #endif
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
   const int f = lane & 3;           // RF,RH,LH,LF
   const int quad0 = lane & ~3;
   const bool active = q < A.nq;
-  if (gwarp * 8 >= A.nq) return;    // whole warp idle (after the block-wide table load)
+  // (a whole-idle warp of the last block keeps running with active == false: the block synchronises every cycle)
   const MapDev& M = A.M;
 
   fhp_query qu;
@@ -123,6 +126,9 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
   const float thrD = P.thrD, thrC = P.thrC;
 
   for (int g = 0; g < A.cycles; ++g) {
+#if FHP_SYNC_LEVEL >= 1
+    __syncthreads();  // keep the block's warps in the same code region (instruction-cache locality)
+#endif
     // getFootholdSearchGridMap for both chains (FP.cpp:788, :830 -> :2166-2250)
     double ccx, ccy, ncx, ncy;
     polygon_center(shfl_d(cenx, quad0), shfl_d(ceny, quad0), shfl_d(cenx, quad0 + 1), shfl_d(ceny, quad0 + 1),
@@ -149,6 +155,9 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     else
       stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
 
+#if FHP_SYNC_LEVEL >= 2
+    __syncthreads();
+#endif
     CentroidOut co;
     co.x = co.y = 0.0;
     co.ccase = -1;
@@ -162,6 +171,9 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     const NominalOut no =
         nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
     const bool ok = no.ok;
+#if FHP_SYNC_LEVEL >= 3
+    __syncthreads();
+#endif
     if (active) {
       if (ok) nz = static_cast<double>(mean_height(M, P, px, py, dw));  // at the CENTRE (FP.cpp:2029)
       if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, P, co.x, co.y));
