@@ -298,14 +298,23 @@ __device__ __forceinline__ void convert_one(uint32_t src, uint32_t dst, int lane
   const uint32_t bF = __ballot_sync(kFull, fabsf(v) < __int_as_float(0x7f800000));
   if (lane == 0) sts_v4(dst, bD, bC, bF, 0u);
 }
-__device__ __forceinline__ void convert_box(int nIter, uint32_t src, uint32_t dst, int lane, float tD, float tC) {
-  int k = 0;
-  for (; k + 4 <= nIter; k += 4) {
+template <int N>
+__device__ __forceinline__ void convert_n(uint32_t src, uint32_t dst, int lane, float tD, float tC) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      convert_one(src + static_cast<uint32_t>(k + i) * 128u, dst + static_cast<uint32_t>(k + i) * 16u, lane, tD, tC);
+  for (int i = 0; i < N; ++i)
+    convert_one(src + static_cast<uint32_t>(i) * 128u, dst + static_cast<uint32_t>(i) * 16u, lane, tD, tC);
+}
+__device__ __forceinline__ void convert_box(int nIter, uint32_t src, uint32_t dst, int lane, float tD, float tC) {
+  switch (nIter) {  // straight-line bodies for the common window sizes (every ballot is a convergence point)
+    case 6: convert_n<6>(src, dst, lane, tD, tC); return;
+    case 7: convert_n<7>(src, dst, lane, tD, tC); return;
+    case 8: convert_n<8>(src, dst, lane, tD, tC); return;
+    default: break;
   }
-  const int rem = nIter - k;  // 0..3, straight-line (a loop would add a divergence check per ballot)
+  int k = 0;
+  for (; k + 4 <= nIter; k += 4)
+    convert_n<4>(src + static_cast<uint32_t>(k) * 128u, dst + static_cast<uint32_t>(k) * 16u, lane, tD, tC);
+  const int rem = nIter - k;  // 0..3, straight-line
   if (rem >= 1) convert_one(src + static_cast<uint32_t>(k) * 128u, dst + static_cast<uint32_t>(k) * 16u, lane, tD, tC);
   if (rem >= 2) convert_one(src + static_cast<uint32_t>(k + 1) * 128u, dst + static_cast<uint32_t>(k + 1) * 16u, lane, tD, tC);
   if (rem >= 3) convert_one(src + static_cast<uint32_t>(k + 2) * 128u, dst + static_cast<uint32_t>(k + 2) * 16u, lane, tD, tC);
@@ -420,6 +429,17 @@ __device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, doubl
   d.br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv);
   d.br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
   return d;
+}
+
+// Pull the elevation cells of a foot disc towards L1 long before mean_height sums them (the loads are otherwise
+// the only exposed global latency of the scalar phase).
+__device__ __forceinline__ void prefetch_disc(const MapDev& M, const float* layer, const DiscWin& dw) {
+  for (int u0 = dw.tl0; u0 <= dw.br0; ++u0)
+    for (int u1 = dw.tl1; u1 <= dw.br1; ++u1)
+      if (in_map(M, u0, u1)) {
+        const int b0 = wrap_add(u0, M.start0, M.rows), b1 = wrap_add(u1, M.start1, M.cols);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(layer + static_cast<size_t>(b1) * M.rows + b0));
+      }
 }
 
 // ------------------------------------------------------------------------------------------------ a9 mean height

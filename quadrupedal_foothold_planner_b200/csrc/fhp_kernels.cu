@@ -150,6 +150,11 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
       if (c0 >= M.rows) c0 -= M.rows;
       w0 -= c0 & 3;
     }
+    DiscWin dw = {0, 0, -1, -1};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
+    if (active) {
+      dw = disc_window(M, px, py, P.r);
+      prefetch_disc(M, M.elev, dw);
+    }
     if (USE_TMA)
       stage_windows_tma(M, G, &A.tmap, T, sw, lane, active, w0, w1, thrD, thrC);
     else
@@ -162,11 +167,9 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     co.x = co.y = 0.0;
     co.ccase = -1;
     double nz = 0.0, cz = 0.0;
-    DiscWin dw = {0, 0, -1, -1};
     if (active) {
       Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
-      dw = disc_window(M, px, py, P.r);
     }
     const NominalOut no =
         nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
