@@ -136,9 +136,29 @@ def algorithmic_bytes(hmap, params, queries, cycles, sample=256):
     return float(w.sum()) / n, float(sp.sum()) / n
 
 
+def as_written_reference(hmap, params, queries, cycles, n=1):
+    """The UNMODIFIED reference FootholdPlanner.cpp (oracle/_ref/libfhp_ref.so, compiled from /root/reference against
+    header shims) on `n` queries of the workload: it copies the whole GridMap by value for every foothold test
+    (FP.cpp:863-903, :2039, :2085, :2117, :2520), so one query on the 4000x4000 map costs seconds.  Reported next
+    to the port for context; None when the prebuilt library is not in the tree."""
+    try:
+        from oracle import binding as ob
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfhp_ref.so")):
+            return None
+        t0 = time.perf_counter()
+        ob.ref_plan(hmap, params, queries[:n], cycles, wrap_correct=True, centroid=False)
+        dt = time.perf_counter() - t0
+        return {"value": n * cycles * 4 / dt, "unit": UNIT, "cores": 4, "kind": "reference",
+                "sample": f"{n} query x {cycles} cycles through the reference class (4 std::threads per cycle), {dt:.1f} s"}
+    except Exception as e:  # the checker must never take the bench down
+        return {"error": str(e)[:200]}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle restatement; the reference itself needs ROS/grid_map/
-    Eigen/NLopt and cannot be built here) on this box's host cores, same metric/config, bounded sample per step."""
+    """--impl reference: the reference's CPU path on this box's host cores, same metric/config, bounded sample per
+    step.  Throughput is measured on the CPU port (oracle/, the reference's algorithm without its by-value map
+    copies, all host threads); the as-written reference build (oracle/_ref) is timed on one query and reported in
+    `as_written_reference` — at ~16 s per query on this map it cannot fill K steps within minutes."""
     if rank != 0:
         return
     hmap, queries, cycles, params, desc = make_workload(args.workload, 0)
@@ -163,6 +183,8 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_as_written:
+        line["as_written_reference"] = as_written_reference(hmap, params, queries[1:], cycles, 1)
     print(json.dumps(line), flush=True)
 
 
@@ -176,6 +198,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=16384, help="queries per step of the CPU arm")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-as-written", action="store_true", help="skip timing oracle/_ref in --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

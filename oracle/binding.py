@@ -163,3 +163,42 @@ def initial_geometry(params, query_xyz=(0.0, 0.0, 0.0)):
     first = np.zeros((4, 2))
     lib().oracle_initial_geometry(C.byref(params), _p(q), _p(init), _p(bias), _p(first))
     return init, bias, first
+
+
+# ---- the reference's own FootholdPlanner.cpp compiled against shims (oracle/ref_shim -> oracle/_ref) -------------
+_REF = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfhp_ref.so")) or os.path.isdir("/root/reference")
+
+
+def ref_lib():
+    """oracle/_ref/libfhp_ref.so; (re)built from /root/reference when that tree is present (this container only —
+    the GPU box uses the prebuilt file that travels with the repo)."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(ROOT, "oracle", "_ref", "libfhp_ref.so")
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle", "ref_shim")])
+        _REF = C.CDLL(path)
+    return _REF
+
+
+def ref_plan(hmap, params, queries, gait_cycles, wrap_correct=False, centroid=True):
+    """plan_global_footholds through the reference class, one service call per query.
+    -> (nominal rows, centroid rows | None, status); status.reserved == 1 where the service returned false."""
+    params = list(params) if isinstance(params, (list, tuple)) else [params]
+    parr = (_abi.Params * len(params))(*params)
+    d, ptrs, keep = hmap.desc()
+    nq = len(queries)
+    R = _abi.rows_per_query(gait_cycles)
+    nom = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE)
+    cen = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE) if centroid else None
+    st = np.zeros(nq, dtype=_abi.STATUS_DTYPE)
+    q = np.ascontiguousarray(queries)
+    rc = ref_lib().ref_plan(C.byref(d), ptrs, parr, _p(q), C.c_int64(nq), C.c_int32(gait_cycles),
+                            C.c_int32(1 if wrap_correct else 0), _p(nom), _p(cen) if centroid else None, _p(st))
+    if rc != 0:
+        raise RuntimeError(f"ref_plan failed rc={rc}")
+    return nom, cen, st

@@ -1,4 +1,8 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see gm_core.hpp header).  PARITY UNPINNED (no reference tests/fixtures exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see gm_core.hpp header).
+// PARITY: the reference has no tests or fixtures of its own.  This restatement is pinned against the reference's
+// OWN FootholdPlanner.cpp compiled here (oracle/ref_shim -> oracle/_ref, tests/test_reference_build.py,
+// tests/golden/ref_*.npz): bit-exact responses of both chains on every completed service call.  What stays
+// unpinned is the grid_map_core layer underneath both (gm_core.hpp: third party, not vendored, restated).
 //
 // CPU restatement of the hot path of lukechencqu/quadrupedal_foothold_planner,
 // foothold_planner/src/FootholdPlanner.cpp ("FP.cpp"), with the reference's float/double member types

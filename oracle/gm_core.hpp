@@ -2,9 +2,10 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // build, link or call it, and only as the checker / reported CPU baseline.
 //
-// PARITY UNPINNED: the reference (lukechencqu/quadrupedal_foothold_planner) has no tests, fixtures or
+// PARITY UNPINNED for this file: the reference (lukechencqu/quadrupedal_foothold_planner) has no tests, fixtures or
 // golden vectors, and this file restates a THIRD-PARTY dependency that is not vendored under
-// /root/reference and not version-pinned there:
+// /root/reference and not version-pinned there (the planner-level restatement in fp_oracle.hpp IS checked against
+// the reference's own FootholdPlanner.cpp, which oracle/ref_shim compiles on top of this very file):
 //     ANYbotics/grid_map -> grid_map_core  (BSD-3; era of the reference => release 1.6.2, ROS kinetic/melodic)
 //     (foothold_planner/CMakeLists.txt:8-18 find_package(... grid_map_core ...), no version).
 // What follows is a restatement of the published grid_map_core algorithms that the reference calls at

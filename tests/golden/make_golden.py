@@ -49,7 +49,37 @@ def member_case():
     return m, _abi.yaml_params(), c, rc
 
 
+def ref_cases():
+    """Cases whose golden vectors come from the REFERENCE's own FootholdPlanner.cpp (oracle/_ref, built by
+    oracle/ref_shim from /root/reference): name -> (HostMap, params, queries, cycles, upstream_spiral).
+    Small maps only: the reference copies the whole GridMap by value for every spiral candidate."""
+    out = {}
+    m, q, n = synth.config_c1()
+    out["ref_c1_flat_trot"] = (m, _abi.yaml_params(), q, n, True)
+    m = synth.rough_map(300, 300, 0.02, seed=5, start=(0, 0))
+    q = synth.uniform_queries(60, (-2.2, 0.8), (-2.2, 2.2), seed=6)
+    out["ref_rough_002"] = (m, _abi.yaml_params(), q, 8, True)
+    m = synth.rough_map(500, 500, 0.01, seed=7, start=(0, 0))
+    q = synth.uniform_queries(60, (-1.7, 0.3), (-1.7, 1.7), seed=8)
+    out["ref_rough_001"] = (m, _abi.yaml_params(), q, 8, True)
+    m = synth.rough_map(300, 300, 0.02, seed=9, start=(33, 250))
+    q = synth.uniform_queries(60, (-2.2, 0.8), (-2.2, 2.2), seed=10)
+    out["ref_rough_002_start_upstream"] = (m, _abi.yaml_params(spiral_mode=_abi.FHP_SPIRAL_FAITHFUL), q, 8, True)
+    out["ref_rough_002_start_repaired"] = (m, _abi.yaml_params(spiral_mode=_abi.FHP_SPIRAL_WRAP_CORRECT), q, 8, False)
+    m = synth.stairs_stones_map(700, 400, 0.01, start=(0, 0))
+    q = synth.uniform_queries(40, (-2.9, -1.2), (-1.2, 1.2), seed=11)
+    out["ref_stairs_001_rf_first"] = (m, _abi.yaml_params(rf_first=1, step_length=0.16, skew=0.04), q, 8, True)
+    return out
+
+
 def main():
+    if ob.ref_available():
+        for name, (m, p, q, n, upstream) in ref_cases().items():
+            nom, cen, st = ob.ref_plan(m, p, q, n, wrap_correct=not upstream)
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), nominal=nom, centroid=cen, status=st)
+            done = st["reserved"] == 0
+            print(name, "service calls completed", int(done.sum()), "of", len(q), "succeed",
+                  int(st["gait_cycles_succeed"][done].sum()))
     for name, (m, ps, q, n) in cases().items():
         nom, cen, st = ob.plan(m, ps, q, n, centroid=True)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), nominal=nom, centroid=cen, status=st)

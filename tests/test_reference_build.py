@@ -1,0 +1,92 @@
+"""Parity against the REFERENCE ITSELF: /root/reference's FootholdPlanner.cpp compiled in place against header shims
+(oracle/ref_shim -> oracle/_ref/libfhp_ref.so; ROS / messages / NLopt stubbed, grid_map_core = the restatement) and
+driven through its real class interface (rosparams -> gridmapCallback -> globalFootholdPlan).
+
+* tests/golden/ref_*.npz were produced by that build (tests/golden/make_golden.py).  CPU: the oracle reproduces them
+  bit for bit; GPU: libfhp reproduces them (ids/status exact, xyz <= 1e-5 m) — on the service calls that completed.
+* A call "does not complete" when the reference's opt (NLopt) chain aborts the whole service (`return false`,
+  FootholdPlanner.cpp:931-934) — with the NLopt stand-in its state drifts off the map for some starts; those queries
+  are skipped (status.reserved == 1), everything else is compared.
+* When the compiled reference is available in the running environment the comparison is also made live.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from quadrupedal_foothold_planner_b200 import _abi
+from tests.parity import XYZ_TOL
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden  # noqa: E402
+
+REF_CASES = sorted(make_golden.ref_cases().keys())
+
+
+def _load(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    return z["nominal"], z["centroid"], z["status"]
+
+
+def _compare_to_reference(got, ref, what, tol):
+    """got = (nominal, centroid, status) of oracle or libfhp; ref = the reference's response rows."""
+    gn, gc, gs = got
+    rn, rc, rs = ref
+    done = rs["reserved"] == 0
+    assert done.sum() >= max(1, len(rs) // 2), f"{what}: too few completed reference calls"
+    for f in ("success", "gait_cycles", "gait_cycles_succeed", "n_rows"):
+        assert np.array_equal(gs[f][done], rs[f][done]), f"{what}: status.{f}"
+    own = (np.arange(rn.shape[1])[None, :] < rs["n_rows"][:, None]) & done[:, None]
+    worst = 0.0
+    for g, r, chain in ((gn, rn, "nominal"), (gc, rc, "centroid")):
+        for f in ("foot_id", "gait_cycle_id"):
+            assert np.array_equal(g[f][own], r[f][own]), f"{what}: {chain}.{f}"
+        for f in ("x", "y", "z"):
+            d = np.abs(g[f][own] - r[f][own])
+            assert not np.isnan(d).any()
+            worst = max(worst, float(d.max()) if d.size else 0.0)
+            assert worst <= tol, f"{what}: {chain}.{f} differs by {worst}"
+    return worst
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_oracle_matches_reference_vectors(oracle, name):
+    m, p, q, n, upstream = make_golden.ref_cases()[name]
+    got = oracle.plan(m, p, q, n, centroid=True)
+    assert _compare_to_reference(got, _load(name), name, 0.0) == 0.0
+
+
+@pytest.mark.parametrize("name", REF_CASES[:3])
+def test_oracle_matches_live_reference(oracle, name):
+    if not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libfhp_ref.so")) and \
+            not os.path.isdir("/root/reference"):
+        pytest.skip("compiled reference not available in this environment")
+    m, p, q, n, upstream = make_golden.ref_cases()[name]
+    q = q[:24]
+    ref = oracle.ref_plan(m, p, q, n, wrap_correct=not upstream)
+    got = oracle.plan(m, p, q, n, centroid=True)
+    assert _compare_to_reference(got, ref, name + " (live)", 0.0) == 0.0
+
+
+def test_reference_vectors_cover_the_cases():
+    """The reference-generated fixtures exercise failures, spiral picks and every chain outcome."""
+    succ = []
+    for name in REF_CASES:
+        rn, rc, rs = _load(name)
+        done = rs["reserved"] == 0
+        succ.append(rs["gait_cycles_succeed"][done])
+        # centroid chain (0,0,0) results (no case matched) occur in the rough maps
+    s = np.concatenate(succ)
+    assert (s == 8).sum() > 50 and (s < 8).sum() > 20 and (s == 0).sum() >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_CASES)
+def test_gpu_matches_reference_vectors(fhp, name):
+    m, p, q, n, upstream = make_golden.ref_cases()[name]
+    fhp.set_map(m)
+    got = fhp.plan(p, q, n, centroid=True)
+    assert np.all(got[2]["reserved"] == 0)
+    _compare_to_reference(got, _load(name), name, XYZ_TOL)
