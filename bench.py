@@ -51,6 +51,34 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "plan_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def single_plan_latency(fhp_ctx, n=200):
+    """p50 / p99 latency of ONE 8-cycle plan_global_footholds call (BASELINE config 1: flat 500x500 @0.02 m, trot)
+    through fhp_plan with host buffers, on its own context (the second half of the BASELINE metric)."""
+    m, q, cycles = synth.config_c1()
+    fhp_ctx.set_map(m)
+    p = _abi.yaml_params()
+    for _ in range(10):
+        fhp_ctx.plan(p, q, cycles)
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        fhp_ctx.plan(p, q, cycles)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return {"p50_ms": ts[len(ts) // 2], "p99_ms": ts[int(len(ts) * 0.99) - 1], "runs": n,
+            "what": "single query, 8 gait cycles, fhp_plan host->device->host, C1 flat map"}
+
+
 def make_workload(name: str, rank: int, with_map: bool = True):
     """-> (HostMap, queries, gait_cycles, params list, description).  with_map=False: geometry only (non-root ranks
     receive the layers by NCCL broadcast)."""
@@ -251,7 +279,10 @@ def main():
     h_q = torch.from_numpy(q_np.view(np.uint8).copy()).pin_memory()
     h_nom = torch.empty(nq * R * _abi.FOOTHOLD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     h_st = torch.empty(nq * _abi.STATUS_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    stream = torch.cuda.current_stream()
+    # an explicit non-default stream: fhp_plan_device treats a NULL stream as "use the context's own stream", and the
+    # timing events must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
 
     def step_resident():
         fhp.plan_device(parr, npar, d_q, nq, cycles, d_nom, None, d_st, stream=stream.cuda_stream)
@@ -282,6 +313,7 @@ def main():
     # ---- warm-up
     for _ in range(args.warmup):
         step_resident()
+    stream.synchronize()
     fhp.synchronize()
     barrier()
 
@@ -296,6 +328,7 @@ def main():
     for _ in range(args.steps):
         step_resident()
     ev1.record(stream)
+    stream.synchronize()
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = fhp.kernel_launches() - launches0
@@ -343,11 +376,15 @@ def main():
                     "d2h_bytes_per_step": int(h_nom.numel() + h_st.numel()), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_foothold": {"read_unique_cells": w_in, "rows_written": w_out},
                          "spiral_taken_frac": spiral_frac, "kernel": "plan_kernel<false>",
                          "avg_launch_ms": ms_per_step},
         }
+        if world == 1:
+            lat_ctx = Fhp(local_rank)
+            line["latency_single_plan"] = single_plan_latency(lat_ctx)
+            lat_ctx.close()
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sq = queries[: min(nq, args.cpu_sample)]

@@ -65,6 +65,11 @@ struct fhp_ctx {
   DevBuf dPars, dQ, dOutN, dOutC, dSt, dErr, dA, dB, dC2, dD;
   long long launches = 0;
   unsigned pendingErrCheck = 0;
+  // kernel error bits live in zero-copy host memory: reading them after a stream sync costs no memcpy
+  unsigned* hErr = nullptr;   // host address
+  unsigned* dErrMapped = nullptr;  // device alias
+  // last uploaded parameter sets (skips the upload + sync when a caller repeats the same parameters)
+  std::vector<fhp_params> lastParams;
 };
 
 namespace {
@@ -334,20 +339,22 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
     if (params[i].spiral_mode == FHP_SPIRAL_FAITHFUL && !(ctx->M.start0 == 0 && ctx->M.start1 == 0)) allowTrim = false;
   int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim);
   if (rc != FHP_OK) return rc;
+  if (ctx->dPars.p && ctx->lastParams.size() == static_cast<size_t>(n_params) &&
+      std::memcmp(ctx->lastParams.data(), params, sizeof(fhp_params) * n_params) == 0)
+    return FHP_OK;  // same parameter sets as the previous call: the derived table is already on the device
   std::vector<ParDev> h(n_params);
   for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i]);
   CU(ctx->dPars.reserve(sizeof(ParDev) * n_params));
   CU(cudaMemcpyAsync(ctx->dPars.p, h.data(), sizeof(ParDev) * n_params, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));  // h goes out of scope
+  ctx->lastParams.assign(params, params + n_params);
   return FHP_OK;
 }
 
 int check_dev_err(fhp_ctx* ctx) {
-  unsigned e = 0;
-  CU(cudaMemcpy(&e, ctx->dErr.p, sizeof(e), cudaMemcpyDeviceToHost));
+  const unsigned e = ctx->hErr ? *static_cast<volatile unsigned*>(ctx->hErr) : 0u;
   if (e) {
-    unsigned z = 0;
-    cudaMemcpy(ctx->dErr.p, &z, sizeof(z), cudaMemcpyHostToDevice);
+    *ctx->hErr = 0;
     char b[160];
     snprintf(b, sizeof b, "kernel reported geometry outside its window tables (bits 0x%x)", e);
     return fail(ctx, FHP_ERR_UNSUPPORTED, b);
@@ -356,9 +363,14 @@ int check_dev_err(fhp_ctx* ctx) {
 }
 
 int ensure_err_word(fhp_ctx* ctx) {
-  if (!ctx->dErr.p) {
-    CU(ctx->dErr.reserve(sizeof(unsigned)));
-    CU(cudaMemset(ctx->dErr.p, 0, sizeof(unsigned)));
+  if (!ctx->hErr) {
+    void* h = nullptr;
+    CU(cudaHostAlloc(&h, sizeof(unsigned), cudaHostAllocMapped));
+    ctx->hErr = static_cast<unsigned*>(h);
+    *ctx->hErr = 0;
+    void* d = nullptr;
+    CU(cudaHostGetDevicePointer(&d, h, 0));
+    ctx->dErrMapped = static_cast<unsigned*>(d);
   }
   return FHP_OK;
 }
@@ -440,6 +452,7 @@ void fhp_destroy(fhp_ctx* ctx) {
   for (DevBuf* b : {&ctx->dPars, &ctx->dQ, &ctx->dOutN, &ctx->dOutC, &ctx->dSt, &ctx->dErr, &ctx->dA, &ctx->dB, &ctx->dC2,
                     &ctx->dD})
     b->release();
+  if (ctx->hErr) cudaFreeHost(ctx->hErr);
   cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
@@ -514,7 +527,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.outN = d_outN;
   A.outC = d_outC;
   A.st = d_st;
-  A.err = static_cast<unsigned*>(ctx->dErr.p);
+  A.err = ctx->dErrMapped;
   CU(launch_plan(A, ctx->G, d_outC != nullptr, s));
   if (n_queries > 0) ctx->launches += 1;
   return FHP_OK;
@@ -603,7 +616,7 @@ int fhp_synchronize(fhp_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream2));
-  if (ctx->pendingErrCheck && ctx->dErr.p) {
+  if (ctx->pendingErrCheck && ctx->hErr) {
     ctx->pendingErrCheck = 0;
     CU(cudaDeviceSynchronize());
     return check_dev_err(ctx);
@@ -644,7 +657,7 @@ static int run_task(fhp_ctx* ctx, int mode, const fhp_params* params, const doub
   A.valid = static_cast<uint8_t*>(ctx->dC2.p);
   A.ccase = static_cast<int8_t*>(ctx->dC2.p);
   A.z = static_cast<float*>(ctx->dD.p);
-  A.err = static_cast<unsigned*>(ctx->dErr.p);
+  A.err = ctx->dErrMapped;
   CU(launch_task(mode, A, ctx->G, s));
   ctx->launches += 1;
   if (out) CU(cudaMemcpyAsync(out, ctx->dOutN.p, sizeof(fhp_foothold) * n, cudaMemcpyDeviceToHost, s));
