@@ -300,9 +300,17 @@ __device__ __forceinline__ void convert_one(uint32_t src, uint32_t dst, int lane
 }
 template <int N>
 __device__ __forceinline__ void convert_n(uint32_t src, uint32_t dst, int lane, float tD, float tC) {
+  float v[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i)
-    convert_one(src + static_cast<uint32_t>(i) * 128u, dst + static_cast<uint32_t>(i) * 16u, lane, tD, tC);
+  for (int i = 0; i < N; ++i) v[i] = lds_f32(src + static_cast<uint32_t>(i) * 128u);  // all loads first: ILP
+  const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const uint32_t bD = __ballot_sync(kFull, v[i] < tD);
+    const uint32_t bC = __ballot_sync(kFull, v[i] < tC);
+    const uint32_t bF = __ballot_sync(kFull, fabsf(v[i]) < inf);
+    if (lane == 0) sts_v4(dst + static_cast<uint32_t>(i) * 16u, bD, bC, bF, 0u);
+  }
 }
 __device__ __forceinline__ void convert_box(int nIter, uint32_t src, uint32_t dst, int lane, float tD, float tC) {
   switch (nIter) {  // straight-line bodies for the common window sizes (every ballot is a convergence point)
@@ -373,20 +381,16 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
     const int nRounds = (nFast + B - 1) >> G.tmaBShift;
     const uint32_t boxBytes = static_cast<uint32_t>(G.boxWords) * 4u;
     const float inf = __int_as_float(0x7f800000);
-    unsigned remIssue = fastMask;
-    // UTMALDG is a warp-uniform instruction: ONE elected lane issues each box with broadcast coordinates.
+    // every eligible lane issues the box of ITS window; cp.async.bulk.tensor is a warp-uniform instruction (UTMALDG),
+    // so the hardware loop ptxas wraps around it (ELECT / R2UR.BROADCAST / BRA.U.ANY) serialises the active lanes
+    const int rank = __popc(fastMask & ((1u << lane) - 1u));
+    const int myRound = rank >> G.tmaBShift;
+    const uint32_t myBox = T.boxAddr + static_cast<uint32_t>(((myRound & 1) << G.tmaBShift) + (rank & (B - 1))) * boxBytes;
     auto issue = [&](int r) {
       const int buf = r & 1;
       const int cnt = min(B, nFast - (r << G.tmaBShift));
       if (lane == 0) mbar_expect_tx(T.bar[buf], static_cast<uint32_t>(cnt) * boxBytes);
-      uint32_t dstBox = T.boxAddr + static_cast<uint32_t>(buf << G.tmaBShift) * boxBytes;
-      for (int sidx = 0; sidx < cnt; ++sidx) {
-        const int j = __ffs(remIssue) - 1;
-        remIssue &= remIssue - 1;
-        const int jc0 = __shfl_sync(kFull, c0, j), jc1 = __shfl_sync(kFull, c1, j);
-        if (lane == 0) tma_load_box(dstBox, tmap, jc0, jc1, T.bar[buf]);
-        dstBox += boxBytes;
-      }
+      if (elig && myRound == r) tma_load_box(myBox, tmap, c0, c1, T.bar[buf]);
     };
     // the box buffers were last read through the generic proxy; order those reads before the async-proxy writes
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
