@@ -370,7 +370,9 @@ def main():
                        "footholds_per_step_per_gpu": footholds_per_step,
                        "l2": "no explicit flush: per-step working set (map 128 MB + response rows %d MB) exceeds the "
                              "126 MB L2" % (nq * R * 40 // 2 ** 20),
-                       "map_generation_s": round(t_gen, 2), "map_broadcast_ms": bcast_ms},
+                       "map_generation_s": round(t_gen, 2), "map_broadcast_ms": bcast_ms,
+                       "map_broadcast_GBps": (None if not bcast_ms else round(
+                           sum(t.numel() * 4 for t in layers) / (bcast_ms * 1e-3) / 1e9, 1))},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_q.numel()),
                     "d2h_bytes_per_step": int(h_nom.numel() + h_st.numel()), "steps": e2e_steps},

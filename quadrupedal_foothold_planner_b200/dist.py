@@ -49,6 +49,9 @@ def replicate_map(hmap: Optional[HostMap], geometry: HostMap, names: Sequence[st
             t = torch.empty((geometry.cols, geometry.rows), dtype=torch.float32, device=dev)
         tensors.append(t)
     if device_index is not None:
+        # communicator set-up / first-use cost is not map replication: pay it on a tiny tensor first
+        warm = torch.zeros(8, dtype=torch.float32, device=dev)
+        dist.broadcast(warm, src=root)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
