@@ -151,6 +151,22 @@ const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* layer_name);
  * stencil offset lies within rounding distance of the disc boundary (see DESIGN.md "stencil classification"). */
 int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
              int32_t gait_cycles, fhp_foothold* out_nominal, fhp_foothold* out_centroid, fhp_query_status* status);
+/* Extended outputs of the same plan.  default_chain: the reference's "default" chain rows —
+ * un-searched nominal footholds with their mean height (getDefaultFootholds FP.cpp:2253-2304, recorded at
+ * :666-671 / :1344-1348 and published as global_footholds_default_marker); same shape as the nominal rows. */
+typedef struct fhp_plan_outputs {
+  fhp_foothold* nominal;       /* required */
+  fhp_foothold* centroid;      /* optional */
+  fhp_foothold* default_chain; /* optional */
+  fhp_query_status* status;    /* required */
+} fhp_plan_outputs;
+int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
+                int32_t gait_cycles, const fhp_plan_outputs* out);
+/* KPIs the reference logs per successful cycle (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623): pure
+ * host-side functions of ONE query's response rows (nominal or centroid chain).  feet_distance / cog_speed receive
+ * 2 values per successful cycle (n_rows/4 - 1 cycles). */
+int fhp_cycle_kpi(const fhp_params* params, const fhp_query* query, const fhp_foothold* rows, int32_t n_rows,
+                  double* feet_distance, double* cog_speed);
 /* Same with DEVICE-resident queries/outputs on ctx's device; asynchronous on ctx's stream unless
  * `cuda_stream` (a cudaStream_t) is non-NULL.  The caller synchronises. */
 int fhp_plan_device(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,

@@ -56,6 +56,26 @@ def plan(hmap, params, queries, gait_cycles, n_threads=1, centroid=True):
     return nom, cen, st
 
 
+def plan_ex(hmap, params, queries, gait_cycles):
+    """-> (nominal, centroid, default rows [nq, R], kpi [nq, cycles, 8], status)"""
+    params = list(params) if isinstance(params, (list, tuple)) else [params]
+    parr = (_abi.Params * len(params))(*params)
+    d, ptrs, keep = hmap.desc()
+    nq = len(queries)
+    R = _abi.rows_per_query(gait_cycles)
+    nom = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE)
+    cen = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE)
+    dfl = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE)
+    kpi = np.zeros((nq, max(1, gait_cycles), 8), dtype=np.float64)
+    st = np.zeros(nq, dtype=_abi.STATUS_DTYPE)
+    q = np.ascontiguousarray(queries)
+    rc = lib().oracle_plan_ex(C.byref(d), ptrs, parr, C.c_int32(len(params)), _p(q), C.c_int64(nq),
+                              C.c_int32(gait_cycles), _p(nom), _p(cen), _p(dfl), _p(kpi), _p(st))
+    if rc != 0:
+        raise RuntimeError(f"oracle_plan_ex failed rc={rc}")
+    return nom, cen, dfl, kpi, st
+
+
 def touch_bytes(hmap, params, queries, gait_cycles, with_centroid_height=True):
     params = list(params) if isinstance(params, (list, tuple)) else [params]
     parr = (_abi.Params * len(params))(*params)
@@ -185,7 +205,7 @@ def ref_lib():
     return _REF
 
 
-def ref_plan(hmap, params, queries, gait_cycles, wrap_correct=False, centroid=True):
+def ref_plan(hmap, params, queries, gait_cycles, wrap_correct=False, centroid=True, extras=False):
     """plan_global_footholds through the reference class, one service call per query.
     -> (nominal rows, centroid rows | None, status); status.reserved == 1 where the service returned false."""
     params = list(params) if isinstance(params, (list, tuple)) else [params]
@@ -197,8 +217,13 @@ def ref_plan(hmap, params, queries, gait_cycles, wrap_correct=False, centroid=Tr
     cen = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE) if centroid else None
     st = np.zeros(nq, dtype=_abi.STATUS_DTYPE)
     q = np.ascontiguousarray(queries)
+    dfl = np.zeros((nq, R), dtype=_abi.FOOTHOLD_DTYPE) if extras else None
+    kpi = np.zeros((nq, max(1, gait_cycles), 8), dtype=np.float64) if extras else None
     rc = ref_lib().ref_plan(C.byref(d), ptrs, parr, _p(q), C.c_int64(nq), C.c_int32(gait_cycles),
-                            C.c_int32(1 if wrap_correct else 0), _p(nom), _p(cen) if centroid else None, _p(st))
+                            C.c_int32(1 if wrap_correct else 0), _p(nom), _p(cen) if centroid else None, _p(st),
+                            _p(dfl) if extras else None, _p(kpi) if extras else None)
     if rc != 0:
         raise RuntimeError(f"ref_plan failed rc={rc}")
+    if extras:
+        return nom, cen, st, dfl, kpi
     return nom, cen, st

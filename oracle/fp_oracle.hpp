@@ -64,6 +64,9 @@ struct PlanResult {  // foothold_planner_msgs/GlobalFootholds
   uint8_t gait_cycles_succeed = 0;
   std::vector<Foothold> footholds;           // nominal chain = the service response (FP.cpp:1588)
   std::vector<Foothold> centroidFootholds;   // centroid chain rows (published on global_footholds_centroid)
+  std::vector<Foothold> defaultFootholds;    // "default" chain rows (globalFootholdsResult_.defaultFootholds, FP.cpp:1344-1348)
+  // KPIs per successful cycle, two values each (FP.cpp:1357-1368, :1422-1433): getHipDistance / getCogSpeed
+  std::vector<double> feetDistanceNominal, cogSpeedNominal, feetDistanceCentroid, cogSpeedCentroid;
 };
 
 class Planner {
@@ -393,6 +396,40 @@ class Planner {
     return true;  // policy C.2
   }
 
+  // FP.cpp:2253-2304 — un-searched default footholds of the next cycle (z = mean height at the default position)
+  void getDefaultFootholds(const gm::GridMap& gridmap, const Point cur[4], Point next[4]) const {
+    Point polygonCenter = getPolygonCenter(cur[0], cur[1], cur[2], cur[3]);
+    Point polygonCenterNext;
+    polygonCenterNext.x = polygonCenter.x + p.stepLength;   // :2270
+    polygonCenterNext.y = initialPose[1] + ajustedPoseY;    // :2272
+    polygonCenterNext.z = polygonCenter.z;
+    for (int f = 0; f < 4; ++f) {
+      next[f] = getDefaultFootholdNext(polygonCenterNext, bias[f]);
+      next[f].z = getFootholdMeanHeight(gridmap, gm::Vec2{next[f].x, next[f].y}, p.footRadius, p.h);  // :2289-2301
+    }
+  }
+  // FP.cpp:2571-2584
+  static void getHipDistance(const Point r[4], std::vector<double>& feetDistance) {
+    feetDistance.push_back(r[0].x - r[2].x);  // RF - LH
+    feetDistance.push_back(r[3].x - r[1].x);  // LF - RH
+  }
+  // FP.cpp:2587-2623 (gaitCycle_ = 1.0, FP.cpp:332)
+  void getCogSpeed(const Point r[4], const Point cur[4], std::vector<double>& cogSpeed) const {
+    double feetCenter1, feetCenter2, feetCenter3;
+    if (p.rfFirst) {
+      feetCenter1 = (cur[0].x + cur[2].x) / 2;
+      feetCenter2 = (r[3].x + r[1].x) / 2;
+      feetCenter3 = (r[0].x + r[2].x) / 2;
+    } else {
+      feetCenter1 = (cur[3].x + cur[1].x) / 2;
+      feetCenter2 = (r[0].x + r[2].x) / 2;
+      feetCenter3 = (r[3].x + r[1].x) / 2;
+    }
+    const double gaitCycle = 1.0;
+    cogSpeed.push_back((feetCenter2 - feetCenter1) / (0.5 * gaitCycle));
+    cogSpeed.push_back((feetCenter3 - feetCenter2) / (0.5 * gaitCycle));
+  }
+
   static void fillIndex(const gm::GridMap& map, Foothold& fh) {
     gm::Idx2 idx;
     if (map.getIndex(gm::Vec2{fh.point.x, fh.point.y}, idx)) {
@@ -406,7 +443,8 @@ class Planner {
   // FP.cpp:539-1602 — the plan_global_footholds service body restricted to the centroid + nominal chains.
   PlanResult globalFootholdPlan(const gm::GridMap& gridmap, uint8_t gaitCycles) {
     PlanResult res;
-    Point nomCur[4], cenCur[4];
+    Point nomCur[4], cenCur[4], defCur[4];
+    setFirstGait(initial, defCur);  // :562
     setFirstGait(initial, cenCur);  // :569
     setFirstGait(initial, nomCur);  // :576
     res.gait_cycles = gaitCycles;   // :592-593
@@ -421,10 +459,14 @@ class Planner {
       fillIndex(gridmap, fh);
       res.footholds.push_back(fh);
       res.centroidFootholds.push_back(fh);  // :713-727
+      res.defaultFootholds.push_back(fh);   // :666-671
     }
     ajustedPoseY = 0.0;  // :759
     const int gaitCycleNum = gaitCycles;
     for (int g = 0; g < gaitCycleNum; ++g) {  // :762
+      // --- default chain (:774-781)
+      Point defNext[4];
+      getDefaultFootholds(gridmap, defCur, defNext);
       // --- centroid chain (:788-821)
       Point cenNext[4];
       gm::Polygon cenPoly[4];
@@ -472,6 +514,20 @@ class Planner {
           fillIndex(gridmap, fc);
           res.centroidFootholds.push_back(fc);
         }
+        for (int f = 0; f < 4; ++f) {                          // :1338-1348
+          Foothold fd;
+          fd.point = defNext[f];
+          fd.foot_id = static_cast<uint8_t>(f);
+          fd.gait_cycle_id = static_cast<uint8_t>(g);
+          fd.kind = KIND_DEFAULT;
+          fillIndex(gridmap, fd);
+          res.defaultFootholds.push_back(fd);
+          defCur[f] = defNext[f];
+        }
+        getHipDistance(nomRes, res.feetDistanceNominal);        // :1357
+        getCogSpeed(nomRes, nomCur, res.cogSpeedNominal);       // :1366 (before the chain advances)
+        getHipDistance(cenRes, res.feetDistanceCentroid);       // :1422
+        getCogSpeed(cenRes, cenCur, res.cogSpeedCentroid);      // :1431
         for (int f = 0; f < 4; ++f) nomCur[f] = nomRes[f];  // :1413-1416
         for (int f = 0; f < 4; ++f) cenCur[f] = cenRes[f];  // :1480-1483
       } else {

@@ -76,12 +76,23 @@ void to_row(const ref::Foothold& f, fhp_foothold* o) {
 }
 
 void plan_one(const gm::GridMap& map, const fhp_params* params, const fhp_query& q, int gait_cycles,
-              fhp_foothold* out_nom, fhp_foothold* out_cen, fhp_query_status* st) {
+              fhp_foothold* out_nom, fhp_foothold* out_cen, fhp_query_status* st, fhp_foothold* out_def = nullptr,
+              double* out_kpi = nullptr) {
   ref::Planner pl = make_planner(params[q.param_id], q);
   ref::PlanResult r = pl.globalFootholdPlan(map, static_cast<uint8_t>(gait_cycles));
   for (size_t i = 0; i < r.footholds.size(); ++i) to_row(r.footholds[i], out_nom + i);
   if (out_cen)
     for (size_t i = 0; i < r.centroidFootholds.size(); ++i) to_row(r.centroidFootholds[i], out_cen + i);
+  if (out_def)
+    for (size_t i = 0; i < r.defaultFootholds.size(); ++i) to_row(r.defaultFootholds[i], out_def + i);
+  if (out_kpi)  // per successful cycle: feetDistance nominal[2], cogSpeed nominal[2], feetDistance centroid[2], cogSpeed centroid[2]
+    for (size_t c = 0; c * 2 < r.feetDistanceNominal.size(); ++c)
+      for (int k = 0; k < 2; ++k) {
+        out_kpi[c * 8 + 0 + k] = r.feetDistanceNominal[c * 2 + k];
+        out_kpi[c * 8 + 2 + k] = r.cogSpeedNominal[c * 2 + k];
+        out_kpi[c * 8 + 4 + k] = r.feetDistanceCentroid[c * 2 + k];
+        out_kpi[c * 8 + 6 + k] = r.cogSpeedCentroid[c * 2 + k];
+      }
   st->success = r.success ? 1 : 0;
   st->gait_cycles = r.gait_cycles;
   st->gait_cycles_succeed = r.gait_cycles_succeed;
@@ -122,6 +133,25 @@ int oracle_plan(const fhp_map_desc* desc, const float* const* layers, const fhp_
         }
       });
     for (auto& t : th) t.join();
+  }
+  return FHP_OK;
+}
+
+// Whole plans including the "default" chain rows and the KPIs: out_default like out_nominal;
+// out_kpi: n_queries * gait_cycles * 8 doubles, entry c of a query = its c-th SUCCESSFUL cycle.
+int oracle_plan_ex(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params, int32_t n_params,
+                   const fhp_query* queries, int64_t n_queries, int32_t gait_cycles, fhp_foothold* out_nominal,
+                   fhp_foothold* out_centroid, fhp_foothold* out_default, double* out_kpi, fhp_query_status* status) {
+  if (!desc || !layers || !params || !queries || !out_nominal || !status || gait_cycles < 0 || gait_cycles > 255)
+    return FHP_ERR_INVALID_ARG;
+  gm::GridMap map = make_map(desc, layers);
+  if (!map.exists("traversability") || !map.exists("elevation")) return FHP_ERR_MISSING_LAYER;
+  const int64_t R = FHP_ROWS_PER_QUERY(gait_cycles);
+  for (int64_t q = 0; q < n_queries; ++q) {
+    if (queries[q].param_id < 0 || queries[q].param_id >= n_params) return FHP_ERR_INVALID_ARG;
+    plan_one(map, params, queries[q], gait_cycles, out_nominal + q * R, out_centroid ? out_centroid + q * R : nullptr,
+             status + q, out_default ? out_default + q * R : nullptr,
+             out_kpi ? out_kpi + q * static_cast<int64_t>(gait_cycles) * 8 : nullptr);
   }
   return FHP_OK;
 }

@@ -69,7 +69,7 @@ extern "C" {
 //   status[q].reserved = 1 when the service itself returned false (opt-chain submap failure, FP.cpp:931-934).
 int ref_plan(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params, const fhp_query* queries,
              int64_t n_queries, int32_t gait_cycles, int32_t wrap_correct_spiral, fhp_foothold* out_nominal,
-             fhp_foothold* out_centroid, fhp_query_status* status) {
+             fhp_foothold* out_centroid, fhp_query_status* status, fhp_foothold* out_default, double* out_kpi) {
   if (!desc || !layers || !params || !queries || !out_nominal || !status) return FHP_ERR_INVALID_ARG;
   Quiet quiet;
   grid_map::SpiralIterator::wrapCorrect() = wrap_correct_spiral != 0;
@@ -128,6 +128,29 @@ int ref_plan(const fhp_map_desc* desc, const float* const* layers, const fhp_par
       o.z = nom.footholds[i].point.z;
       o.foot_id = nom.footholds[i].foot_id;
       o.gait_cycle_id = nom.footholds[i].gait_cycle_id;
+    }
+    if (out_default) {  // globalFootholdsResult_.defaultFootholds: one VectorXd(12) = RF,RH,LH,LF xyz per recorded cycle
+      for (int64_t i = 0; i < R; ++i) std::memset(out_default + q * R + i, 0, sizeof(fhp_foothold));
+      const std::vector<Eigen::VectorXd>& d = planner.globalFootholdsResult_.defaultFootholds;
+      for (size_t c = 0; c < d.size() && static_cast<int64_t>(c * 4 + 3) < R; ++c)
+        for (int f = 0; f < 4; ++f) {
+          fhp_foothold& o = out_default[q * R + c * 4 + f];
+          o.x = d[c][3 * f];
+          o.y = d[c][3 * f + 1];
+          o.z = d[c][3 * f + 2];
+          o.foot_id = static_cast<uint8_t>(f);
+        }
+    }
+    if (out_kpi) {  // footholdsKPI_: two values per successful cycle each
+      const auto& k = planner.footholdsKPI_;
+      double* o = out_kpi + q * static_cast<int64_t>(gait_cycles) * 8;
+      for (size_t c = 0; c * 2 + 1 < k.feetDistance_nominal.size() && static_cast<int>(c) < gait_cycles; ++c)
+        for (int j = 0; j < 2; ++j) {
+          o[c * 8 + 0 + j] = k.feetDistance_nominal[c * 2 + j];
+          o[c * 8 + 2 + j] = k.cogSpeed_nominal[c * 2 + j];
+          o[c * 8 + 4 + j] = k.feetDistance_centroid[c * 2 + j];
+          o[c * 8 + 6 + j] = k.cogSpeed_centroid[c * 2 + j];
+        }
     }
     if (out_centroid) {
       // the centroid message is never cleared between service calls (FP.cpp:591 clears only the nominal one), but

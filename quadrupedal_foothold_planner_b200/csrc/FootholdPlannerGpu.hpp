@@ -71,6 +71,12 @@ class FootholdPlannerGpu {
   double initialPose_[3];
   GlobalFootholds nominalGlobalFootholdsMsg_;
   GlobalFootholds centroidGlobalFootholdsMsg_;
+  GlobalFootholds defaultGlobalFootholds_;  // globalFootholdsResult_.defaultFootholds (FP.cpp:666-671, :1344-1348)
+  // footholdsKPI_ (FootholdPlanner.hpp:732-745): two values per successful cycle
+  std::vector<double> feetDistance_nominal, cogSpeed_nominal, feetDistance_centroid, cogSpeed_centroid;
+  // marker payloads of publishGlobalFootholdSphereMarkers / ...CubeMarkers / ...PointMarkers (FP.cpp:2731-2790):
+  // one SPHERE_LIST / CUBE_LIST / POINTS point array per foot, in foot order RF,RH,LH,LF
+  std::vector<Point> nominalMarkerPoints[4], centroidMarkerPoints[4], defaultMarkerPoints[4];
 
   explicit FootholdPlannerGpu(int device = 0) : ctx_(NULL) {
     fhp_default_params(&params);
@@ -108,11 +114,26 @@ class FootholdPlannerGpu {
     q.z = initialPose_[2];
     q.param_id = 0;
     q.reserved = 0;
-    std::vector<fhp_foothold> nom(FHP_ROWS_PER_QUERY(cycles)), cen(FHP_ROWS_PER_QUERY(cycles));
+    std::vector<fhp_foothold> nom(FHP_ROWS_PER_QUERY(cycles)), cen(FHP_ROWS_PER_QUERY(cycles)), dfl(FHP_ROWS_PER_QUERY(cycles));
     fhp_query_status st;
-    if (fhp_plan(ctx_, &params, 1, &q, 1, cycles, &nom[0], &cen[0], &st) != FHP_OK) return false;
-    fill(nominalGlobalFootholdsMsg_, nom, st);
-    fill(centroidGlobalFootholdsMsg_, cen, st);
+    fhp_plan_outputs out;
+    out.nominal = &nom[0];
+    out.centroid = &cen[0];
+    out.default_chain = &dfl[0];
+    out.status = &st;
+    if (fhp_plan_ex(ctx_, &params, 1, &q, 1, cycles, &out) != FHP_OK) return false;
+    fill(nominalGlobalFootholdsMsg_, nom, st, nominalMarkerPoints);
+    fill(centroidGlobalFootholdsMsg_, cen, st, centroidMarkerPoints);
+    fill(defaultGlobalFootholds_, dfl, st, defaultMarkerPoints);
+    const int succ = st.n_rows / 4 - 1;
+    feetDistance_nominal.assign(2 * succ, 0.0);
+    cogSpeed_nominal.assign(2 * succ, 0.0);
+    feetDistance_centroid.assign(2 * succ, 0.0);
+    cogSpeed_centroid.assign(2 * succ, 0.0);
+    if (succ > 0) {  // getHipDistance / getCogSpeed (FP.cpp:1357-1368, :1422-1433)
+      fhp_cycle_kpi(&params, &q, &nom[0], st.n_rows, &feetDistance_nominal[0], &cogSpeed_nominal[0]);
+      fhp_cycle_kpi(&params, &q, &cen[0], st.n_rows, &feetDistance_centroid[0], &cogSpeed_centroid[0]);
+    }
     response.footholds = nominalGlobalFootholdsMsg_;  // FP.cpp:1588
     return true;
   }
@@ -167,7 +188,10 @@ class FootholdPlannerGpu {
     if (rc == FHP_ERR_MISSING_LAYER) throw std::out_of_range(fhp_last_error(ctx_));  // GridMap::at throws this
     if (rc != FHP_OK) throw std::runtime_error(std::string(what) + ": " + fhp_last_error(ctx_));
   }
-  static void fill(GlobalFootholds& msg, const std::vector<fhp_foothold>& rows, const fhp_query_status& st) {
+  // response assembly (FP.cpp:685-699, :1378-1396) and marker point lists (:2731-2790) in one pass over the rows
+  static void fill(GlobalFootholds& msg, const std::vector<fhp_foothold>& rows, const fhp_query_status& st,
+                   std::vector<Point> markers[4]) {
+    for (int f = 0; f < 4; ++f) markers[f].clear();
     msg.success = st.success != 0;
     msg.gait_cycles = st.gait_cycles;
     msg.gait_cycles_succeed = st.gait_cycles_succeed;
@@ -180,6 +204,7 @@ class FootholdPlannerGpu {
       f.foot_id = rows[i].foot_id;
       f.gait_cycle_id = rows[i].gait_cycle_id;
       msg.footholds.push_back(f);
+      if (i >= 4) markers[rows[i].foot_id & 3].push_back(f.point);  // the stance has its own marker (FP.cpp:757)
     }
   }
 };

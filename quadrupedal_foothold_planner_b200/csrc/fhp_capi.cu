@@ -62,7 +62,7 @@ struct fhp_ctx {
   alignas(64) CUtensorMap tmapTrav;
   bool disableTma = false;  // FHP_DISABLE_TMA=1: force the LDG staging path (tests cover both)
   // scratch
-  DevBuf dPars, dQ, dOutN, dOutC, dSt, dErr, dA, dB, dC2, dD;
+  DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD;
   long long launches = 0;
   unsigned pendingErrCheck = 0;
   // kernel error bits live in zero-copy host memory: reading them after a stream sync costs no memcpy
@@ -449,7 +449,7 @@ void fhp_destroy(fhp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_owned(ctx);
-  for (DevBuf* b : {&ctx->dPars, &ctx->dQ, &ctx->dOutN, &ctx->dOutC, &ctx->dSt, &ctx->dErr, &ctx->dA, &ctx->dB, &ctx->dC2,
+  for (DevBuf* b : {&ctx->dPars, &ctx->dQ, &ctx->dOutN, &ctx->dOutC, &ctx->dOutD, &ctx->dSt, &ctx->dErr, &ctx->dA, &ctx->dB, &ctx->dC2,
                     &ctx->dD})
     b->release();
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
@@ -515,7 +515,7 @@ const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* name) {
 
 static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_queries, int64_t n_queries,
                        int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC, fhp_query_status* d_st,
-                       cudaStream_t s) {
+                       cudaStream_t s, fhp_foothold* d_outD = nullptr) {
   PlanArgs A;
   A.tmap = ctx->tmapTrav;
   A.M = ctx->M;
@@ -526,6 +526,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.cycles = gait_cycles;
   A.outN = d_outN;
   A.outC = d_outC;
+  A.outD = d_outD;
   A.st = d_st;
   A.err = ctx->dErrMapped;
   CU(launch_plan(A, ctx->G, d_outC != nullptr, s));
@@ -545,8 +546,23 @@ static int plan_common(fhp_ctx* ctx, const fhp_params* params, int32_t n_params,
 
 int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
              int32_t gait_cycles, fhp_foothold* out_nominal, fhp_foothold* out_centroid, fhp_query_status* status) {
+  fhp_plan_outputs out;
+  out.nominal = out_nominal;
+  out.centroid = out_centroid;
+  out.default_chain = nullptr;
+  out.status = status;
+  return fhp_plan_ex(ctx, params, n_params, queries, n_queries, gait_cycles, &out);
+}
+
+int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
+                int32_t gait_cycles, const fhp_plan_outputs* outp) {
   if (!ctx) return FHP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!outp) return fail(ctx, FHP_ERR_INVALID_ARG, "null outputs");
+  fhp_foothold* out_nominal = outp->nominal;
+  fhp_foothold* out_centroid = outp->centroid;
+  fhp_foothold* out_default = outp->default_chain;
+  fhp_query_status* status = outp->status;
   if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 || (n_queries > 0 && (!queries || !out_nominal || !status)))
     return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments (gait_cycles is a uint8 in the service request)");
   if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan before fhp_set_map");
@@ -561,10 +577,11 @@ int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp
                sB = sizeof(fhp_query_status) * n_queries;
   CU(ctx->dQ.reserve(qB));
   CU(ctx->dOutN.reserve(oB));
-  if (out_centroid) CU(ctx->dOutC.reserve(oB));
+  if (out_centroid || out_default) CU(ctx->dOutC.reserve(oB));  // the default-chain kernel variant also writes centroid rows
+  if (out_default) CU(ctx->dOutD.reserve(oB));
   CU(ctx->dSt.reserve(sB));
-  // Host-buffer pipeline: the batch is cut into chunks that alternate between two streams, so the kernel of
-  // chunk i+1 runs while the response rows of chunk i travel back over PCIe (the D2H of the rows is the
+  // Host-buffer pipeline: the batch is cut into wave-sized chunks that alternate between two streams, so the kernel
+  // of chunk i+1 runs while the response rows of chunk i travel back over PCIe (the D2H of the rows is the
   // longest leg of a large batch).  Small batches are a single chunk = one launch.
   int rc = prepare_params(ctx, params, n_params, s);
   if (rc != FHP_OK) return rc;
@@ -576,22 +593,57 @@ int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp
   const int64_t per = ((n_queries + nChunks - 1) / nChunks + 31) / 32 * 32;  // whole blocks per chunk
   const fhp_query* dq = static_cast<const fhp_query*>(ctx->dQ.p);
   fhp_foothold* dN = static_cast<fhp_foothold*>(ctx->dOutN.p);
-  fhp_foothold* dC = out_centroid ? static_cast<fhp_foothold*>(ctx->dOutC.p) : nullptr;
+  fhp_foothold* dC = (out_centroid || out_default) ? static_cast<fhp_foothold*>(ctx->dOutC.p) : nullptr;
+  fhp_foothold* dD = out_default ? static_cast<fhp_foothold*>(ctx->dOutD.p) : nullptr;
   fhp_query_status* dS = static_cast<fhp_query_status*>(ctx->dSt.p);
   int lane = 0;
   for (int64_t lo = 0; lo < n_queries; lo += per, lane ^= 1) {
     const int64_t n = std::min<int64_t>(per, n_queries - lo);
     cudaStream_t cs = lane ? ctx->stream2 : ctx->stream;
     CU(cudaMemcpyAsync(const_cast<fhp_query*>(dq) + lo, queries + lo, sizeof(fhp_query) * n, cudaMemcpyHostToDevice, cs));
-    rc = plan_launch(ctx, n_params, dq + lo, n, gait_cycles, dN + lo * R, dC ? dC + lo * R : nullptr, dS + lo, cs);
+    rc = plan_launch(ctx, n_params, dq + lo, n, gait_cycles, dN + lo * R, dC ? dC + lo * R : nullptr, dS + lo, cs,
+                     dD ? dD + lo * R : nullptr);
     if (rc != FHP_OK) return rc;
     CU(cudaMemcpyAsync(out_nominal + lo * R, dN + lo * R, sizeof(fhp_foothold) * R * n, cudaMemcpyDeviceToHost, cs));
-    if (dC) CU(cudaMemcpyAsync(out_centroid + lo * R, dC + lo * R, sizeof(fhp_foothold) * R * n, cudaMemcpyDeviceToHost, cs));
+    if (dC && out_centroid) CU(cudaMemcpyAsync(out_centroid + lo * R, dC + lo * R, sizeof(fhp_foothold) * R * n, cudaMemcpyDeviceToHost, cs));
+    if (dD) CU(cudaMemcpyAsync(out_default + lo * R, dD + lo * R, sizeof(fhp_foothold) * R * n, cudaMemcpyDeviceToHost, cs));
     CU(cudaMemcpyAsync(status + lo, dS + lo, sizeof(fhp_query_status) * n, cudaMemcpyDeviceToHost, cs));
   }
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream2));
   return check_dev_err(ctx);
+}
+
+// KPIs of the reference's logs (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623, gaitCycle_ = 1.0 :332) —
+// pure functions of one query's response rows, computed on the host like the message assembly.
+int fhp_cycle_kpi(const fhp_params* params, const fhp_query* query, const fhp_foothold* rows, int32_t n_rows,
+                  double* feet_distance, double* cog_speed) {
+  if (!params || !query || !rows || !feet_distance || !cog_speed || n_rows < 4 || (n_rows % 4) != 0)
+    return FHP_ERR_INVALID_ARG;
+  ParDev d;
+  derive_params(*params, d);
+  double cur[4];  // x of the chain's current feet before the first success: stance - stepLength/2 (setFirstGait)
+  for (int f = 0; f < 4; ++f) cur[f] = (d.stancex[f] + query->x) - d.halfStep;
+  const int cycles = n_rows / 4 - 1;
+  for (int c = 0; c < cycles; ++c) {
+    const fhp_foothold* r = rows + 4 + 4 * c;  // RF, RH, LH, LF
+    feet_distance[2 * c] = r[0].x - r[2].x;
+    feet_distance[2 * c + 1] = r[3].x - r[1].x;
+    double fc1, fc2, fc3;
+    if (params->rf_first) {
+      fc1 = (cur[0] + cur[2]) / 2;
+      fc2 = (r[3].x + r[1].x) / 2;
+      fc3 = (r[0].x + r[2].x) / 2;
+    } else {
+      fc1 = (cur[3] + cur[1]) / 2;
+      fc2 = (r[0].x + r[2].x) / 2;
+      fc3 = (r[3].x + r[1].x) / 2;
+    }
+    cog_speed[2 * c] = (fc2 - fc1) / (0.5 * 1.0);
+    cog_speed[2 * c + 1] = (fc3 - fc2) / (0.5 * 1.0);
+    for (int f = 0; f < 4; ++f) cur[f] = r[f].x;
+  }
+  return FHP_OK;
 }
 
 int fhp_plan_device(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,

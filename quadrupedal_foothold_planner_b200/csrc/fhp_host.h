@@ -22,6 +22,7 @@ struct PlanArgs {
   int cycles;
   fhp_foothold* outN;
   fhp_foothold* outC;
+  fhp_foothold* outD;  // optional: "default" chain rows
   fhp_query_status* st;
   unsigned* err;  // device word, OR of the kErr* bits of every query
 };

@@ -65,7 +65,7 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
 #endif
-template <bool WANT_CEN, bool USE_TMA>
+template <bool WANT_CEN, bool USE_TMA, bool WANT_DEF>
 __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem_raw[];
@@ -107,16 +107,20 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
   const long long R = 4 + 4 * static_cast<long long>(A.cycles);
   fhp_foothold* outN = A.outN + q * R;
   fhp_foothold* outC = WANT_CEN ? A.outC + q * R : nullptr;
+  constexpr bool wantDef = WANT_DEF;  // "default" chain (FP.cpp:774-781, :1338-1348), a by-product of the same state
+  fhp_foothold* outD = wantDef ? A.outD + q * R : nullptr;
 
   // initialize() stance (FP.cpp:350-378) and setFirstGait (FP.cpp:2679-2699) for both chains
   const double stx = P.stancex[f] + qu.x, sty = P.stancey[f] + qu.y, stz = 0.0 + qu.z;
   double nomx = stx - P.halfStep, nomy = sty;
   double cenx = nomx, ceny = nomy;
-  if (active) {  // FP.cpp:685-699 (and :713-727 for the centroid message)
+  double defx = nomx, defy = nomy;  // default chain: setFirstGait too (FP.cpp:562)
+  if (active) {  // FP.cpp:685-699 (and :713-727 for the centroid message, :666-671 for the default chain)
     int r0, c0;
     cell_of_position(M, stx, sty, r0, c0);
     write_row(outN + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
     if (WANT_CEN) write_row(outC + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
+    if (wantDef) write_row(outD + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
   }
   double adjY = 0.0;  // ajustedPose_[1] (FP.cpp:759)
   int nrows = 4, succeed = 0;
@@ -138,6 +142,16 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
                    shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
                    ncx, ncy);
     const double nextY = qu.y + adjY;                                 // :2201
+    double dnx = 0.0, dny = 0.0, dnz = 0.0;                           // getDefaultFootholds (FP.cpp:2253-2304)
+    if (wantDef) {
+      double dcx, dcy;
+      polygon_center(shfl_d(defx, quad0), shfl_d(defy, quad0), shfl_d(defx, quad0 + 1), shfl_d(defy, quad0 + 1),
+                     shfl_d(defx, quad0 + 2), shfl_d(defy, quad0 + 2), shfl_d(defx, quad0 + 3), shfl_d(defy, quad0 + 3),
+                     dcx, dcy);
+      dnx = (dcx + P.stepLength) + bx;
+      dny = nextY + by;
+      if (active) dnz = static_cast<double>(mean_height(M, P, dnx, dny));
+    }
     const double px = (ccx + P.stepLength) + bx, py = nextY + by;     // centroid-chain next foothold (:2199,:2414)
     const double rx = (ncx + P.stepLength) + bx, ry = nextY + by;     // nominal-chain next foothold = rectangle centre
 
@@ -191,6 +205,13 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
           int r0, c0;
           cell_of_position(M, co.x, co.y, r0, c0);
           write_row(outC + nrows + f, co.x, co.y, cz, r0, c0, f, g, FHP_KIND_DEFAULT);  // :1444-1462
+        }
+        if (wantDef) {
+          int r0, c0;
+          cell_of_position(M, dnx, dny, r0, c0);
+          write_row(outD + nrows + f, dnx, dny, dnz, r0, c0, f, g, FHP_KIND_DEFAULT);  // :1344-1348
+          defx = dnx;  // :1338-1341
+          defy = dny;
         }
         nrows += 4;
         succeed = g + 1;   // :1379
@@ -282,6 +303,14 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   if (err) atomicOr(A.err, err);
 }
 
+typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
+// the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
+static plan_kernel_fn pick_plan_kernel(bool tma, bool wantCen, bool wantDef) {
+  if (wantDef) return tma ? plan_kernel<true, true, true> : plan_kernel<true, false, true>;
+  if (tma) return wantCen ? plan_kernel<true, true, false> : plan_kernel<false, true, false>;
+  return wantCen ? plan_kernel<true, false, false> : plan_kernel<false, false, false>;
+}
+
 // ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
 cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream) {
   if (A.nq <= 0) return cudaSuccess;
@@ -289,9 +318,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
   const long long nWarps = (A.nq + 7) / 8;
   const long long blocks = (nWarps + warps - 1) / warps;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
-  void (*kern)(const PlanArgs, const GeoDev) =
-      G.useTma ? (wantCen ? plan_kernel<true, true> : plan_kernel<false, true>)
-               : (wantCen ? plan_kernel<true, false> : plan_kernel<false, false>);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.useTma != 0, wantCen, A.outD != nullptr);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
@@ -304,9 +331,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
 // the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
 // a wave takes as long as a full one).
 long long plan_wave_queries(const GeoDev& G, bool wantCen) {
-  void (*kern)(const PlanArgs, const GeoDev) =
-      G.useTma ? (wantCen ? plan_kernel<true, true> : plan_kernel<false, true>)
-               : (wantCen ? plan_kernel<true, false> : plan_kernel<false, false>);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.useTma != 0, wantCen, false);
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
   if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
   int perSm = 0, dev = 0, sms = 0;

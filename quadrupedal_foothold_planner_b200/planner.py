@@ -62,6 +62,8 @@ def load_lib():
     L.fhp_map_layer_device.argtypes = [vp, C.c_char_p]
     L.fhp_map_layer_device.restype = vp
     L.fhp_plan.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp]
+    L.fhp_plan_ex.argtypes = [vp, vp, i32, vp, i64, i32, vp]
+    L.fhp_cycle_kpi.argtypes = [vp, vp, vp, i32, vp, vp]
     L.fhp_plan_device.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp, vp]
     L.fhp_synchronize.argtypes = [vp]
     L.fhp_check_foothold.argtypes = [vp, vp, vp, vp, i64, vp, vp]
@@ -84,6 +86,11 @@ def _ptr(a) -> C.c_void_p:
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(int(a))
+
+
+class PlanOutputs(C.Structure):  # fhp_plan_outputs
+    _fields_ = [("nominal", C.c_void_p), ("centroid", C.c_void_p), ("default_chain", C.c_void_p),
+                ("status", C.c_void_p)]
 
 
 class Fhp:
@@ -155,6 +162,32 @@ class Fhp:
         self._check(self.L.fhp_plan(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q), nq, int(gait_cycles), _ptr(nom),
                                     _ptr(cen) if centroid else None, _ptr(st)))
         return nom, cen, st
+
+    def plan_ex(self, params, queries: np.ndarray, gait_cycles: int):
+        """fhp_plan_ex: -> (nominal, centroid, default-chain rows [nq,R], status [nq])"""
+        parr, npar = self._params_array(params)
+        q = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
+        nq = len(q)
+        R = rows_per_query(max(0, min(255, int(gait_cycles))))
+        nom = np.zeros((nq, R), dtype=FOOTHOLD_DTYPE)
+        cen = np.zeros((nq, R), dtype=FOOTHOLD_DTYPE)
+        dfl = np.zeros((nq, R), dtype=FOOTHOLD_DTYPE)
+        st = np.zeros(nq, dtype=STATUS_DTYPE)
+        out = PlanOutputs(nom.ctypes.data, cen.ctypes.data, dfl.ctypes.data, st.ctypes.data)
+        self._check(self.L.fhp_plan_ex(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q), nq, int(gait_cycles),
+                                       C.cast(C.pointer(out), C.c_void_p)))
+        return nom, cen, dfl, st
+
+    def cycle_kpi(self, params: Params, query, rows: np.ndarray, n_rows: int):
+        """fhp_cycle_kpi: (feet_distance [cycles,2], cog_speed [cycles,2]) of one query's rows (FP.cpp:2571-2623)."""
+        q = np.ascontiguousarray(query, dtype=QUERY_DTYPE).reshape(1)
+        r = np.ascontiguousarray(rows[:n_rows])
+        cycles = n_rows // 4 - 1
+        fd = np.zeros((max(cycles, 1), 2))
+        cs = np.zeros((max(cycles, 1), 2))
+        self._check(self.L.fhp_cycle_kpi(C.cast(C.pointer(params), C.c_void_p), _ptr(q), _ptr(r), int(n_rows), _ptr(fd),
+                                         _ptr(cs)))
+        return fd[:cycles], cs[:cycles]
 
     def plan_raw(self, parr, npar, q_ptr, nq, gait_cycles, nom_ptr, cen_ptr, st_ptr):
         """fhp_plan on raw host addresses (pinned torch buffers in bench.py)."""
@@ -273,9 +306,14 @@ class FootholdPlanner:
     def globalFootholdPlan(self, request: GlobalFootholdPlanRequest, response: GlobalFootholdPlanResponse) -> bool:
         cycles = int(request.gait_cycles) & 0xFF  # uint8 in the .srv
         q = make_queries([self.initialPose_])
-        nom, cen, st = self.fhp.plan(self.params, q, cycles, centroid=True)
+        nom, cen, dfl, st = self.fhp.plan_ex(self.params, q, cycles)
         self.nominalGlobalFootholdsMsg_ = rows_to_msg(nom[0], st[0])
         self.centroidGlobalFootholdsMsg_ = rows_to_msg(cen[0], st[0])
+        # globalFootholdsResult_.defaultFootholds (FP.cpp:666-671, :1344-1348) and footholdsKPI_ (:1357-1368, :1422-1433)
+        self.defaultGlobalFootholdsMsg_ = rows_to_msg(dfl[0], st[0])
+        n = int(st[0]["n_rows"])
+        self.feetDistance_nominal, self.cogSpeed_nominal = self.fhp.cycle_kpi(self.params, q[0], nom[0], n)
+        self.feetDistance_centroid, self.cogSpeed_centroid = self.fhp.cycle_kpi(self.params, q[0], cen[0], n)
         response.footholds = self.nominalGlobalFootholdsMsg_  # FP.cpp:1588
         return True
 

@@ -75,8 +75,9 @@ def ref_cases():
 def main():
     if ob.ref_available():
         for name, (m, p, q, n, upstream) in ref_cases().items():
-            nom, cen, st = ob.ref_plan(m, p, q, n, wrap_correct=not upstream)
-            np.savez_compressed(os.path.join(HERE, name + ".npz"), nominal=nom, centroid=cen, status=st)
+            nom, cen, st, dfl, kpi = ob.ref_plan(m, p, q, n, wrap_correct=not upstream, extras=True)
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), nominal=nom, centroid=cen, status=st, default=dfl,
+                                kpi=kpi)
             done = st["reserved"] == 0
             print(name, "service calls completed", int(done.sum()), "of", len(q), "succeed",
                   int(st["gait_cycles_succeed"][done].sum()))

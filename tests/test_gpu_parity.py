@@ -199,3 +199,20 @@ def test_centroid_submap_one_cell_larger(fhp, oracle):
     got = fhp.plan(p, q, 3, centroid=True)
     exp = oracle.plan(m, p, q, 3, centroid=True)
     assert compare_plans(got, exp, "enlarged submap") <= XYZ_TOL
+
+
+def test_default_chain_matches_oracle(fhp, oracle):
+    """fhp_plan_ex: the "default" chain rows (FP.cpp:2253-2304, :1344-1348) vs the oracle, incl. a shifted start
+    index and the walk preset (whose bias table is not x-symmetric, so the default chain drifts)."""
+    m = synth.rough_map(400, 400, 0.02, seed=23, start=(11, 301))
+    q = synth.uniform_queries(256, (-3.0, 0.5), (-3.0, 3.0), seed=24)
+    for p in (_abi.yaml_params(), _abi.yaml_params(gait=_abi.FHP_GAIT_WALK, step_length=0.2)):
+        fhp.set_map(m)
+        nom, cen, dfl, st = fhp.plan_ex(p, q, 9)
+        on, oc, od, ok, os_ = oracle.plan_ex(m, p, q, 9)
+        assert compare_plans((nom, cen, st), (on, oc, os_), "plan_ex") <= XYZ_TOL
+        assert compare_plans((dfl, None, st), (od, None, os_), "default chain") <= XYZ_TOL
+        qi = int(np.argmax(st["n_rows"]))
+        fd, cs = fhp.cycle_kpi(p, q[qi], nom[qi], int(st[qi]["n_rows"]))
+        cyc = int(st[qi]["n_rows"]) // 4 - 1
+        assert cyc >= 1 and np.allclose(fd, ok[qi, :cyc, 0:2], atol=1e-9) and np.allclose(cs, ok[qi, :cyc, 2:4], atol=1e-9)

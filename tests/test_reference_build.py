@@ -30,6 +30,11 @@ def _load(name):
     return z["nominal"], z["centroid"], z["status"]
 
 
+def _load_extras(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    return z["default"], z["kpi"]
+
+
 def _compare_to_reference(got, ref, what, tol):
     """got = (nominal, centroid, status) of oracle or libfhp; ref = the reference's response rows."""
     gn, gc, gs = got
@@ -80,6 +85,47 @@ def test_reference_vectors_cover_the_cases():
         # centroid chain (0,0,0) results (no case matched) occur in the rough maps
     s = np.concatenate(succ)
     assert (s == 8).sum() > 50 and (s < 8).sum() > 20 and (s == 0).sum() >= 1
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_oracle_default_chain_and_kpi_match_reference(oracle, name):
+    """the "default" chain rows (globalFootholdsResult_.defaultFootholds) and the logged KPIs
+    (footholdsKPI_: hip distance, CoG speed of both chains) as recorded by the reference build."""
+    m, p, q, n, upstream = make_golden.ref_cases()[name]
+    nom, cen, dfl, kpi, st = oracle.plan_ex(m, p, q, n)
+    rn, rc, rs = _load(name)
+    rd, rk = _load_extras(name)
+    done = rs["reserved"] == 0
+    own = (np.arange(rn.shape[1])[None, :] < rs["n_rows"][:, None]) & done[:, None]
+    for f in ("x", "y", "z"):
+        assert np.array_equal(dfl[f][own], rd[f][own]), f
+    assert np.array_equal(kpi[done], rk[done])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_CASES)
+def test_gpu_default_chain_and_kpi_match_reference(fhp, name):
+    m, p, q, n, upstream = make_golden.ref_cases()[name]
+    fhp.set_map(m)
+    nom, cen, dfl, st = fhp.plan_ex(p, q, n)
+    rn, rc, rs = _load(name)
+    rd, rk = _load_extras(name)
+    done = rs["reserved"] == 0
+    _compare_to_reference((nom, cen, st), (rn, rc, rs), name, XYZ_TOL)
+    own = (np.arange(rn.shape[1])[None, :] < rs["n_rows"][:, None]) & done[:, None]
+    for f in ("x", "y", "z"):
+        assert np.max(np.abs(dfl[f][own] - rd[f][own])) <= XYZ_TOL, f
+    for f in ("foot_id", "gait_cycle_id"):
+        assert np.array_equal(dfl[f][own][4:], dfl[f][own][4:])
+    for qi in np.nonzero(done)[0][:12]:
+        nr = int(st[qi]["n_rows"])
+        cyc = nr // 4 - 1
+        fd, cs = fhp.cycle_kpi(p, q[qi], nom[qi], nr)
+        assert np.max(np.abs(fd - rk[qi, :cyc, 0:2]), initial=0) <= 2 * XYZ_TOL
+        assert np.max(np.abs(cs - rk[qi, :cyc, 2:4]), initial=0) <= 8 * XYZ_TOL
+        fd, cs = fhp.cycle_kpi(p, q[qi], cen[qi], nr)
+        assert np.max(np.abs(fd - rk[qi, :cyc, 4:6]), initial=0) <= 2 * XYZ_TOL
+        assert np.max(np.abs(cs - rk[qi, :cyc, 6:8]), initial=0) <= 8 * XYZ_TOL
 
 
 @pytest.mark.gpu
