@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     if (wantDef) write_row(outD + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
   }
   double adjY = 0.0;  // ajustedPose_[1] (FP.cpp:759)
+  int prevW0 = -0x7fffffff, prevW1 = -0x7fffffff;  // window staged in the previous cycle (still in this lane's slot)
   int nrows = 4, succeed = 0;
   bool success = false;
   unsigned err = 0;
@@ -169,10 +170,15 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
       dw = disc_window(M, px, py, P.r);
       prefetch_disc(M, M.elev, dw);
     }
+    // A query that failed keeps its chains (FP.cpp:1571-1576) and only drifts 7 mm sideways per cycle, so its next
+    // window is usually the SAME cells: the bit-planes are still in this lane's slot, nothing to stage.
+    const bool restage = active && !(w0 == prevW0 && w1 == prevW1);
+    prevW0 = w0;
+    prevW1 = w1;
     if (USE_TMA)
-      stage_windows_tma(M, G, &A.tmap, T, sw, lane, active, w0, w1, thrD, thrC);
+      stage_windows_tma(M, G, &A.tmap, T, sw, lane, restage, w0, w1, thrD, thrC);
     else
-      stage_windows(M, G, sw, lane, active, w0, w1, thrD, thrC);
+      stage_windows(M, G, sw, lane, restage, w0, w1, thrD, thrC);
 
 #if FHP_SYNC_LEVEL >= 2
     __syncthreads();
