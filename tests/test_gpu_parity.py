@@ -216,3 +216,28 @@ def test_default_chain_matches_oracle(fhp, oracle):
         fd, cs = fhp.cycle_kpi(p, q[qi], nom[qi], int(st[qi]["n_rows"]))
         cyc = int(st[qi]["n_rows"]) // 4 - 1
         assert cyc >= 1 and np.allclose(fd, ok[qi, :cyc, 0:2], atol=1e-9) and np.allclose(cs, ok[qi, :cyc, 2:4], atol=1e-9)
+
+
+def test_c3_full_size_bit_exact(fhp, oracle):
+    """BASELINE config 3 at FULL size — the bench.py workload: 65,536 queries x 16 cycles on the 4000x4000 @0.02 m
+    rough map with start index (1234,2777) — every row of every query against the oracle (all host threads)."""
+    import os
+    m, q, n = synth.config_c3()
+    p = _abi.yaml_params()
+    fhp.set_map(m)
+    got = fhp.plan(p, q, n, centroid=True)
+    exp = oracle.plan(m, p, q, n, n_threads=os.cpu_count() or 4, centroid=True)
+    assert compare_plans(got, exp, "C3 full size") == 0.0
+    st = got[2]
+    assert 0.2 < st["success"].mean() < 0.95 and st["n_rows"].sum() > 2_000_000
+
+
+def test_c2_full_size_bit_exact(fhp, oracle):
+    """BASELINE config 2 at full size: walk preset, 1024 start poses x 32 cycles, 2000x2000 @0.01 m stairs/stones."""
+    import os
+    m, q, n = synth.config_c2()
+    p = _abi.yaml_params(gait=_abi.FHP_GAIT_WALK)
+    fhp.set_map(m)
+    got = fhp.plan(p, q, n, centroid=True)
+    exp = oracle.plan(m, p, q, n, n_threads=os.cpu_count() or 4, centroid=True)
+    assert compare_plans(got, exp, "C2 full size") == 0.0
