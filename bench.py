@@ -380,7 +380,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_foothold": {"read_unique_cells": w_in, "rows_written": w_out},
-                         "spiral_taken_frac": spiral_frac, "kernel": "plan_kernel<false>",
+                         "spiral_taken_frac": spiral_frac, "kernel": "plan_kernel<false,true,false> (TMA staging)",
                          "avg_launch_ms": ms_per_step},
         }
         if world == 1:
