@@ -18,7 +18,6 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <cstdio>
 
 #include "fhp_types.h"
 
@@ -131,7 +130,6 @@ struct Planes {  // view of one query's staged window in shared memory
     sh = (b & 3) << 3;
     return (w[k * 4 + plane] >> sh) & 0xffu;
   }
-  __device__ __forceinline__ bool bit(int plane, int a, int b) const { return (col(plane, b) >> a) & 1u; }
 };
 enum { PL_D = 0, PL_C = 1, PL_F = 2 };
 

@@ -12,7 +12,6 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // error bits reported per query (status.reserved) — any non-zero bit fails the whole call loudly
 constexpr unsigned kErrWindow = 1u;   // a cell needed by the reference lies outside the staged window
-constexpr unsigned kErrDiscBig = 2u;  // foot disc window larger than 64 cells
 
 struct MapDev {
   const float* trav;

@@ -241,3 +241,28 @@ def test_c2_full_size_bit_exact(fhp, oracle):
     got = fhp.plan(p, q, n, centroid=True)
     exp = oracle.plan(m, p, q, n, n_threads=os.cpu_count() or 4, centroid=True)
     assert compare_plans(got, exp, "C2 full size") == 0.0
+
+
+def test_row_pitch_not_multiple_of_16_bytes(fhp, oracle):
+    """TMA needs the row pitch (rows*4 bytes) to be a multiple of 16: a 302-row map silently takes the LDG staging
+    path on the default context too — results must not change."""
+    m = synth.rough_map(302, 290, 0.02, seed=41, start=(5, 200))
+    q = synth.uniform_queries(200, (-2.0, 0.5), (-2.0, 2.0), seed=42)
+    p = _abi.yaml_params()
+    fhp.set_map(m)
+    got = fhp.plan(p, q, 8, centroid=True)
+    exp = oracle.plan(m, p, q, 8, centroid=True)
+    assert compare_plans(got, exp, "odd pitch") == 0.0
+
+
+def test_large_map_fine_resolution(fhp, oracle):
+    """C5-shaped stress (reduced): 6000x6000 @0.01 m (144 MB per layer), three layers (the extra `slope` layer is
+    carried but unused), wrapped start index, 2048 queries x 32 cycles — the 32-row / 23-column box geometry."""
+    import os
+    m = synth.rough_map(6000, 6000, 0.01, seed=6, start=(4321, 1234), with_slope=True, pitch_m=0.35)
+    q = synth.uniform_queries(2048, (-28.0, 22.0), (-28.0, 28.0), seed=7)
+    p = _abi.yaml_params()
+    fhp.set_map(m)
+    got = fhp.plan(p, q, 32, centroid=True)
+    exp = oracle.plan(m, p, q, 32, n_threads=os.cpu_count() or 4, centroid=True)
+    assert compare_plans(got, exp, "large fine map") == 0.0
