@@ -60,7 +60,16 @@ struct fhp_ctx {
   GeoDev G{};
   // TMA descriptor of the traversability layer (box = one staged window); rebuilt with the geometry tables
   alignas(64) CUtensorMap tmapTrav;
-  bool disableTma = false;  // FHP_DISABLE_TMA=1: force the LDG staging path (tests cover both)
+  // preferred window staging path: FHP_STAGING=mask|tma|ldg (default mask; FHP_DISABLE_TMA=1 is the old spelling
+  // of ldg).  The tests run every path; calls the preferred path cannot serve fall back mask -> tma -> ldg.
+  int stagePref = kStageMask;
+  int geoStage = -1;  // staging path the cached geometry tables were laid out for
+  // D/C/F mask planes of the traversability layer for one threshold pair (rebuilt lazily after a map update)
+  DevBuf dMask;
+  bool maskValid = false;
+  float maskThrD = 0, maskThrC = 0;
+  int maskRowWords = 0;
+  long long maskBuilds = 0;
   // scratch
   DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD;
   long long launches = 0;
@@ -111,6 +120,7 @@ int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
   M.fcx = M.posx + (M.halfx - 0.5 * M.res);      // mapPosition + getVectorToFirstCell
   M.fcy = M.posy + (M.halfy - 0.5 * M.res);
   ctx->haveGeo = false;
+  ctx->maskValid = false;  // every map update passes through here
   return FHP_OK;
 }
 
@@ -185,7 +195,6 @@ int sgn(int v) { return (v > 0) - (v < 0); }
 // Returns false (=> LDG staging path) when TMA's layout rules are not met: row pitch not a multiple of 16 bytes,
 // base pointer not 16-byte aligned, or the driver entry point is unavailable.
 bool build_tma(fhp_ctx* ctx) {
-  if (ctx->disableTma) return false;
   const MapDev& M = ctx->M;
   const GeoDev& G = ctx->G;
   if (!M.trav || (M.rows % 4) != 0 || (reinterpret_cast<uintptr_t>(M.trav) & 15u) != 0) return false;
@@ -214,8 +223,9 @@ bool build_tma(fhp_ctx* ctx) {
 
 // Tables that depend only on (footRadius, searchRadius, resolution): the SpiralIterator visiting order and the
 // cell-centred foot-disc stencil.
-int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim) {
-  if (ctx->haveGeo && ctx->geoFoot == footRadius && ctx->geoSearch == searchRadius && ctx->geoTrim == allowTrim)
+int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim, int stage) {
+  if (ctx->haveGeo && ctx->geoFoot == footRadius && ctx->geoSearch == searchRadius && ctx->geoTrim == allowTrim &&
+      ctx->geoStage == stage)
     return FHP_OK;
   const MapDev& M = ctx->M;
   GeoDev& G = ctx->G;
@@ -272,6 +282,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   if (G.WIN > 32)
     return fail(ctx, FHP_ERR_UNSUPPORTED, "(searchRadius+footRadius)/resolution needs a window wider than 32 cells");
   G.pack = G.WIN <= 8 ? 4 : (G.WIN <= 16 ? 2 : 1);
+  if (stage == kStageMask) G.pack = 1;  // one 16-byte {D, C, F, pad} entry per window column
   G.rpShift = G.pack == 4 ? 3 : (G.pack == 2 ? 4 : 5);
   G.nIter = (G.WIN + G.pack - 1) / G.pack;
   G.stride = 4 * G.nIter;
@@ -320,8 +331,11 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   G.tmaB = 1 << G.tmaBShift;
   G.mbarOff = planesEnd;                                   // multiple of 4 words -> 8-byte aligned
   G.boxOff = ((G.mbarOff + warps * 4 + 31) / 32) * 32;     // 128-byte aligned
-  G.useTma = build_tma(ctx) ? 1 : 0;
+  G.useTma = (stage == kStageTma && build_tma(ctx)) ? 1 : 0;
+  G.stageMode = stage == kStageTma ? (G.useTma ? kStageTma : kStageLdg) : stage;
+  G.winRows = G.useTma ? std::min(32 / G.pack, G.WIN + 3) : G.WIN;
   G.smemWords = G.useTma ? G.boxOff + warps * 2 * G.tmaB * G.boxWords : planesEnd;
+  ctx->geoStage = stage;
   ctx->geoFoot = footRadius;
   ctx->geoSearch = searchRadius;
   ctx->geoTrim = allowTrim;
@@ -337,8 +351,27 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   bool allowTrim = true;  // see build_geo: ring trimming is exact unless the bug-compatible spiral meets a shifted start
   for (int i = 0; i < n_params; ++i)
     if (params[i].spiral_mode == FHP_SPIRAL_FAITHFUL && !(ctx->M.start0 == 0 && ctx->M.start1 == 0)) allowTrim = false;
-  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim);
+  // the mask planes bake the two thresholds in: usable when every parameter set of the call shares them
+  int stage = ctx->stagePref;
+  if (stage == kStageMask)
+    for (int i = 1; i < n_params; ++i)
+      if (params[i].thr_default != params[0].thr_default || params[i].thr_candidate != params[0].thr_candidate)
+        stage = kStageTma;
+  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim, stage);
   if (rc != FHP_OK) return rc;
+  if (ctx->G.stageMode == kStageMask &&
+      !(ctx->maskValid && ctx->maskThrD == params[0].thr_default && ctx->maskThrC == params[0].thr_candidate)) {
+    ctx->maskRowWords = (ctx->M.rows + 31) / 32;
+    CU(ctx->dMask.reserve(static_cast<size_t>(ctx->maskRowWords) * ctx->M.cols * sizeof(uint4)));
+    CU(launch_mask_build(ctx->M, params[0].thr_default, params[0].thr_candidate, static_cast<uint4*>(ctx->dMask.p),
+                         ctx->maskRowWords, s));
+    CU(cudaStreamSynchronize(s));  // later calls may run on other streams
+    ctx->maskThrD = params[0].thr_default;
+    ctx->maskThrC = params[0].thr_candidate;
+    ctx->maskValid = true;
+    ctx->maskBuilds += 1;
+    ctx->launches += 1;
+  }
   if (ctx->dPars.p && ctx->lastParams.size() == static_cast<size_t>(n_params) &&
       std::memcmp(ctx->lastParams.data(), params, sizeof(fhp_params) * n_params) == 0)
     return FHP_OK;  // same parameter sets as the previous call: the derived table is already on the device
@@ -431,8 +464,13 @@ int fhp_create(int device, fhp_ctx** out) {
   fhp_ctx* ctx = new fhp_ctx();
   ctx->device = device;
   std::memset(&ctx->tmapTrav, 0, sizeof(ctx->tmapTrav));
-  const char* dt = std::getenv("FHP_DISABLE_TMA");
-  ctx->disableTma = dt && dt[0] == '1';
+  if (const char* dt = std::getenv("FHP_DISABLE_TMA"))
+    if (dt[0] == '1') ctx->stagePref = kStageLdg;
+  if (const char* st = std::getenv("FHP_STAGING")) {
+    if (!std::strcmp(st, "mask")) ctx->stagePref = kStageMask;
+    else if (!std::strcmp(st, "tma")) ctx->stagePref = kStageTma;
+    else if (!std::strcmp(st, "ldg")) ctx->stagePref = kStageLdg;
+  }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
@@ -450,7 +488,7 @@ void fhp_destroy(fhp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_owned(ctx);
   for (DevBuf* b : {&ctx->dPars, &ctx->dQ, &ctx->dOutN, &ctx->dOutC, &ctx->dOutD, &ctx->dSt, &ctx->dErr, &ctx->dA, &ctx->dB, &ctx->dC2,
-                    &ctx->dD})
+                    &ctx->dD, &ctx->dMask})
     b->release();
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
   cudaStreamDestroy(ctx->stream);
@@ -519,6 +557,8 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   PlanArgs A;
   A.tmap = ctx->tmapTrav;
   A.M = ctx->M;
+  A.mask = static_cast<const uint4*>(ctx->dMask.p);
+  A.maskRowWords = ctx->maskRowWords;
   A.pars = static_cast<const ParDev*>(ctx->dPars.p);
   A.nPars = n_params;
   A.q = d_queries;

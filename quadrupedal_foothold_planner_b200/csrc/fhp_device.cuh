@@ -418,6 +418,79 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
   __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------ mask staging
+// The thresholds are per-call constants, so the three predicates of a cell are computed ONCE per map update
+// (mask_build_kernel) into `mask`: entry (k, c) = {D, C, F, 0} for buffer rows 32k..32k+31 of buffer column c, stored
+// k-major (entry index k*cols + c) so that neighbouring columns of a row word are contiguous.  Staging a window is
+// then pure word work: window column b, rows w0..w0+WIN-1 = funnel shift of entries (k0, col) and (k0+1, col).
+// 8 lanes serve one window (consecutive columns -> one or two 128-byte lines per load instruction), 4 windows per
+// pass; each lane writes its columns straight into the owner's slot (pack = 1 layout: 16 bytes per column).
+// Fast = the window lies inside the map and does not cross the circular-buffer ROW seam (the column seam is
+// handled per column); everything else takes stage_slow on the float layer, exactly like the other paths.
+__device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev& G, const uint4* __restrict__ mask,
+                                                   int rowWords, uint32_t smemWarp, int lane, bool has_window, int w0,
+                                                   int w1, float thrD, float thrC) {
+  const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -32 || w1 <= -G.WIN);
+  int bb0 = w0 + M.start0, bb1 = w1 + M.start1;  // |w| <= 2^30 + HW: no overflow
+  if (bb0 >= M.rows) bb0 -= M.rows;
+  if (bb1 >= M.cols) bb1 -= M.cols;
+  const bool fast = has_window && w0 >= 0 && w1 >= 0 && w0 <= M.rows - G.WIN && w1 <= M.cols - G.WIN &&
+                    bb0 <= M.rows - G.WIN;
+  const unsigned fastMask = __ballot_sync(kFull, fast);
+  const unsigned slowMask = __ballot_sync(kFull, has_window && !fast && !empty);
+  if (__ballot_sync(kFull, has_window) == 0u) {
+    __syncwarp();
+    return;
+  }
+  __syncwarp();  // every lane is done reading the planes of the previous leg/cycle
+  if (empty) {
+    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
+    for (int k = 0; k < G.nIter; ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
+  }
+  if (fastMask) {
+    const int k0 = bb0 >> 5;
+    const int org = k0 * M.cols;                                  // entry index of (k0, column 0); < 2^27
+    const int sh = (bb0 & 31) | ((k0 + 1 < rowWords) ? 32 : 0);   // row shift; bit 5: the next row word exists
+    const int sub = lane & 7, grp = lane >> 3;
+    for (int pass = 0; pass < 8; ++pass) {
+      if (((fastMask >> (pass * 4)) & 0xfu) == 0u) continue;  // warp-uniform
+      const int j = pass * 4 + grp;
+      const int jorg = __shfl_sync(kFull, org, j);
+      const int jb1 = __shfl_sync(kFull, bb1, j);
+      const int jsh = __shfl_sync(kFull, sh, j);
+      const bool jf = (fastMask >> j) & 1u;
+      const int s = jsh & 31;
+      const int hiStep = (jsh & 32) ? M.cols : 0;  // last row word of the map: the high half is never needed
+      const uint4* src = mask + jorg;
+      const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
+      for (int c = sub; c < G.WIN; c += 16) {  // two columns per iteration: four independent loads in flight
+        const int ca = c, cb = c + 8;
+        const bool fa = jf, fb = jf && cb < G.WIN;
+        int cola = jb1 + ca, colb = jb1 + cb;
+        if (cola >= M.cols) cola -= M.cols;
+        if (colb >= M.cols) colb -= M.cols;
+        uint4 la = make_uint4(0, 0, 0, 0), ha = la, lb = la, hb = la;
+        if (fa) {
+          la = __ldg(src + cola);
+          ha = __ldg(src + hiStep + cola);
+        }
+        if (fb) {
+          lb = __ldg(src + colb);
+          hb = __ldg(src + hiStep + colb);
+        }
+        if (fa)
+          sts_v4(dst + static_cast<uint32_t>(ca) * 16u, __funnelshift_r(la.x, ha.x, s), __funnelshift_r(la.y, ha.y, s),
+                 __funnelshift_r(la.z, ha.z, s), 0u);
+        if (fb)
+          sts_v4(dst + static_cast<uint32_t>(cb) * 16u, __funnelshift_r(lb.x, hb.x, s), __funnelshift_r(lb.y, hb.y, s),
+                 __funnelshift_r(lb.z, hb.z, s), 0u);
+      }
+    }
+  }
+  if (slowMask) stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
+  __syncwarp();
+}
+
 // CircleIterator::findSubmapParameters: bounded corners -> unwrapped index window [tl, br] of the foot disc
 struct DiscWin {
   int tl0, tl1, br0, br1;
@@ -529,7 +602,7 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
   // window coordinates of the submap inside the staged planes
   const int a0 = tl0 - w0, a1 = br0 - w0, c0 = tl1 - w1, c1 = br1 - w1;
   uint32_t any, edgeRel;  // bit i <-> submap row i: any cell below the threshold / row is an "edge"
-  if (a0 < 0 || c0 < 0 || a1 >= min(32, G.WIN + 3) || c1 >= G.WIN) {
+  if (a0 < 0 || c0 < 0 || a1 >= G.winRows || c1 >= G.WIN) {
     // the submap sticks out of the staged window (its size is one cell larger when the corner's lattice phase is
     // within ~1e-7 of a cell boundary): count straight from global memory
     const unsigned long long pk = centroid_rows_slow(M, P.thrD, tl0, tl1, n0, n1);
@@ -637,7 +710,7 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
       if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
       ++visited;
       const int a = u0 - w0, b = u1 - w1;
-      if (a < 0 || b < 0 || a >= min(32, G.WIN + 3) || b >= G.WIN) {
+      if (a < 0 || b < 0 || a >= G.winRows || b >= G.WIN) {
         err |= kErrWindow;
         continue;
       }
@@ -653,7 +726,7 @@ __device__ __forceinline__ void box_masks(const MapDev& M, const GeoDev& G, cons
                                           uint32_t& rowsBox, uint32_t& colsBox) {
   rowsBox = 0;
   colsBox = 0;
-  const int nr = min(32, G.WIN + 3);  // the TMA path shifts the window origin down by up to 3 rows
+  const int nr = G.winRows;  // the TMA path shifts the window origin down by up to 3 rows
   for (int a = 0; a < nr; ++a) {
     const double X = pos_axis(M.fcx, M.res, w0 + a);
     if (X >= bx.xlo && X < bx.xhi) rowsBox |= 1u << a;

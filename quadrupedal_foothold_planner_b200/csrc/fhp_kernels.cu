@@ -65,12 +65,13 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
 #endif
-template <bool WANT_CEN, bool USE_TMA, bool WANT_DEF>
+template <bool WANT_CEN, int STAGE, bool WANT_DEF>
 __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem_raw[];
   // 128-byte aligned base (TMA destinations must be 128-byte aligned; the launcher adds the slack)
   uint32_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) / 4u;
+  constexpr bool USE_TMA = STAGE == kStageTma;
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
   TmaWarp T;
@@ -175,7 +176,9 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     const bool restage = active && !(w0 == prevW0 && w1 == prevW1);
     prevW0 = w0;
     prevW1 = w1;
-    if (USE_TMA)
+    if (STAGE == kStageMask)
+      stage_windows_mask(M, G, A.mask, A.maskRowWords, sw, lane, restage, w0, w1, thrD, thrC);
+    else if (USE_TMA)
       stage_windows_tma(M, G, &A.tmap, T, sw, lane, restage, w0, w1, thrD, thrC);
     else
       stage_windows(M, G, sw, lane, restage, w0, w1, thrD, thrC);
@@ -309,12 +312,57 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   if (err) atomicOr(A.err, err);
 }
 
+// ---- mask planes: one pass over the traversability layer per (map update, threshold pair) ------------------------
+// A warp owns 32 consecutive buffer columns of one row word: 32 coalesced 128-byte column reads, three ballots each,
+// lane i keeps the words of column i, then one 512-byte store.  Rows beyond the map read as NaN (all bits 0).
+__global__ void __launch_bounds__(256) mask_build_kernel(const float* __restrict__ trav, int rows, int cols, int rowWords,
+                                                         float thrD, float thrC, uint4* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int colTiles = (cols + 31) >> 5;
+  const int k = static_cast<int>(warp / colTiles), ct = static_cast<int>(warp % colTiles);
+  if (k >= rowWords) return;
+  const int row = k * 32 + lane;
+  const float inf = __int_as_float(0x7f800000);
+  uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+  for (int i0 = 0; i0 < 32; i0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = ct * 32 + i0 + i;
+      v[i] = __int_as_float(0x7fc00000);
+      if (col < cols && row < rows) v[i] = __ldg(trav + static_cast<size_t>(col) * rows + row);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t bD = __ballot_sync(kFull, v[i] < thrD);
+      const uint32_t bC = __ballot_sync(kFull, v[i] < thrC);
+      const uint32_t bF = __ballot_sync(kFull, fabsf(v[i]) < inf);
+      if (lane == i0 + i) mine = make_uint4(bD, bC, bF, 0u);
+    }
+  }
+  const int col = ct * 32 + lane;
+  if (col < cols) mask[static_cast<size_t>(k) * cols + col] = mine;
+}
+
+cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, cudaStream_t stream) {
+  const long long warps = static_cast<long long>(rowWords) * ((M.cols + 31) / 32);
+  const long long blocks = (warps + 7) / 8;
+  mask_build_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(M.trav, M.rows, M.cols, rowWords, thrD, thrC, mask);
+  return cudaGetLastError();
+}
+
 typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
 // the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
-static plan_kernel_fn pick_plan_kernel(bool tma, bool wantCen, bool wantDef) {
-  if (wantDef) return tma ? plan_kernel<true, true, true> : plan_kernel<true, false, true>;
-  if (tma) return wantCen ? plan_kernel<true, true, false> : plan_kernel<false, true, false>;
-  return wantCen ? plan_kernel<true, false, false> : plan_kernel<false, false, false>;
+template <int STAGE>
+static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef) {
+  if (wantDef) return plan_kernel<true, STAGE, true>;
+  return wantCen ? plan_kernel<true, STAGE, false> : plan_kernel<false, STAGE, false>;
+}
+static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef) {
+  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask>(wantCen, wantDef);
+  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma>(wantCen, wantDef);
+  return pick_plan_kernel_s<kStageLdg>(wantCen, wantDef);
 }
 
 // ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
@@ -324,7 +372,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
   const long long nWarps = (A.nq + 7) / 8;
   const long long blocks = (nWarps + warps - 1) / warps;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.useTma != 0, wantCen, A.outD != nullptr);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
@@ -337,7 +385,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
 // the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
 // a wave takes as long as a full one).
 long long plan_wave_queries(const GeoDev& G, bool wantCen) {
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.useTma != 0, wantCen, false);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false);
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
   if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
   int perSm = 0, dev = 0, sms = 0;

@@ -9,6 +9,10 @@ namespace fhp {
 constexpr int kMaxCand = 1024;  // spiral table entries (nRings <= 15)
 constexpr int kMaxSten = 96;    // foot-disc stencil entries
 constexpr unsigned kFull = 0xffffffffu;
+// window staging paths of plan_kernel
+constexpr int kStageLdg = 0;   // pipelined coalesced loads of the float layer + ballots
+constexpr int kStageTma = 1;   // one 2-D TMA box per window + ballots
+constexpr int kStageMask = 2;  // funnel-shifted words of the precomputed D/C/F mask planes (no per-cell work)
 
 // error bits reported per query (status.reserved) — any non-zero bit fails the whole call loudly
 constexpr unsigned kErrWindow = 1u;   // a cell needed by the reference lies outside the staged window
@@ -35,6 +39,8 @@ struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int rpShift;   // log2(32/pack): lanes per column group
   int nIter;     // ceil(WIN / pack) = words per bit-plane
   int stride;    // shared-memory words per query (4 per load iteration: D, C, F, pad)
+  int stageMode; // kStageLdg / kStageTma / kStageMask: how plan_kernel fills the planes
+  int winRows;   // window rows a consumer may read: WIN, plus the TMA row-alignment shift (<= 3) in TMA mode
   int spiralWords;  // 32-bit words reserved at the start of shared memory for the spiral table (16-byte multiple)
   // TMA staging (plan_kernel): each window is fetched as one 2-D box of boxWords floats (32 rows*cols per load
   // iteration) into shared memory; tmaB windows per round, two rounds in flight per warp.

@@ -19,17 +19,18 @@ def oracle():
     return oracle_binding
 
 
-@pytest.fixture(scope="session", params=["tma", "ldg"])
+@pytest.fixture(scope="session", params=["mask", "tma", "ldg"])
 def fhp(request):
-    """One libfhp context on cuda:0 per window-staging path (GPU tests only): "tma" = 2-D TMA box loads (default),
-    "ldg" = FHP_DISABLE_TMA=1, the pipelined LDG path that also serves maps TMA cannot describe."""
+    """One libfhp context on cuda:0 per window-staging path (GPU tests only): "mask" = precomputed D/C/F mask planes
+    (default), "tma" = 2-D TMA box loads of the float layer, "ldg" = pipelined coalesced loads (also serves maps TMA
+    cannot describe)."""
     from quadrupedal_foothold_planner_b200.planner import Fhp
-    old = os.environ.get("FHP_DISABLE_TMA")
-    os.environ["FHP_DISABLE_TMA"] = "1" if request.param == "ldg" else "0"
+    old = os.environ.get("FHP_STAGING")
+    os.environ["FHP_STAGING"] = request.param
     ctx = Fhp(0)
     if old is None:
-        del os.environ["FHP_DISABLE_TMA"]
+        del os.environ["FHP_STAGING"]
     else:
-        os.environ["FHP_DISABLE_TMA"] = old
+        os.environ["FHP_STAGING"] = old
     yield ctx
     ctx.close()
