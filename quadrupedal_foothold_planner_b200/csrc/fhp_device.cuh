@@ -491,11 +491,17 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
   __syncwarp();
 }
 
-// CircleIterator::findSubmapParameters: bounded corners -> unwrapped index window [tl, br] of the foot disc
+// CircleIterator::findSubmapParameters: bounded corners -> unwrapped index window [tl, br] of the foot disc, plus
+// the membership of every window cell decided ONCE with the iterator's arithmetic (squared centre distance <= r^2 and
+// cell inside the map): bit (8*i1 + i0) of `m` <-> cell (tl0+i0, tl1+i1).  The default test, the height mean and the
+// prefetch all walk the same disc, so none of them repeats the double-precision work.  Windows wider than 8 cells
+// (footRadius > ~3 cells) keep m = 0 and take the generic loops.
 struct DiscWin {
   int tl0, tl1, br0, br1;
+  unsigned long long m;
+  __device__ __forceinline__ bool small() const { return br0 - tl0 < 8 && br1 - tl1 < 8; }
 };
-__device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, double cy, double r) {
+__device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, double cy, double r, double r2) {
   DiscWin d;
   const double tlx = bound_axis(cx + r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + r, M.leny, M.posy, M.halfy);
   const double brx = bound_axis(cx - r, M.lenx, M.posx, M.halfx), bry = bound_axis(cy - r, M.leny, M.posy, M.halfy);
@@ -503,38 +509,60 @@ __device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, doubl
   d.tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res, M.rinv);
   d.br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv);
   d.br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
+  d.m = 0ull;
+  if (d.small()) {
+    for (int u1 = d.tl1; u1 <= d.br1; ++u1) {
+      if (u1 < 0 || u1 >= M.cols) continue;
+      const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+      const double dy2 = dy * dy;
+      unsigned colBits = 0;
+      for (int u0 = d.tl0; u0 <= d.br0; ++u0) {
+        const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+        if (dx * dx + dy2 <= r2 && u0 >= 0 && u0 < M.rows) colBits |= 1u << (u0 - d.tl0);
+      }
+      d.m |= static_cast<unsigned long long>(colBits) << (8 * (u1 - d.tl1));
+    }
+  }
   return d;
 }
 
 // Pull the elevation cells of a foot disc towards L1 long before mean_height sums them (the loads are otherwise
 // the only exposed global latency of the scalar phase).
 __device__ __forceinline__ void prefetch_disc(const MapDev& M, const float* layer, const DiscWin& dw) {
-  for (int u0 = dw.tl0; u0 <= dw.br0; ++u0)
-    for (int u1 = dw.tl1; u1 <= dw.br1; ++u1)
-      if (in_map(M, u0, u1)) {
-        const int b0 = wrap_add(u0, M.start0, M.rows), b1 = wrap_add(u1, M.start1, M.cols);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(layer + static_cast<size_t>(b1) * M.rows + b0));
-      }
+  for (unsigned long long t = dw.m; t; t &= t - 1) {
+    const int bit = __ffsll(static_cast<long long>(t)) - 1;
+    const int b0 = wrap_add(dw.tl0 + (bit & 7), M.start0, M.rows), b1 = wrap_add(dw.tl1 + (bit >> 3), M.start1, M.cols);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(layer + static_cast<size_t>(b1) * M.rows + b0));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ a9 mean height
 // FootholdPlanner::getFootholdMeanHeight (FP.cpp:2520-2554) over grid_map::CircleIterator (row-major over the
 // bounded window in unwrapped index space, cells with squared distance <= r^2).
+__device__ __forceinline__ void height_cell(const MapDev& M, int u0, int u1, float& iHeight, float& meanHeight, int& i) {
+  const float e = load_cell(M, M.elev, u0, u1);
+  iHeight = (fabsf(e) < __int_as_float(0x7f800000)) ? e : 0.0f;
+  if (iHeight < 10.0f) {
+    i++;
+    meanHeight = meanHeight + iHeight;
+  }
+}
 __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw) {
   const int tl0 = dw.tl0, tl1 = dw.tl1, br0 = dw.br0, br1 = dw.br1;
   float iHeight = 0.0f, meanHeight = 0.0f;
   int i = 0;
-  for (int u0 = tl0; u0 <= br0; ++u0) {
-    const double dx = pos_axis(M.fcx, M.res, u0) - cx;
-    const double dx2 = dx * dx;
-    for (int u1 = tl1; u1 <= br1; ++u1) {
-      const double dy = pos_axis(M.fcy, M.res, u1) - cy;
-      if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
-      const float e = load_cell(M, M.elev, u0, u1);
-      iHeight = (fabsf(e) < __int_as_float(0x7f800000)) ? e : 0.0f;
-      if (iHeight < 10.0f) {
-        i++;
-        meanHeight = meanHeight + iHeight;
+  if (dw.small()) {  // membership already decided (disc_window); same row-major visiting order
+    for (int i0 = 0; i0 <= br0 - tl0; ++i0)
+      for (int i1 = 0; i1 <= br1 - tl1; ++i1)
+        if ((dw.m >> (8 * i1 + i0)) & 1ull) height_cell(M, tl0 + i0, tl1 + i1, iHeight, meanHeight, i);
+  } else {
+    for (int u0 = tl0; u0 <= br0; ++u0) {
+      const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+      const double dx2 = dx * dx;
+      for (int u1 = tl1; u1 <= br1; ++u1) {
+        const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+        if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
+        height_cell(M, u0, u1, iHeight, meanHeight, i);
       }
     }
   }
@@ -546,7 +574,7 @@ __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, doub
   return static_cast<float>(static_cast<double>(meanHeight) + P.h);
 }
 __device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy) {
-  return mean_height(M, P, cx, cy, disc_window(M, cx, cy, P.r));
+  return mean_height(M, P, cx, cy, disc_window(M, cx, cy, P.r, P.r2));
 }
 
 // Rare path of the centroid method: whole-window test and edge rows counted from global memory (submap rows
@@ -698,8 +726,8 @@ __device__ __forceinline__ Box search_box(const ParDev& P, double rx, double ry)
 }
 
 // FootholdPlanner::checkDefaultFoothold (FP.cpp:2039-2082): CircleIterator(centre, footRadius) on the staged planes.
-__device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl, int w0,
-                                             int w1, double cx, double cy, const DiscWin& dw, unsigned& err) {
+__device__ __noinline__ bool default_eval_generic(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl,
+                                                  int w0, int w1, double cx, double cy, const DiscWin& dw, unsigned& err) {
   int visited = 0;
   bool below = false;
   for (int u0 = dw.tl0; u0 <= dw.br0; ++u0) {
@@ -719,6 +747,23 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
     }
   }
   return (visited > 0) && !below;
+}
+__device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl, int w0,
+                                             int w1, double cx, double cy, const DiscWin& dw, unsigned& err) {
+  if (!dw.small()) return default_eval_generic(M, G, P, pl, w0, w1, cx, cy, dw, err);
+  if (dw.m == 0ull) return false;  // the disc visits no cell
+  const int a0 = dw.tl0 - w0, b0 = dw.tl1 - w1;
+  if (a0 < 0 || b0 < 0 || dw.br0 - w0 >= G.winRows || dw.br1 - w1 >= G.WIN) {
+    err |= kErrWindow;
+    return false;
+  }
+  uint32_t below = 0;
+  int b = b0;
+  for (unsigned long long t = dw.m; t; t >>= 8, ++b) {  // one byte of membership per window column
+    const uint32_t colMem = static_cast<uint32_t>(t) & 0xffu;
+    if (colMem) below |= ((pl.col(PL_D, b) & pl.col(PL_F, b)) >> a0) & colMem;
+  }
+  return below == 0u;
 }
 
 // Which window rows / columns have their cell centre inside the box, with the reference's position arithmetic.

@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
       if (c0 >= M.rows) c0 -= M.rows;
       w0 -= c0 & 3;
     }
-    DiscWin dw = {0, 0, -1, -1};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
+    DiscWin dw = {0, 0, -1, -1, 0ull};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
     if (active) {
-      dw = disc_window(M, px, py, P.r);
+      dw = disc_window(M, px, py, P.r, P.r2);
       prefetch_disc(M, M.elev, dw);
     }
     // A query that failed keeps its chains (FP.cpp:1571-1576) and only drifts 7 mm sideways per cycle, so its next
@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
   Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
   if (MODE == 0 || MODE == 3) {
-    DiscWin dw = {0, 0, -1, -1};
-    if (active) dw = disc_window(M, px, py, P.r);
+    DiscWin dw = {0, 0, -1, -1, 0ull};
+    if (active) dw = disc_window(M, px, py, P.r, P.r2);
     NominalOut no;
     if (MODE == 0)
       no = nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
