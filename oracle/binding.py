@@ -91,6 +91,19 @@ def touch_bytes(hmap, params, queries, gait_cycles, with_centroid_height=True):
     return out, sp
 
 
+def spiral_rank_hist(hmap, params, queries, gait_cycles):
+    """hist[0..255]: spiral searches that ended on their k-th visited cell; hist[256]: searches that found none."""
+    params = list(params) if isinstance(params, (list, tuple)) else [params]
+    parr = (_abi.Params * len(params))(*params)
+    d, ptrs, keep = hmap.desc()
+    hist = np.zeros(257, dtype=np.int64)
+    q = np.ascontiguousarray(queries)
+    rc = lib().oracle_spiral_rank_hist(C.byref(d), ptrs, parr, C.c_int32(len(params)), _p(q), C.c_int64(len(q)),
+                                       C.c_int32(gait_cycles), _p(hist))
+    assert rc == 0, rc
+    return hist
+
+
 def check_foothold(hmap, params, centres, rect_centres):
     d, ptrs, keep = hmap.desc()
     c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)

@@ -87,6 +87,9 @@ class Planner {
   bool centroidHeight = true;
   int64_t touchedCells = 0;
   int64_t spiralTaken = 0;  // footholds whose default-disc test failed (spiral search executed)
+  // instrumentation for kernel design (scratch statistics, never part of a result): when set, rankHist[k] counts
+  // spiral searches that ended on their k-th visited cell (k capped at 255) and rankHist[256] those that found none
+  mutable int64_t* rankHist = nullptr;
 
   void initialize() {
     // FP.cpp:340-341 (float arithmetic)
@@ -257,8 +260,9 @@ class Planner {
                               float searchRadius, const gm::Polygon& polygon, Point& footholdResult,
                               gm::Idx2* chosen = nullptr) const {
     bool validation = false;
+    int visitedCells = 0;
     for (gm::SpiralIterator it(gridmap, spiralCenter, searchRadius, p.spiralMode == SPIRAL_WRAP_CORRECT);
-         !it.isPastEnd(); ++it) {
+         !it.isPastEnd(); ++it, ++visitedCells) {
       gm::Vec2 footCenter;
       gm::Idx2 idx = *it;
       gridmap.getPosition(idx, footCenter);
@@ -272,6 +276,7 @@ class Planner {
         break;
       }
     }
+    if (rankHist) ++rankHist[validation ? (visitedCells < 255 ? visitedCells : 255) : 256];
     return validation;
   }
 

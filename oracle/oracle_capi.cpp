@@ -178,6 +178,23 @@ int oracle_plan_touch_bytes(const fhp_map_desc* desc, const float* const* layers
   return FHP_OK;
 }
 
+// Spiral statistics for kernel design: hist[0..255] = searches that ended on their k-th visited cell, hist[256] =
+// searches that found no cell (257 entries, accumulated over all queries).
+int oracle_spiral_rank_hist(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params,
+                            int32_t n_params, const fhp_query* queries, int64_t n_queries, int32_t gait_cycles,
+                            int64_t* hist257) {
+  if (!desc || !layers || !params || !queries || !hist257) return FHP_ERR_INVALID_ARG;
+  gm::GridMap map = make_map(desc, layers);
+  if (!map.exists("traversability") || !map.exists("elevation")) return FHP_ERR_MISSING_LAYER;
+  for (int64_t q = 0; q < n_queries; ++q) {
+    if (queries[q].param_id < 0 || queries[q].param_id >= n_params) return FHP_ERR_INVALID_ARG;
+    ref::Planner pl = make_planner(params[queries[q].param_id], queries[q]);
+    pl.rankHist = hist257;
+    pl.globalFootholdPlan(map, static_cast<uint8_t>(gait_cycles));
+  }
+  return FHP_OK;
+}
+
 // ---- fine-grained members (same contracts as the fhp_check_* entry points) ---------------------------------
 int oracle_check_foothold(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params,
                           const double* centres_xy, const double* rect_centres_xy, int64_t n, fhp_foothold* out,

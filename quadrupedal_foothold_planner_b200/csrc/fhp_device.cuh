@@ -821,34 +821,50 @@ __device__ __forceinline__ void spiral_entry(const uint16_t* sSpiral, int k, int
   d1 = static_cast<int>(static_cast<int8_t>(e >> 8));
 }
 
+// Bits a (< nBits) with 0 <= org + a < n: the window rows / columns whose cell index lies inside the map.
+__device__ __forceinline__ uint32_t in_range_mask(int org, int n, int nBits) {
+  const int lo = max(0, -org), hi = min(nBits - 1, n - 1 - org);
+  if (hi < lo) return 0u;
+  return (hi - lo >= 31 ? 0xffffffffu : ((1u << (hi - lo + 1)) - 1u)) << lo;
+}
+
 // checkCandidateFoothold (FP.cpp:2085-2114) over grid_map::SpiralIterator — warp-cooperative rank scan.
 // For every lane j with `need`:
-//   1. lane b (< WIN) builds the "bad cell" mask of window column b from j's staged planes: a finite cell is bad when
+//   1. lane b (< WIN) holds the "bad cell" mask of window column b of j's staged planes: a finite cell is bad when
 //      it is below candidateFootholdThreshold or its centre is outside the search rectangle (FP.cpp:2138); NaN and
-//      out-of-map cells are never bad (the CircleIterator skips them).  The masks are then dilated by the foot-disc
-//      stencil, so bit a of column b says "the foot disc centred on cell (a,b) contains a bad cell", and cells whose
-//      own index is outside the map are marked too (checkIfIndexInRange in SpiralIterator::generateRing).
+//      out-of-map cells are never bad (the CircleIterator skips them).  PAD variant (pack == 1 plane layout): lane j
+//      has already computed its masks itself and left them in the pad word of each column entry (nominal_eval), so
+//      this is one shared-memory load.  The masks are then dilated by the foot-disc stencil, so bit a of column b
+//      says "the foot disc centred on cell (a,b) contains a bad cell", and cells whose own index is outside the map
+//      are marked too (checkIfIndexInRange in SpiralIterator::generateRing).
 //   2. the 32 lanes test candidates rank base..base+31 at once: table lookup, one shuffle to fetch the column mask,
 //      one bit test, plus the exact last-two-rings distance filter; the first set bit of the ballot is the first
 //      valid cell in spiral order and the scan stops at the first 32-block that has one.
 // Handles wrap_correct mode, and faithful mode when the start index is (0,0) (identical there).
+template <bool PAD>
 __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
                                                  uint32_t smemWarp, int lane, bool need, int uc0, int uc1,
                                                  int w0, double cx, double cy, double R2, uint32_t rowsBox,
-                                                 uint32_t colsBox, bool& found, int& fq0, int& fq1) {
+                                                 uint32_t colsBox, uint32_t rowsIn, uint32_t colsIn, bool& found,
+                                                 int& fq0, int& fq1) {
   const unsigned needMask = __ballot_sync(kFull, need);
+  const int haMine = uc0 - w0;  // window row of the centre cell (HW, plus the TMA alignment shift)
   for (unsigned m = needMask; m; m &= m - 1) {
     const int j = __ffs(m) - 1;
-    const int juc0 = __shfl_sync(kFull, uc0, j), juc1 = __shfl_sync(kFull, uc1, j);
-    const int ha = juc0 - __shfl_sync(kFull, w0, j);  // window row of the centre cell (HW, plus the TMA alignment shift)
-    const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
-    const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
+    const int ha = __shfl_sync(kFull, haMine, j);
+    const uint32_t jrowsIn = __shfl_sync(kFull, rowsIn, j), jcolsIn = __shfl_sync(kFull, colsIn, j);
     // 1. column masks (lane = window column)
     uint32_t bad = 0;
-    if (lane < G.WIN) {
-      const uint32_t F = pj.col(PL_F, lane), C = pj.col(PL_C, lane);
-      const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
-      bad = F & (C | ~box);
+    if (PAD) {
+      if (lane < G.WIN) bad = lds_u32(smemWarp + static_cast<uint32_t>(j * G.stride + lane * 4 + 3) * 4u);
+    } else {
+      const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
+      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
+      if (lane < G.WIN) {
+        const uint32_t F = pj.col(PL_F, lane), C = pj.col(PL_C, lane);
+        const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
+        bad = F & (C | ~box);
+      }
     }
     uint32_t dil = bad;
     if (G.nSten > 1) {  // dilate by the foot-disc stencil (a single-cell stencil needs nothing)
@@ -862,23 +878,18 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
       }
     }
     // candidate cells outside the map: rows (bits) and this lane's column
-    {
-      const int lo = max(0, ha - juc0), hi = min(31, M.rows - 1 - juc0 + ha);  // window rows inside the map
-      uint32_t rowsIn = 0;
-      if (hi >= lo) rowsIn = (hi - lo >= 31 ? 0xffffffffu : ((1u << (hi - lo + 1)) - 1u)) << lo;
-      const int q1 = juc1 + lane - G.HW;
-      const bool colIn = q1 >= 0 && q1 < M.cols;
-      dil = colIn ? (dil | ~rowsIn) : 0xffffffffu;
-    }
+    dil = ((jcolsIn >> lane) & 1u) ? (dil | ~jrowsIn) : 0xffffffffu;
     // quick reject: no cell of the spiral footprint is acceptable even before the distance filter (a query that is
-    // stuck on an untraversable patch re-scans the same window every remaining cycle)
-    {
+    // stuck on an untraversable patch re-scans the same window every remaining cycle).  With a single-cell stencil the
+    // PAD variant has already made this test in the owning lane.
+    if (!PAD || G.nSten > 1) {
       const uint32_t footprint = (lane < G.WIN) ? (G.candRows[lane] << (ha - G.HW)) : 0u;
       if (__ballot_sync(kFull, (footprint & ~dil) != 0u) == 0u) continue;
     }
     // 2. rank scan
     bool haveC = false;
     double jcx = 0, jcy = 0, jR2 = 0;
+    int juc0 = 0, juc1 = 0;
     for (int base = 0; base < G.nCand; base += 32) {
       const int k = base + lane;
       bool cand = k < G.nCand;
@@ -892,6 +903,8 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
           jcx = __shfl_sync(kFull, cx, j);
           jcy = __shfl_sync(kFull, cy, j);
           jR2 = __shfl_sync(kFull, R2, j);
+          juc0 = __shfl_sync(kFull, uc0, j);
+          juc1 = __shfl_sync(kFull, uc1, j);
           haveC = true;
         }
         if (cand && k >= G.lastTwoStart) {
@@ -905,8 +918,8 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
         const int wd0 = __shfl_sync(kFull, d0, src), wd1 = __shfl_sync(kFull, d1, src);
         if (lane == j) {
           found = true;
-          fq0 = juc0 + wd0;
-          fq1 = juc1 + wd1;
+          fq0 = uc0 + wd0;
+          fq1 = uc1 + wd1;
         }
         break;
       }
@@ -955,7 +968,7 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
 // WARP-COLLECTIVE: every lane of the warp must call it (inactive lanes pass active = false).
 // (cx,cy): search centre; (rx,ry): centre of the search rectangle; (uc0,uc1): raw unwrapped index of the centre;
 // (w0,w1): unwrapped origin of the staged window (uc-HW, minus the TMA row-alignment shift).
-template <bool DEFAULT_ONLY>
+template <bool DEFAULT_ONLY, bool PAD>
 __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P,
                                                    const uint16_t* sSpiral, uint32_t smemWarp, int lane,
                                                    bool active, int uc0, int uc1, int w0, int w1, double cx, double cy,
@@ -966,7 +979,8 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
   o.ok = false;
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
-  const Planes pl(smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
+  const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
+  const Planes pl(mine, G.pack, G.rpShift);
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
                                in_map(M, uc0, uc1);
@@ -978,17 +992,43 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
 
   const bool need = active && !o.ok;
   const bool faithful = (P.spiralMode == FHP_SPIRAL_FAITHFUL) && !(M.start0 == 0 && M.start1 == 0);
-  uint32_t rowsBox = 0, colsBox = 0;
+  uint32_t rowsBox = 0, colsBox = 0, rowsIn = 0, colsIn = 0;
   Box bx = {0, 0, 0, 0};
+  bool found = false;
+  int fq0 = 0, fq1 = 0;
+  bool pend = need && !faithful;
   if (need) {
     o.kind = FHP_KIND_CANDIDATE;
     bx = search_box(P, rx, ry);
     box_masks(M, G, bx, w0, w1, rowsBox, colsBox);
+    rowsIn = in_range_mask(w0, M.rows, 32);
+    colsIn = in_range_mask(w1, M.cols, G.WIN);
+    if (PAD && pend) {
+      // The owning lane turns its planes into per-column "bad cell" masks once (left in the pad word of each column
+      // entry for the cooperative scan) and, for a single-cell foot stencil, settles the two most common outcomes
+      // itself: no acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
+      const int sh = (uc0 - w0) - G.HW;
+      uint32_t anyOk = 0;
+      for (int b = 0; b < G.WIN; ++b) {
+        const uint32_t F = pl.col(PL_F, b), C = pl.col(PL_C, b);
+        const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
+        const uint32_t bad = F & (C | ~box);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(b * 4 + 3) * 4u), "r"(bad) : "memory");
+        const uint32_t okb = ((colsIn >> b) & 1u) ? ((G.candRows[b] << sh) & ~bad & rowsIn) : 0u;
+        anyOk |= okb;
+        if (b == G.HW && G.lastTwoStart > 0 && ((okb >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
+          found = true;
+          fq0 = uc0;
+          fq1 = uc1;
+        }
+      }
+      if (G.nSten == 1 && (found || anyOk == 0u)) pend = false;
+      if (G.nSten > 1) found = false;  // the shortcuts need the dilated masks
+    }
   }
-  bool found = false;
-  int fq0 = 0, fq1 = 0;
-  spiral_scan_coop(M, G, sSpiral, smemWarp, lane, need && !faithful, uc0, uc1, w0, cx, cy, P.R2, rowsBox, colsBox,
-                   found, fq0, fq1);
+  if (PAD) __syncwarp();  // pad words visible to the cooperating lanes
+  spiral_scan_coop<PAD>(M, G, sSpiral, smemWarp, lane, pend, uc0, uc1, w0, cx, cy, P.R2, rowsBox, colsBox, rowsIn, colsIn,
+                        found, fq0, fq1);
   if (need && faithful)
     spiral_scan_faithful(M, G, sSpiral, pl, P.thrC, uc0, uc1, w0, cx, cy, P.R2, bx, rowsBox, colsBox, found, fq0, fq1);
   if (found) {

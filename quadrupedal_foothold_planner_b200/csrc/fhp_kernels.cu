@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
     }
     const NominalOut no =
-        nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
+        nominal_eval<false, STAGE == kStageMask>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
     const bool ok = no.ok;
 #if FHP_SYNC_LEVEL >= 3
     __syncthreads();
@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     if (active) dw = disc_window(M, px, py, P.r, P.r2);
     NominalOut no;
     if (MODE == 0)
-      no = nominal_eval<false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
+      no = nominal_eval<false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
     else
-      no = nominal_eval<true>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
+      no = nominal_eval<true, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
     if (active) {
       if (MODE == 0) {
         double z = 0.0;
