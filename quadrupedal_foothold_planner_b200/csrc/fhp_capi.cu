@@ -68,7 +68,7 @@ struct fhp_ctx {
   DevBuf dMask;
   bool maskValid = false;
   float maskThrD = 0, maskThrC = 0;
-  int maskRowWords = 0;
+  bool maskNegInf = false;  // the layer holds -inf cells: their raw compare differs from their class -> float paths
   long long maskBuilds = 0;
   // scratch
   DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD;
@@ -286,6 +286,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   G.rpShift = G.pack == 4 ? 3 : (G.pack == 2 ? 4 : 5);
   G.nIter = (G.WIN + G.pack - 1) / G.pack;
   G.stride = 4 * G.nIter;
+  G.lpwShift = G.WIN <= 8 ? 3 : (G.WIN <= 16 ? 4 : 5);
 
   // ---- SpiralIterator order: centre, then ring d = 1..nRings generated by the upstream walk and consumed from
   // the BACK of the ring vector (pointsRing_.back()/pop_back()).
@@ -343,6 +344,8 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   return FHP_OK;
 }
 
+int ensure_err_word(fhp_ctx* ctx);
+
 int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cudaStream_t s) {
   if (!params || n_params <= 0) return fail(ctx, FHP_ERR_INVALID_ARG, "params missing");
   for (int i = 1; i < n_params; ++i)
@@ -351,27 +354,35 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   bool allowTrim = true;  // see build_geo: ring trimming is exact unless the bug-compatible spiral meets a shifted start
   for (int i = 0; i < n_params; ++i)
     if (params[i].spiral_mode == FHP_SPIRAL_FAITHFUL && !(ctx->M.start0 == 0 && ctx->M.start1 == 0)) allowTrim = false;
-  // the mask planes bake the two thresholds in: usable when every parameter set of the call shares them
+  // the mask planes bake the two thresholds in: usable when every parameter set of the call shares them, the
+  // classes nest (thrC <= thrD) and the layer holds no -inf cell (found while building, see mask_build_kernel)
   int stage = ctx->stagePref;
-  if (stage == kStageMask)
+  if (stage == kStageMask) {
+    if (!(params[0].thr_candidate <= params[0].thr_default)) stage = kStageTma;
     for (int i = 1; i < n_params; ++i)
       if (params[i].thr_default != params[0].thr_default || params[i].thr_candidate != params[0].thr_candidate)
         stage = kStageTma;
-  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim, stage);
-  if (rc != FHP_OK) return rc;
-  if (ctx->G.stageMode == kStageMask &&
+  }
+  if (stage == kStageMask &&
       !(ctx->maskValid && ctx->maskThrD == params[0].thr_default && ctx->maskThrC == params[0].thr_candidate)) {
-    ctx->maskRowWords = (ctx->M.rows + 31) / 32;
-    CU(ctx->dMask.reserve(static_cast<size_t>(ctx->maskRowWords) * ctx->M.cols * sizeof(uint4)));
-    CU(launch_mask_build(ctx->M, params[0].thr_default, params[0].thr_candidate, static_cast<uint4*>(ctx->dMask.p),
-                         ctx->maskRowWords, s));
-    CU(cudaStreamSynchronize(s));  // later calls may run on other streams
+    int rc = ensure_err_word(ctx);
+    if (rc != FHP_OK) return rc;
+    const int rowWords = (ctx->M.rows + 31) / 32;
+    CU(ctx->dMask.reserve(static_cast<size_t>(rowWords) * ctx->M.cols * sizeof(uint4)));
+    ctx->hErr[1] = 0u;
+    CU(launch_mask_build(ctx->M, params[0].thr_default, params[0].thr_candidate, static_cast<uint4*>(ctx->dMask.p), rowWords,
+                         ctx->dErrMapped + 1, s));
+    CU(cudaStreamSynchronize(s));  // later calls may run on other streams; the flag word is zero-copy host memory
+    ctx->maskNegInf = (*static_cast<volatile unsigned*>(ctx->hErr + 1) & 1u) != 0u;
     ctx->maskThrD = params[0].thr_default;
     ctx->maskThrC = params[0].thr_candidate;
     ctx->maskValid = true;
     ctx->maskBuilds += 1;
     ctx->launches += 1;
   }
+  if (stage == kStageMask && ctx->maskNegInf) stage = kStageTma;
+  int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim, stage);
+  if (rc != FHP_OK) return rc;
   if (ctx->dPars.p && ctx->lastParams.size() == static_cast<size_t>(n_params) &&
       std::memcmp(ctx->lastParams.data(), params, sizeof(fhp_params) * n_params) == 0)
     return FHP_OK;  // same parameter sets as the previous call: the derived table is already on the device
@@ -398,9 +409,9 @@ int check_dev_err(fhp_ctx* ctx) {
 int ensure_err_word(fhp_ctx* ctx) {
   if (!ctx->hErr) {
     void* h = nullptr;
-    CU(cudaHostAlloc(&h, sizeof(unsigned), cudaHostAllocMapped));
+    CU(cudaHostAlloc(&h, 2 * sizeof(unsigned), cudaHostAllocMapped));  // [0] kernel error bits, [1] mask-build flags
     ctx->hErr = static_cast<unsigned*>(h);
-    *ctx->hErr = 0;
+    ctx->hErr[0] = ctx->hErr[1] = 0;
     void* d = nullptr;
     CU(cudaHostGetDevicePointer(&d, h, 0));
     ctx->dErrMapped = static_cast<unsigned*>(d);
@@ -558,7 +569,6 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.tmap = ctx->tmapTrav;
   A.M = ctx->M;
   A.mask = static_cast<const uint4*>(ctx->dMask.p);
-  A.maskRowWords = ctx->maskRowWords;
   A.pars = static_cast<const ParDev*>(ctx->dPars.p);
   A.nPars = n_params;
   A.q = d_queries;

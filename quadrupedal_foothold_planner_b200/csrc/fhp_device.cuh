@@ -419,17 +419,20 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
 }
 
 // ------------------------------------------------------------------------------------------------ mask staging
-// The thresholds are per-call constants, so the three predicates of a cell are computed ONCE per map update
-// (mask_build_kernel) into `mask`: entry (k, c) = {D, C, F, 0} for buffer rows 32k..32k+31 of buffer column c, stored
-// k-major (entry index k*cols + c) so that neighbouring columns of a row word are contiguous.  Staging a window is
-// then pure word work: window column b, rows w0..w0+WIN-1 = funnel shift of entries (k0, col) and (k0+1, col).
-// 8 lanes serve one window (consecutive columns -> one or two 128-byte lines per load instruction), 4 windows per
-// pass; each lane writes its columns straight into the owner's slot (pack = 1 layout: 16 bytes per column).
+// The thresholds are per-call constants, so the predicates of a cell are computed ONCE per map update
+// (mask_build_kernel) as a 2-bit class per cell — 0 not finite, 1 finite and >= thrD, 2 finite in [thrC, thrD),
+// 3 finite and < thrC (thrC <= thrD; maps holding -inf cells, whose raw compare differs from their class, and
+// thrC > thrD take the float paths) — split into two bit planes e0/e1 over buffer rows.  Entry (k, c) of `mask` =
+// {e0 rows 32k..32k+31, e0 rows 32k+32..32k+63, e1 same, e1 same} of buffer column c, stored k-major (index
+// k*cols + c): ONE 16-byte load holds the 32 window rows starting at any row of word k, and neighbouring columns
+// are contiguous.  Staging a window column = 1 load, 2 funnel shifts, D = e1, C = e0 & e1, F = e0 | e1, 1 store.
+// 2^lpwShift lanes serve one window (consecutive columns -> one or two 128-byte lines per load instruction) and
+// write straight into the owner's slot (pack = 1 layout: 16 bytes {D, C, F, pad} per column).
 // Fast = the window lies inside the map and does not cross the circular-buffer ROW seam (the column seam is
 // handled per column); everything else takes stage_slow on the float layer, exactly like the other paths.
 __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev& G, const uint4* __restrict__ mask,
-                                                   int rowWords, uint32_t smemWarp, int lane, bool has_window, int w0,
-                                                   int w1, float thrD, float thrC) {
+                                                   uint32_t smemWarp, int lane, bool has_window, int w0, int w1,
+                                                   float thrD, float thrC) {
   const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -32 || w1 <= -G.WIN);
   int bb0 = w0 + M.start0, bb1 = w1 + M.start1;  // |w| <= 2^30 + HW: no overflow
   if (bb0 >= M.rows) bb0 -= M.rows;
@@ -448,42 +451,38 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
     for (int k = 0; k < G.nIter; ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
   }
   if (fastMask) {
-    const int k0 = bb0 >> 5;
-    const int org = k0 * M.cols;                                  // entry index of (k0, column 0); < 2^27
-    const int sh = (bb0 & 31) | ((k0 + 1 < rowWords) ? 32 : 0);   // row shift; bit 5: the next row word exists
-    const int sub = lane & 7, grp = lane >> 3;
-    for (int pass = 0; pass < 8; ++pass) {
-      if (((fastMask >> (pass * 4)) & 0xfu) == 0u) continue;  // warp-uniform
-      const int j = pass * 4 + grp;
-      const int jorg = __shfl_sync(kFull, org, j);
-      const int jb1 = __shfl_sync(kFull, bb1, j);
-      const int jsh = __shfl_sync(kFull, sh, j);
-      const bool jf = (fastMask >> j) & 1u;
-      const int s = jsh & 31;
-      const int hiStep = (jsh & 32) ? M.cols : 0;  // last row word of the map: the high half is never needed
-      const uint4* src = mask + jorg;
-      const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
-      for (int c = sub; c < G.WIN; c += 16) {  // two columns per iteration: four independent loads in flight
-        const int ca = c, cb = c + 8;
-        const bool fa = jf, fb = jf && cb < G.WIN;
-        int cola = jb1 + ca, colb = jb1 + cb;
-        if (cola >= M.cols) cola -= M.cols;
-        if (colb >= M.cols) colb -= M.cols;
-        uint4 la = make_uint4(0, 0, 0, 0), ha = la, lb = la, hb = la;
-        if (fa) {
-          la = __ldg(src + cola);
-          ha = __ldg(src + hiStep + cola);
-        }
-        if (fb) {
-          lb = __ldg(src + colb);
-          hb = __ldg(src + hiStep + colb);
-        }
-        if (fa)
-          sts_v4(dst + static_cast<uint32_t>(ca) * 16u, __funnelshift_r(la.x, ha.x, s), __funnelshift_r(la.y, ha.y, s),
-                 __funnelshift_r(la.z, ha.z, s), 0u);
-        if (fb)
-          sts_v4(dst + static_cast<uint32_t>(cb) * 16u, __funnelshift_r(lb.x, hb.x, s), __funnelshift_r(lb.y, hb.y, s),
-                 __funnelshift_r(lb.z, hb.z, s), 0u);
+    const int org = (bb0 >> 5) * M.cols;          // entry index of (row word, column 0); < 2^27
+    const int b1s = bb1 | ((bb0 & 31) << 26);     // first buffer column | row shift (cols < 2^26)
+    const int lpw = 1 << G.lpwShift;              // lanes per window
+    const int c = lane & (lpw - 1);
+    const int grp = lane >> G.lpwShift;
+    const int wpp = 32 >> G.lpwShift;             // windows per pass
+    const unsigned passBits = (wpp >= 32) ? 0xffffffffu : ((1u << wpp) - 1u);
+    const bool cIn = c < G.WIN;
+    for (int j0 = 0; j0 < 32; j0 += 2 * wpp) {    // two passes per iteration: two independent loads in flight
+      const bool anyA = ((fastMask >> j0) & passBits) != 0u;
+      const bool anyB = (j0 + wpp < 32) && ((fastMask >> (j0 + wpp)) & passBits) != 0u;
+      if (!anyA && !anyB) continue;  // warp-uniform
+      const int ja = j0 + grp, jb = (j0 + wpp + grp) & 31;
+      const int orgA = __shfl_sync(kFull, org, ja), bsA = __shfl_sync(kFull, b1s, ja);
+      const int orgB = __shfl_sync(kFull, org, jb), bsB = __shfl_sync(kFull, b1s, jb);
+      const bool fa = cIn && ((fastMask >> ja) & 1u);
+      const bool fb = cIn && anyB && ((fastMask >> jb) & 1u);
+      int colA = (bsA & 0x3ffffff) + c, colB = (bsB & 0x3ffffff) + c;
+      if (colA >= M.cols) colA -= M.cols;
+      if (colB >= M.cols) colB -= M.cols;
+      uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
+      if (fa) ea = __ldg(mask + orgA + colA);
+      if (fb) eb = __ldg(mask + orgB + colB);
+      if (fa) {
+        const int s = static_cast<unsigned>(bsA) >> 26;
+        const uint32_t e0 = __funnelshift_r(ea.x, ea.y, s), e1 = __funnelshift_r(ea.z, ea.w, s);
+        sts_v4(smemWarp + static_cast<uint32_t>(ja * G.stride + c * 4) * 4u, e1, e0 & e1, e0 | e1, 0u);
+      }
+      if (fb) {
+        const int s = static_cast<unsigned>(bsB) >> 26;
+        const uint32_t e0 = __funnelshift_r(eb.x, eb.y, s), e1 = __funnelshift_r(eb.z, eb.w, s);
+        sts_v4(smemWarp + static_cast<uint32_t>(jb * G.stride + c * 4) * 4u, e1, e0 & e1, e0 | e1, 0u);
       }
     }
   }

@@ -15,8 +15,7 @@ constexpr int kPlanThreads = FHP_PLAN_THREADS;
 struct PlanArgs {
   alignas(64) CUtensorMap tmap;  // traversability layer, box = one staged window (valid iff G.useTma)
   MapDev M;
-  const uint4* mask;  // D/C/F mask planes of the traversability layer (valid iff G.stageMode == kStageMask)
-  int maskRowWords;   // ceil(rows / 32)
+  const uint4* mask;  // cell-class planes of the traversability layer (valid iff G.stageMode == kStageMask)
   const ParDev* pars;
   int nPars;
   const fhp_query* q;
@@ -44,7 +43,8 @@ struct TaskArgs {
 
 cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream);
 long long plan_wave_queries(const GeoDev& G, bool wantCen);
-cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, cudaStream_t stream);
+cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, unsigned* flags,
+                              cudaStream_t stream);
 cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream_t stream);
 
 }  // namespace fhp

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     prevW0 = w0;
     prevW1 = w1;
     if (STAGE == kStageMask)
-      stage_windows_mask(M, G, A.mask, A.maskRowWords, sw, lane, restage, w0, w1, thrD, thrC);
+      stage_windows_mask(M, G, A.mask, sw, lane, restage, w0, w1, thrD, thrC);
     else if (USE_TMA)
       stage_windows_tma(M, G, &A.tmap, T, sw, lane, restage, w0, w1, thrD, thrC);
     else
@@ -313,10 +313,13 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
 }
 
 // ---- mask planes: one pass over the traversability layer per (map update, threshold pair) ------------------------
-// A warp owns 32 consecutive buffer columns of one row word: 32 coalesced 128-byte column reads, three ballots each,
-// lane i keeps the words of column i, then one 512-byte store.  Rows beyond the map read as NaN (all bits 0).
+// A warp owns 32 consecutive buffer columns of one row word k: 32 coalesced 128-byte column reads, two ballots each
+// (the 2-bit cell class, see stage_windows_mask), lane i keeps the words of column i; the words go to entry (k, c)
+// as the low halves and to entry (k-1, c) as the high halves.  Rows beyond the map read as NaN (class 0); the high
+// halves of the last row word are zeroed by the warp that owns it.  *flags |= 1 when a -inf cell is seen.
 __global__ void __launch_bounds__(256) mask_build_kernel(const float* __restrict__ trav, int rows, int cols, int rowWords,
-                                                         float thrD, float thrC, uint4* __restrict__ mask) {
+                                                         float thrD, float thrC, uint4* __restrict__ mask,
+                                                         unsigned* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const long long warp = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int colTiles = (cols + 31) >> 5;
@@ -324,7 +327,8 @@ __global__ void __launch_bounds__(256) mask_build_kernel(const float* __restrict
   if (k >= rowWords) return;
   const int row = k * 32 + lane;
   const float inf = __int_as_float(0x7f800000);
-  uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t m0 = 0u, m1 = 0u;
+  bool negInf = false;
   for (int i0 = 0; i0 < 32; i0 += 8) {
     float v[8];
 #pragma unroll
@@ -335,20 +339,41 @@ __global__ void __launch_bounds__(256) mask_build_kernel(const float* __restrict
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint32_t bD = __ballot_sync(kFull, v[i] < thrD);
-      const uint32_t bC = __ballot_sync(kFull, v[i] < thrC);
-      const uint32_t bF = __ballot_sync(kFull, fabsf(v[i]) < inf);
-      if (lane == i0 + i) mine = make_uint4(bD, bC, bF, 0u);
+      const bool fin = fabsf(v[i]) < inf;
+      const bool bD = fin && v[i] < thrD, bC = fin && v[i] < thrC;
+      negInf |= (v[i] == -inf);
+      const uint32_t e0 = __ballot_sync(kFull, fin && (bC || !bD));  // classes 1 and 3
+      const uint32_t e1 = __ballot_sync(kFull, bD);                  // classes 2 and 3
+      if (lane == i0 + i) {
+        m0 = e0;
+        m1 = e1;
+      }
     }
   }
+  if (negInf) atomicOr(flags, 1u);
   const int col = ct * 32 + lane;
-  if (col < cols) mask[static_cast<size_t>(k) * cols + col] = mine;
+  if (col < cols) {
+    uint32_t* e = reinterpret_cast<uint32_t*>(mask + static_cast<size_t>(k) * cols + col);
+    e[0] = m0;
+    e[2] = m1;
+    if (k + 1 == rowWords) {
+      e[1] = 0u;
+      e[3] = 0u;
+    }
+    if (k > 0) {
+      uint32_t* p = reinterpret_cast<uint32_t*>(mask + static_cast<size_t>(k - 1) * cols + col);
+      p[1] = m0;
+      p[3] = m1;
+    }
+  }
 }
 
-cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, cudaStream_t stream) {
+cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, unsigned* flags,
+                              cudaStream_t stream) {
   const long long warps = static_cast<long long>(rowWords) * ((M.cols + 31) / 32);
   const long long blocks = (warps + 7) / 8;
-  mask_build_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(M.trav, M.rows, M.cols, rowWords, thrD, thrC, mask);
+  mask_build_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(M.trav, M.rows, M.cols, rowWords, thrD, thrC, mask,
+                                                                       flags);
   return cudaGetLastError();
 }
 
