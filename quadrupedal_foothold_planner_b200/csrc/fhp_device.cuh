@@ -39,6 +39,17 @@ __device__ __forceinline__ double bound_axis(double p, double len, double mp, do
 // IEEE double division as ONE out-of-line subroutine: the inline expansion is ~35 instructions per site, and the
 // instruction footprint of the scalar phases is what limits this kernel (profiles/).
 __device__ __noinline__ double div_rn(double a, double b) { return a / b; }
+// a / 3.0, correctly rounded, without the division subroutine: y = RN(1/3); a quotient estimate refined once is
+// faithful, and Markstein's final step q + RN(a - 3q)*y (residual exact in one FMA) then rounds correctly.  The FMAs
+// are explicit (the translation unit is built with -fmad=false); operands outside the guard band (where a residual
+// could leave the normal range) take the exact subroutine.  scratch-tested against a/3.0 on 4e8 operands.
+__device__ __forceinline__ double div3_rn(double a) {
+  if (!(fabs(a) > 1e-280 && fabs(a) < 1e280)) return div_rn(a, 3.0);
+  const double y = 0.33333333333333331482961625624739;  // 0x3FD5555555555555
+  const double q0 = a * y;
+  const double q1 = __fma_rn(__fma_rn(-3.0, q0, a), y, q0);
+  return __fma_rn(__fma_rn(-3.0, q1, a), y, q1);
+}
 
 // getIndexFromPosition without the start-index wrap: (int)(-(((p - 0.5*len) - mapPos)/res)).
 // Fast path: multiply by the correctly rounded reciprocal; the product differs from the IEEE quotient by at most a
@@ -471,9 +482,9 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
       int colA = (bsA & 0x3ffffff) + c, colB = (bsB & 0x3ffffff) + c;
       if (colA >= M.cols) colA -= M.cols;
       if (colB >= M.cols) colB -= M.cols;
-      uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
-      if (fa) ea = __ldg(mask + orgA + colA);
-      if (fb) eb = __ldg(mask + orgB + colB);
+      // (lanes without a column load entry 0: valid memory, result unused — cheaper than predicated zero-fills)
+      const uint4 ea = __ldg(mask + (fa ? orgA + colA : 0));
+      const uint4 eb = __ldg(mask + (fb ? orgB + colB : 0));
       if (fa) {
         const int s = static_cast<unsigned>(bsA) >> 26;
         const uint32_t e0 = __funnelshift_r(ea.x, ea.y, s), e1 = __funnelshift_r(ea.z, ea.w, s);
@@ -766,19 +777,30 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
 }
 
 // Which window rows / columns have their cell centre inside the box, with the reference's position arithmetic.
+// The cell-centre coordinate pos(org + a) strictly decreases with a, so "pos < bound" is false...false,true...true
+// over a = 0..n-1: first_below returns the first a where it holds (n if none), found from a reciprocal estimate and
+// verified with the exact predicate on both sides (any estimate gives the right answer; a good one costs two tests).
+__device__ __forceinline__ int first_below(double fc, double res, double rinv, int org, int n, double bound) {
+  double t = (fc - bound) * rinv - static_cast<double>(org);  // pos(org+a) < bound  <=>  a > t (up to rounding)
+  t = fmin(fmax(t, -1.0), static_cast<double>(n));             // NaN -> -1
+  int a = static_cast<int>(t) + 1;
+  a = max(0, min(a, n));
+  while (a > 0 && pos_axis(fc, res, org + a - 1) < bound) --a;
+  while (a < n && !(pos_axis(fc, res, org + a) < bound)) ++a;
+  return a;
+}
+__device__ __forceinline__ uint32_t bits_between(int lo, int hi) {  // bits lo..hi-1 (0 <= lo, hi <= 32)
+  if (hi <= lo) return 0u;
+  const uint32_t upTo = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+  return upTo & ~((1u << lo) - 1u);
+}
 __device__ __forceinline__ void box_masks(const MapDev& M, const GeoDev& G, const Box& bx, int w0, int w1,
                                           uint32_t& rowsBox, uint32_t& colsBox) {
-  rowsBox = 0;
-  colsBox = 0;
-  const int nr = G.winRows;  // the TMA path shifts the window origin down by up to 3 rows
-  for (int a = 0; a < nr; ++a) {
-    const double X = pos_axis(M.fcx, M.res, w0 + a);
-    if (X >= bx.xlo && X < bx.xhi) rowsBox |= 1u << a;
-    if (a < G.WIN) {
-      const double Y = pos_axis(M.fcy, M.res, w1 + a);
-      if (Y >= bx.ylo && Y < bx.yhi) colsBox |= 1u << a;
-    }
-  }
+  // inside: lo <= pos < hi  <=>  first_below(hi) <= a < first_below(lo)
+  rowsBox = bits_between(first_below(M.fcx, M.res, M.rinv, w0, G.winRows, bx.xhi),
+                         first_below(M.fcx, M.res, M.rinv, w0, G.winRows, bx.xlo));
+  colsBox = bits_between(first_below(M.fcy, M.res, M.rinv, w1, G.WIN, bx.yhi),
+                         first_below(M.fcy, M.res, M.rinv, w1, G.WIN, bx.ylo));
 }
 
 // checkCirclePolygonFoothold (FP.cpp:2117-2163) for the candidate at window coordinates (qa,qb), on the planes:
@@ -979,7 +1001,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
   const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
-  const Planes pl(mine, G.pack, G.rpShift);
+  const Planes pl(mine, PAD ? 1 : G.pack, G.rpShift);  // PAD <=> mask staging: pack is 1 at compile time
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
                                in_map(M, uc0, uc1);

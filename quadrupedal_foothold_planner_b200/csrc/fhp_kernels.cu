@@ -31,8 +31,8 @@ __device__ __forceinline__ void polygon_center(double rfx, double rfy, double rh
   sum_x += (x1 + x2 + x3) * s;
   sum_y += (y1 + y2 + y3) * s;
   sum_s += s;
-  cx = div_rn(div_rn(sum_x, sum_s), 3.0);
-  cy = div_rn(div_rn(sum_y, sum_s), 3.0);
+  cx = div3_rn(div_rn(sum_x, sum_s));
+  cy = div3_rn(div_rn(sum_y, sum_s));
 }
 
 __device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y, double z, int row, int col, int foot,
@@ -60,7 +60,7 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 }
 
 #ifndef FHP_SYNC_LEVEL
-#define FHP_SYNC_LEVEL 2
+#define FHP_SYNC_LEVEL 3
 #endif
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
@@ -191,9 +191,12 @@ __global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel
     co.ccase = -1;
     double nz = 0.0, cz = 0.0;
     if (active) {
-      Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
+      Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, STAGE == kStageMask ? 1 : G.pack, G.rpShift);
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
     }
+#if FHP_SYNC_LEVEL >= 4
+    __syncthreads();
+#endif
     const NominalOut no =
         nominal_eval<false, STAGE == kStageMask>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
     const bool ok = no.ok;
