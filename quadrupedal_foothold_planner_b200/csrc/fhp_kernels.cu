@@ -65,8 +65,11 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
 #endif
+#ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
+#define FHP_PLAN_MIN_BLOCKS_MASK 7
+#endif
 template <bool WANT_CEN, int STAGE, bool WANT_DEF>
-__global__ void __launch_bounds__(kPlanThreads, FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
+__global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem_raw[];
   // 128-byte aligned base (TMA destinations must be 128-byte aligned; the launcher adds the slack)

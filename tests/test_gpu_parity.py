@@ -266,3 +266,35 @@ def test_large_map_fine_resolution(fhp, oracle):
     got = fhp.plan(p, q, 32, centroid=True)
     exp = oracle.plan(m, p, q, 32, n_threads=os.cpu_count() or 4, centroid=True)
     assert compare_plans(got, exp, "large fine map") == 0.0
+
+
+def test_mask_planes_lifecycle_and_fallbacks(fhp, oracle):
+    """The cell-class mask planes are a cache of (map, thresholds): rebuilt on a threshold change and on a map update;
+    maps with infinite cells and thrC > thrD (where a 2-bit class cannot represent the reference's raw compares) take
+    the float staging paths.  Every combination must equal the oracle."""
+    q = synth.uniform_queries(384, (-4.0, 1.0), (-4.0, 4.0), seed=13)
+    ma = synth.rough_map(500, 500, 0.02, seed=31, start=(40, 9))
+    mb = synth.rough_map(500, 500, 0.02, seed=32, start=(40, 9))
+    pa, pb = _abi.yaml_params(), _abi.yaml_params(thr_default=0.8, thr_candidate=0.5)
+    fhp.set_map(ma)
+    for p, name in ((pa, "thr A"), (pb, "thr B"), (pa, "thr A again")):
+        assert compare_plans(fhp.plan(p, q, 8), oracle.plan(ma, p, q, 8), name) <= XYZ_TOL
+    fhp.set_map(mb)  # same geometry, new cell values
+    assert compare_plans(fhp.plan(pa, q, 8), oracle.plan(mb, pa, q, 8), "map update") <= XYZ_TOL
+    # thrC > thrD: the classes do not nest
+    pc = _abi.yaml_params(thr_default=0.6, thr_candidate=0.85)
+    assert compare_plans(fhp.plan(pc, q, 8), oracle.plan(mb, pc, q, 8), "thrC > thrD") <= XYZ_TOL
+    # +-inf cells: -inf compares below every threshold but is not a valid (finite) cell
+    mi = synth.rough_map(500, 500, 0.02, seed=33, start=(3, 471))
+    t = mi.layers["traversability"].copy()
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, t.size, size=t.size // 25)
+    t[np.unravel_index(idx[: len(idx) // 2], t.shape)] = -np.inf
+    t[np.unravel_index(idx[len(idx) // 2:], t.shape)] = np.inf
+    mi.set_layer("traversability", t)
+    e = mi.layers["elevation"].copy()
+    e[np.unravel_index(rng.integers(0, e.size, size=e.size // 50), e.shape)] = np.inf
+    mi.set_layer("elevation", e)
+    got, exp = _run_both(fhp, oracle, mi, pa, q, 8)
+    assert compare_plans(got, exp, "inf cells") <= XYZ_TOL
+    assert (got[2]["n_rows"] > 4).sum() > 20  # the case still plans something
