@@ -133,6 +133,50 @@ const char* fhp_version(void);
  * copied to the device once per map update (layer-planar, column-major, start index kept); the caller keeps
  * ownership of the host buffers. */
 int fhp_set_map(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* layers_colmajor_host);
+/* Message ingest — replaces GridMapRosConverter::fromMessage + the copy above in one step (FP.cpp:506; SURVEY §8f
+ * rank 1).  grid_map_ros is third-party and absent from the reference tree; the semantics restated here are those of
+ * grid_map_ros 1.6.x fromMessage / multiArrayMessageCopyToMatrixEigen / GridMap::setGeometry:
+ *   size = (int)round(length / resolution) per axis, length := size * resolution, position = info.pose.position.xy,
+ *   layers.size() must equal data.size(), every data[i] must be column-major (layout.dim[0].label == "column_index",
+ *   dim[0].size = cols, dim[1].label == "row_index", dim[1].size = rows), start index = (outer, inner)_start_index.
+ * The float arrays are read IN PLACE (no Eigen copy) and streamed to the device through pinned staging buffers.
+ * Unlike the reference (which ignores fromMessage's return value and keeps a half-updated map), a malformed message
+ * returns FHP_ERR_INVALID_ARG with upstream's error text and leaves the previous map in place.
+ *
+ * fhp_gridmap_msg: the fields of a DESERIALISED grid_map_msgs/GridMap (what a roscpp callback holds); strings are
+ * (pointer, length) pairs so std::string::data()/size() can be passed without copies. */
+typedef struct fhp_str {
+  const char* p;
+  uint32_t n;
+} fhp_str;
+typedef struct fhp_multiarray {   /* std_msgs/Float32MultiArray */
+  fhp_str dim0_label;             /* layout.dim[0].label */
+  uint32_t dim0_size;             /* layout.dim[0].size */
+  fhp_str dim1_label;             /* layout.dim[1].label */
+  uint32_t dim1_size;             /* layout.dim[1].size */
+  uint32_t n_dims;                /* layout.dim.size() (upstream reads dim[0] and dim[1]) */
+  uint32_t reserved;
+  const float* data;              /* data.data() — may be unaligned when it points into wire bytes */
+  uint64_t n;                     /* data.size() */
+} fhp_multiarray;
+typedef struct fhp_gridmap_msg {
+  double resolution, length_x, length_y; /* info.resolution, info.length_x, info.length_y */
+  double pos_x, pos_y;                   /* info.pose.position.x / .y */
+  int32_t n_layers;                      /* layers.size() */
+  int32_t n_data;                        /* data.size() */
+  const fhp_str* layers;
+  const fhp_multiarray* data;
+  uint16_t outer_start_index, inner_start_index;
+  uint32_t reserved;
+} fhp_gridmap_msg;
+int fhp_set_map_msg(fhp_ctx* ctx, const fhp_gridmap_msg* msg);
+/* Same from the ROS1 WIRE bytes of a grid_map_msgs/GridMap (what a ShapeShifter / rosbag reader / raw TCPROS
+ * subscriber holds): little-endian fields in message-definition order, strings and arrays prefixed by a uint32
+ * count.  The bytes are parsed in place; truncated or inconsistent input returns FHP_ERR_INVALID_ARG. */
+int fhp_set_map_wire(fhp_ctx* ctx, const uint8_t* bytes, uint64_t len);
+/* Geometry of the map currently held (the gridMapInfo_ the reference's callback prints, FP.cpp:508-515);
+ * layer_names is set to NULL.  FHP_ERR_NO_MAP before the first ingest. */
+int fhp_map_info(const fhp_ctx* ctx, fhp_map_desc* out);
 /* Same, but the layers are ALREADY device-resident on ctx's device (e.g. after an NCCL broadcast); the
  * pointers are adopted without a copy and must stay valid until the next fhp_set_map* / fhp_destroy. */
 int fhp_set_map_device(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* layers_colmajor_device);

@@ -41,6 +41,22 @@ class Params(C.Structure):
     ]
 
 
+class Str(C.Structure):  # fhp_str
+    _fields_ = [("p", C.c_char_p), ("n", C.c_uint32)]
+
+
+class MultiArray(C.Structure):  # fhp_multiarray (std_msgs/Float32MultiArray)
+    _fields_ = [("dim0_label", Str), ("dim0_size", C.c_uint32), ("dim1_label", Str), ("dim1_size", C.c_uint32),
+                ("n_dims", C.c_uint32), ("reserved", C.c_uint32), ("data", C.c_void_p), ("n", C.c_uint64)]
+
+
+class GridMapMsg(C.Structure):  # fhp_gridmap_msg (deserialised grid_map_msgs/GridMap)
+    _fields_ = [("resolution", C.c_double), ("length_x", C.c_double), ("length_y", C.c_double),
+                ("pos_x", C.c_double), ("pos_y", C.c_double), ("n_layers", C.c_int32), ("n_data", C.c_int32),
+                ("layers", C.POINTER(Str)), ("data", C.POINTER(MultiArray)),
+                ("outer_start_index", C.c_uint16), ("inner_start_index", C.c_uint16), ("reserved", C.c_uint32)]
+
+
 # numpy views of the array-of-struct buffers (zero-copy between numpy, ctypes and pinned torch tensors)
 QUERY_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("param_id", "<i4"), ("reserved", "<i4")])
 FOOTHOLD_DTYPE = np.dtype([

@@ -23,6 +23,51 @@
 
 #include "fhp.h"
 
+#ifndef FHP_WITH_ROS
+// stand-ins with the field names of grid_map_msgs/GridMap and the std_msgs / geometry_msgs types it embeds
+namespace std_msgs {
+struct Header {
+  uint32_t seq;
+  struct { uint32_t sec, nsec; } stamp;
+  std::string frame_id;
+  Header() : seq(0) { stamp.sec = stamp.nsec = 0; }
+};
+struct MultiArrayDimension {
+  std::string label;
+  uint32_t size, stride;
+  MultiArrayDimension() : size(0), stride(0) {}
+};
+struct MultiArrayLayout {
+  std::vector<MultiArrayDimension> dim;
+  uint32_t data_offset;
+  MultiArrayLayout() : data_offset(0) {}
+};
+struct Float32MultiArray {
+  MultiArrayLayout layout;
+  std::vector<float> data;
+};
+}  // namespace std_msgs
+namespace grid_map_msgs {
+struct GridMapInfo {
+  std_msgs::Header header;
+  double resolution, length_x, length_y;
+  struct { struct { double x, y, z; } position; struct { double x, y, z, w; } orientation; } pose;
+  GridMapInfo() : resolution(0), length_x(0), length_y(0) {
+    pose.position.x = pose.position.y = pose.position.z = 0;
+    pose.orientation.x = pose.orientation.y = pose.orientation.z = 0;
+    pose.orientation.w = 1;
+  }
+};
+struct GridMap {
+  GridMapInfo info;
+  std::vector<std::string> layers, basic_layers;
+  std::vector<std_msgs::Float32MultiArray> data;
+  uint16_t outer_start_index, inner_start_index;
+  GridMap() : outer_start_index(0), inner_start_index(0) {}
+};
+}  // namespace grid_map_msgs
+#endif
+
 namespace foothold_planner {
 
 #ifndef FHP_WITH_ROS
@@ -85,7 +130,71 @@ class FootholdPlannerGpu {
   }
   ~FootholdPlannerGpu() { fhp_destroy(ctx_); }
 
-  // FP.cpp:504-536 — upload once per map update
+  // gridMapInfo_ of the reference (FootholdPlanner.hpp; filled at FP.cpp:508-515)
+  struct GridMapInfo {
+    double x, y, length, width, resolution;
+    int row, col;
+    std::string frameID;
+    GridMapInfo() : x(0), y(0), length(0), width(0), resolution(0), row(0), col(0) {}
+  } gridMapInfo_;
+
+  // FP.cpp:504-536 with the message itself: GridMapRosConverter::fromMessage and the device upload in one step —
+  // the layer arrays are read in place from msg.data[i].data (no Eigen copy, no by-value message copy).
+  void gridmapCallback(const grid_map_msgs::GridMap& msg) {
+    std::vector<fhp_str> names(msg.layers.size());
+    for (size_t i = 0; i < msg.layers.size(); ++i) {
+      names[i].p = msg.layers[i].data();
+      names[i].n = static_cast<uint32_t>(msg.layers[i].size());
+    }
+    std::vector<fhp_multiarray> arrs(msg.data.size());
+    for (size_t i = 0; i < msg.data.size(); ++i) {
+      const std_msgs::Float32MultiArray& a = msg.data[i];
+      fhp_multiarray& v = arrs[i];
+      v.n_dims = static_cast<uint32_t>(a.layout.dim.size());
+      v.reserved = 0;
+      v.dim0_label.p = v.dim1_label.p = NULL;
+      v.dim0_label.n = v.dim1_label.n = 0;
+      v.dim0_size = v.dim1_size = 0;
+      if (v.n_dims > 0) {
+        v.dim0_label.p = a.layout.dim[0].label.data();
+        v.dim0_label.n = static_cast<uint32_t>(a.layout.dim[0].label.size());
+        v.dim0_size = a.layout.dim[0].size;
+      }
+      if (v.n_dims > 1) {
+        v.dim1_label.p = a.layout.dim[1].label.data();
+        v.dim1_label.n = static_cast<uint32_t>(a.layout.dim[1].label.size());
+        v.dim1_size = a.layout.dim[1].size;
+      }
+      v.data = a.data.empty() ? NULL : &a.data[0];
+      v.n = a.data.size();
+    }
+    fhp_gridmap_msg m;
+    m.resolution = msg.info.resolution;
+    m.length_x = msg.info.length_x;
+    m.length_y = msg.info.length_y;
+    m.pos_x = msg.info.pose.position.x;
+    m.pos_y = msg.info.pose.position.y;
+    m.n_layers = static_cast<int32_t>(names.size());
+    m.n_data = static_cast<int32_t>(arrs.size());
+    m.layers = names.empty() ? NULL : &names[0];
+    m.data = arrs.empty() ? NULL : &arrs[0];
+    m.outer_start_index = msg.outer_start_index;
+    m.inner_start_index = msg.inner_start_index;
+    m.reserved = 0;
+    check(fhp_set_map_msg(ctx_, &m), "fhp_set_map_msg");
+    fhp_map_desc d;
+    check(fhp_map_info(ctx_, &d), "fhp_map_info");
+    gridMapInfo_.x = d.pos_x;  // FP.cpp:508-515
+    gridMapInfo_.y = d.pos_y;
+    gridMapInfo_.length = d.length_x;
+    gridMapInfo_.width = d.length_y;
+    gridMapInfo_.row = d.rows;
+    gridMapInfo_.col = d.cols;
+    gridMapInfo_.resolution = d.resolution;
+    gridMapInfo_.frameID = msg.info.header.frame_id;
+  }
+
+  // the same from an already converted grid_map::GridMap (geometry + gridmap_[layer].data() pointers)
   void gridmapCallback(const GridMapView& m) {
     std::vector<const char*> names;
     for (size_t i = 0; i < m.layer_names.size(); ++i) names.push_back(m.layer_names[i].c_str());

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -53,6 +55,11 @@ struct fhp_ctx {
   std::vector<std::string> layerNames;
   std::vector<const float*> layerPtrs;  // device
   std::vector<float*> owned;            // device buffers we allocated
+  size_t ownedBytes = 0;                // size of each owned layer buffer (reused when a map update keeps its size)
+  // pinned staging of the host->device map upload (two chunks in flight; allocated on the first large upload)
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t pinEv[2] = {nullptr, nullptr};
+  bool pinUsed[2] = {false, false};
   // geometry tables cache
   bool haveGeo = false;
   float geoFoot = 0, geoSearch = 0;
@@ -96,6 +103,7 @@ int fail(const fhp_ctx* c, int code, const std::string& msg) {
 void free_owned(fhp_ctx* ctx) {
   for (float* p : ctx->owned) cudaFree(p);
   ctx->owned.clear();
+  ctx->ownedBytes = 0;
 }
 
 int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
@@ -122,6 +130,94 @@ int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
   ctx->haveGeo = false;
   ctx->maskValid = false;  // every map update passes through here
   return FHP_OK;
+}
+
+
+// ---- host -> device map upload ---------------------------------------------------------------------------------------
+// Pageable source memory (an Eigen matrix, a std::vector<float> of a ROS message, wire bytes) cannot be DMA'd in
+// place: a plain cudaMemcpy stages it through the driver's single-threaded bounce buffer.  Large layers instead go
+// through two pinned chunks owned by the context: chunk i+1 is filled by a few host threads while chunk i is in
+// flight, so the upload runs at min(host memcpy, PCIe) rather than at their sum.  Already-pinned sources and small
+// layers are copied directly.
+constexpr size_t kPinChunk = 8u << 20;
+constexpr size_t kDirectBytes = 1u << 20;
+constexpr int kCopyThreads = 4;
+
+void parallel_memcpy(void* dst, const void* src, size_t n) {
+  if (n < (1u << 20)) {
+    std::memcpy(dst, src, n);
+    return;
+  }
+  const size_t per = (n / kCopyThreads + 63) & ~static_cast<size_t>(63);
+  std::thread th[kCopyThreads - 1];
+  int nt = 0;
+  for (int t = 1; t < kCopyThreads; ++t) {
+    const size_t lo = per * t;
+    if (lo >= n) break;
+    const size_t len = std::min(per, n - lo);
+    th[nt++] = std::thread([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, len); });
+  }
+  std::memcpy(dst, src, std::min(per, n));
+  for (int t = 0; t < nt; ++t) th[t].join();
+}
+
+int upload_layer(fhp_ctx* ctx, float* dst, const void* src, size_t bytes, cudaStream_t s) {
+  bool pinned = false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+  cudaGetLastError();  // unregistered host memory reports an error on older drivers; not ours
+  if (pinned || bytes <= kDirectBytes) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return FHP_OK;
+  }
+  for (int b = 0; b < 2; ++b)
+    if (!ctx->pin[b]) {
+      CU(cudaHostAlloc(&ctx->pin[b], kPinChunk, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&ctx->pinEv[b], cudaEventDisableTiming));
+    }
+  int b = 0;
+  for (size_t off = 0; off < bytes; off += kPinChunk, b ^= 1) {
+    const size_t n = std::min(kPinChunk, bytes - off);
+    if (ctx->pinUsed[b]) CU(cudaEventSynchronize(ctx->pinEv[b]));  // the DMA that last read this chunk is done
+    parallel_memcpy(ctx->pin[b], static_cast<const char*>(src) + off, n);
+    CU(cudaMemcpyAsync(reinterpret_cast<char*>(dst) + off, ctx->pin[b], n, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(ctx->pinEv[b], s));
+    ctx->pinUsed[b] = true;
+  }
+  return FHP_OK;
+}
+
+int bind_layers(fhp_ctx* ctx);
+
+// Common tail of fhp_set_map / fhp_set_map_msg / fhp_set_map_wire: geometry, device buffers (reused when the layer
+// count and size are unchanged — the steady state of a robot's periodic map updates), upload, layer binding.
+int ingest_host(fhp_ctx* ctx, const fhp_map_desc& d, const std::vector<std::string>& names,
+                const std::vector<const void*>& ptrs) {
+  for (const void* p : ptrs)
+    if (!p) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer");
+  int rc = set_geometry(ctx, &d);
+  if (rc != FHP_OK) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream2));
+  const size_t bytes = static_cast<size_t>(d.rows) * d.cols * sizeof(float);
+  if (!(ctx->owned.size() == names.size() && ctx->ownedBytes == bytes)) {
+    free_owned(ctx);
+    for (size_t i = 0; i < names.size(); ++i) {
+      float* p = nullptr;
+      CU(cudaMalloc(&p, bytes));
+      ctx->owned.push_back(p);
+    }
+    ctx->ownedBytes = bytes;
+  }
+  ctx->haveMap = false;
+  ctx->layerNames = names;
+  ctx->layerPtrs.assign(ctx->owned.begin(), ctx->owned.end());
+  for (size_t i = 0; i < names.size(); ++i) {
+    rc = upload_layer(ctx, ctx->owned[i], ptrs[i], bytes, ctx->stream);
+    if (rc != FHP_OK) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return bind_layers(ctx);
 }
 
 int bind_layers(fhp_ctx* ctx) {
@@ -502,6 +598,10 @@ void fhp_destroy(fhp_ctx* ctx) {
                     &ctx->dD, &ctx->dMask})
     b->release();
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
+    if (ctx->pinEv[b]) cudaEventDestroy(ctx->pinEv[b]);
+  }
   cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
@@ -514,25 +614,203 @@ int fhp_set_map(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* laye
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   if (!layers || !desc || !desc->layer_names) return fail(ctx, FHP_ERR_INVALID_ARG, "null map");
-  int rc = set_geometry(ctx, desc);
-  if (rc != FHP_OK) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
-  free_owned(ctx);
-  ctx->layerNames.clear();
-  ctx->layerPtrs.clear();
-  ctx->haveMap = false;
-  const size_t bytes = static_cast<size_t>(desc->rows) * desc->cols * sizeof(float);
+  std::vector<std::string> names;
+  std::vector<const void*> ptrs;
   for (int i = 0; i < desc->n_layers; ++i) {
     if (!layers[i] || !desc->layer_names[i]) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer");
-    float* d = nullptr;
-    CU(cudaMalloc(&d, bytes));
-    ctx->owned.push_back(d);
-    CU(cudaMemcpyAsync(d, layers[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->layerNames.push_back(desc->layer_names[i]);
-    ctx->layerPtrs.push_back(d);
+    names.push_back(desc->layer_names[i]);
+    ptrs.push_back(layers[i]);
   }
-  CU(cudaStreamSynchronize(ctx->stream));
-  return bind_layers(ctx);
+  return ingest_host(ctx, *desc, names, ptrs);
+}
+
+// GridMapRosConverter::fromMessage (grid_map_ros 1.6.x) on the message fields, without the Eigen copies.
+int fhp_set_map_msg(fhp_ctx* ctx, const fhp_gridmap_msg* m) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (!m || m->n_layers < 0 || m->n_data < 0 || (m->n_layers > 0 && !m->layers) || (m->n_data > 0 && !m->data))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "null grid map message");
+  // GridMap::setGeometry: size = round(length / resolution), length = size * resolution, start index reset
+  if (!(m->resolution > 0) || !std::isfinite(m->resolution) || !std::isfinite(m->length_x) || !std::isfinite(m->length_y))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "grid map message: resolution / length not finite and positive");
+  const double s0 = std::round(m->length_x / m->resolution), s1 = std::round(m->length_y / m->resolution);
+  if (!(s0 >= 1 && s1 >= 1 && s0 < 2147483647.0 && s1 < 2147483647.0))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "grid map message: empty or oversized map");
+  fhp_map_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.rows = static_cast<int32_t>(s0);
+  d.cols = static_cast<int32_t>(s1);
+  d.resolution = m->resolution;
+  d.length_x = static_cast<double>(d.rows) * m->resolution;
+  d.length_y = static_cast<double>(d.cols) * m->resolution;
+  d.pos_x = m->pos_x;
+  d.pos_y = m->pos_y;
+  d.start_row = m->outer_start_index;  // setStartIndex(Index(outer_start_index, inner_start_index))
+  d.start_col = m->inner_start_index;
+  d.n_layers = m->n_layers;
+  if (m->n_layers != m->n_data)
+    return fail(ctx, FHP_ERR_INVALID_ARG, "Different number of layers and data in grid map message.");
+  std::vector<std::string> names;
+  std::vector<const void*> ptrs;
+  const std::string colLabel = "column_index", rowLabel = "row_index";
+  for (int i = 0; i < m->n_layers; ++i) {
+    const fhp_multiarray& a = m->data[i];
+    if (!m->layers[i].p && m->layers[i].n) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer name");
+    if (a.n_dims < 2 || !a.dim0_label.p || !a.dim1_label.p)
+      return fail(ctx, FHP_ERR_INVALID_ARG, "grid map message: a data array has fewer than two layout dimensions");
+    const std::string l0(a.dim0_label.p, a.dim0_label.n);
+    if (l0 == rowLabel)  // isRowMajor(m) != EigenType::IsRowMajor
+      return fail(ctx, FHP_ERR_INVALID_ARG,
+                  "multiArrayMessageToMatrixEigen() failed because the storage order is not compatible.");
+    if (l0 != colLabel) return fail(ctx, FHP_ERR_INVALID_ARG, "isRowMajor() failed because layout label is not set correctly.");
+    // getCols = dim[0].size, getRows = dim[1].size; GridMap::add asserts the size equals the geometry's
+    if (static_cast<int64_t>(a.dim1_size) != d.rows || static_cast<int64_t>(a.dim0_size) != d.cols ||
+        a.n != static_cast<uint64_t>(d.rows) * static_cast<uint64_t>(d.cols) || !a.data)
+      return fail(ctx, FHP_ERR_INVALID_ARG, "grid map message: layer \"" + std::string(m->layers[i].p, m->layers[i].n) +
+                                                "\" does not have the size of the map geometry");
+    names.emplace_back(m->layers[i].p ? m->layers[i].p : "", m->layers[i].n);
+    ptrs.push_back(a.data);
+  }
+  if (d.start_row >= d.rows || d.start_col >= d.cols)
+    return fail(ctx, FHP_ERR_INVALID_ARG, "grid map message: start index outside the map");
+  return ingest_host(ctx, d, names, ptrs);
+}
+
+namespace {
+// bounds-checked little-endian reader over ROS1 wire bytes
+struct WireReader {
+  const uint8_t* p;
+  uint64_t n, o = 0;
+  bool ok = true;
+  WireReader(const uint8_t* p_, uint64_t n_) : p(p_), n(n_) {}
+  bool need(uint64_t k) {
+    if (!ok || k > n - o) ok = false;
+    return ok;
+  }
+  uint32_t u32() {
+    uint32_t v = 0;
+    if (need(4)) {
+      std::memcpy(&v, p + o, 4);
+      o += 4;
+    }
+    return v;
+  }
+  uint16_t u16() {
+    uint16_t v = 0;
+    if (need(2)) {
+      std::memcpy(&v, p + o, 2);
+      o += 2;
+    }
+    return v;
+  }
+  double f64() {
+    double v = 0;
+    if (need(8)) {
+      std::memcpy(&v, p + o, 8);
+      o += 8;
+    }
+    return v;
+  }
+  fhp_str str() {
+    fhp_str s = {nullptr, 0};
+    const uint32_t len = u32();
+    if (need(len)) {
+      s.p = reinterpret_cast<const char*>(p + o);
+      s.n = len;
+      o += len;
+    }
+    return s;
+  }
+  uint32_t count(uint64_t minElemBytes) {  // array length prefix, bounded by the bytes that are actually there
+    const uint32_t c = u32();
+    if (ok && static_cast<uint64_t>(c) * minElemBytes > n - o) ok = false;
+    return ok ? c : 0;
+  }
+};
+}  // namespace
+
+// grid_map_msgs/GridMap, ROS1 serialisation: GridMapInfo info {Header {uint32 seq, time stamp, string frame_id},
+// float64 resolution, length_x, length_y, geometry_msgs/Pose pose}, string[] layers, string[] basic_layers,
+// std_msgs/Float32MultiArray[] data {MultiArrayLayout {MultiArrayDimension[] dim {string label, uint32 size,
+// uint32 stride}, uint32 data_offset}, float32[] data}, uint16 outer_start_index, uint16 inner_start_index.
+int fhp_set_map_wire(fhp_ctx* ctx, const uint8_t* bytes, uint64_t len) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  if (!bytes) return fail(ctx, FHP_ERR_INVALID_ARG, "null message bytes");
+  WireReader r(bytes, len);
+  fhp_gridmap_msg m;
+  std::memset(&m, 0, sizeof(m));
+  r.u32();  // header.seq
+  r.u32();  // header.stamp.secs
+  r.u32();  // header.stamp.nsecs
+  r.str();  // header.frame_id
+  m.resolution = r.f64();
+  m.length_x = r.f64();
+  m.length_y = r.f64();
+  m.pos_x = r.f64();  // pose.position.x
+  m.pos_y = r.f64();
+  r.f64();            // pose.position.z
+  for (int i = 0; i < 4; ++i) r.f64();  // pose.orientation
+  std::vector<fhp_str> layers;
+  const uint32_t nl = r.count(4);
+  for (uint32_t i = 0; i < nl && r.ok; ++i) layers.push_back(r.str());
+  const uint32_t nb = r.count(4);
+  for (uint32_t i = 0; i < nb && r.ok; ++i) r.str();  // basic_layers: not used by the path
+  std::vector<fhp_multiarray> data;
+  const uint32_t nd = r.count(12);
+  for (uint32_t i = 0; i < nd && r.ok; ++i) {
+    fhp_multiarray a;
+    std::memset(&a, 0, sizeof(a));
+    const uint32_t ndim = r.count(12);
+    a.n_dims = ndim;
+    for (uint32_t k = 0; k < ndim && r.ok; ++k) {
+      const fhp_str label = r.str();
+      const uint32_t size = r.u32();
+      r.u32();  // stride
+      if (k == 0) {
+        a.dim0_label = label;
+        a.dim0_size = size;
+      } else if (k == 1) {
+        a.dim1_label = label;
+        a.dim1_size = size;
+      }
+    }
+    r.u32();  // data_offset (upstream maps data.data() from element 0 regardless)
+    const uint32_t nf = r.count(4);
+    a.n = nf;
+    if (r.need(static_cast<uint64_t>(nf) * 4)) {
+      a.data = reinterpret_cast<const float*>(r.p + r.o);  // possibly unaligned: only ever memcpy'd
+      r.o += static_cast<uint64_t>(nf) * 4;
+    }
+    data.push_back(a);
+  }
+  m.outer_start_index = r.u16();
+  m.inner_start_index = r.u16();
+  if (!r.ok) return fail(ctx, FHP_ERR_INVALID_ARG, "grid map wire message is truncated or inconsistent");
+  if (r.o != len) return fail(ctx, FHP_ERR_INVALID_ARG, "grid map wire message has trailing bytes");
+  m.n_layers = static_cast<int32_t>(layers.size());
+  m.n_data = static_cast<int32_t>(data.size());
+  m.layers = layers.data();
+  m.data = data.data();
+  return fhp_set_map_msg(ctx, &m);
+}
+
+int fhp_map_info(const fhp_ctx* ctx, fhp_map_desc* out) {
+  if (!ctx || !out) return FHP_ERR_INVALID_ARG;
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "no map set");
+  std::memset(out, 0, sizeof(*out));
+  out->rows = ctx->M.rows;
+  out->cols = ctx->M.cols;
+  out->resolution = ctx->M.res;
+  out->length_x = ctx->M.lenx;
+  out->length_y = ctx->M.leny;
+  out->pos_x = ctx->M.posx;
+  out->pos_y = ctx->M.posy;
+  out->start_row = ctx->M.start0;
+  out->start_col = ctx->M.start1;
+  out->n_layers = static_cast<int32_t>(ctx->layerNames.size());
+  out->layer_names = nullptr;
+  return FHP_OK;
 }
 
 int fhp_set_map_device(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* layers) {

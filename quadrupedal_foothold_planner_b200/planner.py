@@ -59,6 +59,9 @@ def load_lib():
     L.fhp_version.restype = C.c_char_p
     L.fhp_set_map.argtypes = [vp, C.POINTER(MapDesc), vp]
     L.fhp_set_map_device.argtypes = [vp, C.POINTER(MapDesc), vp]
+    L.fhp_set_map_msg.argtypes = [vp, vp]
+    L.fhp_set_map_wire.argtypes = [vp, vp, C.c_uint64]
+    L.fhp_map_info.argtypes = [vp, C.POINTER(MapDesc)]
     L.fhp_map_layer_device.argtypes = [vp, C.c_char_p]
     L.fhp_map_layer_device.restype = vp
     L.fhp_plan.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp]
@@ -126,6 +129,21 @@ class Fhp:
         d, ptrs, keep = hmap.desc()
         self._check(self.L.fhp_set_map(self.h, C.byref(d), C.cast(ptrs, C.c_void_p)))
         self.map_geometry = hmap
+
+    def set_map_wire(self, wire: bytes):
+        """fhp_set_map_wire: ROS1-serialised grid_map_msgs/GridMap bytes (gridmap_msg.serialize_gridmap)."""
+        buf = np.frombuffer(wire, dtype=np.uint8)
+        self._check(self.L.fhp_set_map_wire(self.h, C.c_void_p(buf.ctypes.data), len(buf)))
+
+    def set_map_msg(self, msg):
+        """fhp_set_map_msg: a deserialised message (gridmap_msg.GridMapMessage)."""
+        cmsg, keep = msg.as_c()
+        self._check(self.L.fhp_set_map_msg(self.h, C.cast(C.pointer(cmsg), C.c_void_p)))
+
+    def map_info(self) -> MapDesc:
+        d = MapDesc()
+        self._check(self.L.fhp_map_info(self.h, C.byref(d)))
+        return d
 
     def set_map_device(self, geometry: HostMap, names: Sequence[str], device_ptrs: Sequence[int], keepalive=None):
         """Adopt device-resident layers (no copy).  `geometry` supplies rows/cols/resolution/pos/start only."""

@@ -1,6 +1,8 @@
 // Drives the C++ host shim (FootholdPlannerGpu.hpp) exactly like a ROS node would: map update, then the
 // plan_global_footholds service body.  Reads a raw map file written by the test, prints the response rows.
-//   shim_main <map.bin> <rows> <cols> <res> <start_row> <start_col> <x> <y> <z> <gait_cycles>
+//   shim_main <map.bin> <rows> <cols> <res> <start_row> <start_col> <x> <y> <z> <gait_cycles> [msg]
+// With the trailing "msg" the map arrives as a grid_map_msgs/GridMap (the reference's callback argument) instead of
+// an already converted grid_map::GridMap view.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -8,7 +10,7 @@
 #include "FootholdPlannerGpu.hpp"
 
 int main(int argc, char** argv) {
-  if (argc != 11) return 2;
+  if (argc != 11 && argc != 12) return 2;
   const int rows = atoi(argv[2]), cols = atoi(argv[3]);
   const double res = atof(argv[4]);
   std::vector<float> trav(static_cast<size_t>(rows) * cols), elev(trav.size());
@@ -31,7 +33,32 @@ int main(int argc, char** argv) {
   m.layer_names.push_back("elevation");
   m.layer_data.push_back(&trav[0]);
   m.layer_data.push_back(&elev[0]);
-  planner.gridmapCallback(m);
+  if (argc == 12) {
+    grid_map_msgs::GridMap msg;
+    msg.info.header.frame_id = "odom";
+    msg.info.resolution = res;
+    msg.info.length_x = rows * res;
+    msg.info.length_y = cols * res;
+    msg.layers = m.layer_names;
+    msg.outer_start_index = static_cast<uint16_t>(m.start_row);
+    msg.inner_start_index = static_cast<uint16_t>(m.start_col);
+    for (int l = 0; l < 2; ++l) {  // GridMapRosConverter::toMessage layout of a column-major matrix
+      std_msgs::Float32MultiArray a;
+      a.layout.dim.resize(2);
+      a.layout.dim[0].label = "column_index";
+      a.layout.dim[0].size = cols;
+      a.layout.dim[0].stride = rows * cols;
+      a.layout.dim[1].label = "row_index";
+      a.layout.dim[1].size = rows;
+      a.layout.dim[1].stride = rows;
+      a.data = l == 0 ? trav : elev;
+      msg.data.push_back(a);
+    }
+    planner.gridmapCallback(msg);
+    if (planner.gridMapInfo_.row != rows || planner.gridMapInfo_.col != cols || planner.gridMapInfo_.frameID != "odom") return 6;
+  } else {
+    planner.gridmapCallback(m);
+  }
   planner.initialPose_[0] = atof(argv[7]);
   planner.initialPose_[1] = atof(argv[8]);
   planner.initialPose_[2] = atof(argv[9]);

@@ -33,9 +33,9 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle):
     with open(path, "wb") as f:
         f.write(np.asfortranarray(m.layers["traversability"]).tobytes(order="F"))
         f.write(np.asfortranarray(m.layers["elevation"]).tobytes(order="F"))
-    for pose in ([-2.5, 0.3, 0.0], [-1.0, -1.2, 0.125]):
+    for pose, extra in (([-2.5, 0.3, 0.0], []), ([-1.0, -1.2, 0.125], ["msg"])):  # second run: message callback
         out = subprocess.check_output([exe, path, "400", "300", "0.02", "31", "250", repr(pose[0]), repr(pose[1]),
-                                       repr(pose[2]), "9"], text=True).strip().splitlines()
+                                       repr(pose[2]), "9"] + extra, text=True).strip().splitlines()
         nom, _, st = oracle.plan(m, _abi.yaml_params(), _abi.make_queries([pose]), 9)
         s, gc, gs, n = (int(v) for v in out[0].split())
         assert (s, gc, gs, n) == (st[0]["success"], 9, st[0]["gait_cycles_succeed"], st[0]["n_rows"])
