@@ -206,6 +206,15 @@ typedef struct fhp_plan_outputs {
 } fhp_plan_outputs;
 int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
                 int32_t gait_cycles, const fhp_plan_outputs* out);
+/* The same plan with a COMPACT response, as the service returns it: query q owns rows
+ * out_rows[row_offsets[q] .. row_offsets[q+1]) = its 4 stance rows + 4 per successful cycle (nominal chain,
+ * response.footholds.footholds of FP.cpp:1588), back to back; row_offsets has n_queries + 1 entries.  capacity_rows is
+ * the size of out_rows; n_queries * FHP_ROWS_PER_QUERY(gait_cycles) always suffices.  When it is too small the call
+ * returns FHP_ERR_INVALID_ARG with row_offsets[n_queries] = the rows needed.  Only produced rows cross PCIe, and
+ * they do so chunk by chunk while the next chunk plans. */
+int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                     int64_t n_queries, int32_t gait_cycles, fhp_foothold* out_rows, int64_t capacity_rows,
+                     int64_t* row_offsets, fhp_query_status* status);
 /* KPIs the reference logs per successful cycle (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623): pure
  * host-side functions of ONE query's response rows (nominal or centroid chain).  feet_distance / cog_speed receive
  * 2 values per successful cycle (n_rows/4 - 1 cycles). */

@@ -78,7 +78,11 @@ struct fhp_ctx {
   bool maskNegInf = false;  // the layer holds -inf cells: their raw compare differs from their class -> float paths
   long long maskBuilds = 0;
   // scratch
-  DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD;
+  DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD, dCompact, dOffs;
+  cudaStream_t copyStream = nullptr;   // response rows of fhp_plan_compact travel here while the next chunk plans
+  long long* hTotals = nullptr;        // pinned: rows per chunk (fhp_plan_compact)
+  int hTotalsCap = 0;
+  std::vector<cudaEvent_t> chunkEv;
   long long launches = 0;
   unsigned pendingErrCheck = 0;
   // kernel error bits live in zero-copy host memory: reading them after a stream sync costs no memcpy
@@ -595,9 +599,12 @@ void fhp_destroy(fhp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_owned(ctx);
   for (DevBuf* b : {&ctx->dPars, &ctx->dQ, &ctx->dOutN, &ctx->dOutC, &ctx->dOutD, &ctx->dSt, &ctx->dErr, &ctx->dA, &ctx->dB, &ctx->dC2,
-                    &ctx->dD, &ctx->dMask})
+                    &ctx->dD, &ctx->dMask, &ctx->dCompact, &ctx->dOffs})
     b->release();
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
+  if (ctx->hTotals) cudaFreeHost(ctx->hTotals);
+  for (cudaEvent_t e : ctx->chunkEv) cudaEventDestroy(e);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   for (int b = 0; b < 2; ++b) {
     if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
     if (ctx->pinEv[b]) cudaEventDestroy(ctx->pinEv[b]);
@@ -840,6 +847,13 @@ const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* name) {
   return nullptr;
 }
 
+// Chunk size of the host-buffer pipelines (FHP_CHUNK_DIV overrides the divisor for experiments).
+static int64_t chunk_queries(fhp_ctx* ctx, bool wantCen) {
+  int div = 3;
+  if (const char* e = std::getenv("FHP_CHUNK_DIV")) div = std::max(1, atoi(e));
+  return std::max<int64_t>(1024, plan_wave_queries(ctx->G, wantCen) / div);
+}
+
 static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_queries, int64_t n_queries,
                        int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC, fhp_query_status* d_st,
                        cudaStream_t s, fhp_foothold* d_outD = nullptr) {
@@ -908,15 +922,15 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
   if (out_centroid || out_default) CU(ctx->dOutC.reserve(oB));  // the default-chain kernel variant also writes centroid rows
   if (out_default) CU(ctx->dOutD.reserve(oB));
   CU(ctx->dSt.reserve(sB));
-  // Host-buffer pipeline: the batch is cut into wave-sized chunks that alternate between two streams, so the kernel
+  // Host-buffer pipeline: the batch is cut into chunks (a third of a wave) that alternate between two streams, so the kernel
   // of chunk i+1 runs while the response rows of chunk i travel back over PCIe (the D2H of the rows is the
   // longest leg of a large batch).  Small batches are a single chunk = one launch.
   int rc = prepare_params(ctx, params, n_params, s);
   if (rc != FHP_OK) return rc;
   rc = ensure_err_word(ctx);
   if (rc != FHP_OK) return rc;
-  const int64_t wave = plan_wave_queries(ctx->G, out_centroid != nullptr);
-  int64_t nChunks = (n_queries + wave - 1) / wave;  // wave-sized chunks: a partial wave costs as much as a full one
+  const int64_t wave = chunk_queries(ctx, out_centroid != nullptr);
+  int64_t nChunks = (n_queries + wave - 1) / wave;
   if (nChunks < 1) nChunks = 1;
   const int64_t per = ((n_queries + nChunks - 1) / nChunks + 31) / 32 * 32;  // whole blocks per chunk
   const fhp_query* dq = static_cast<const fhp_query*>(ctx->dQ.p);
@@ -939,6 +953,100 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
   }
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream2));
+  return check_dev_err(ctx);
+}
+
+// The same plan with a COMPACT response: like the service, every query returns only the rows it produced.
+// Chunk i plans, scans its n_rows and packs its rows on one of two streams while the packed rows of chunk i-1 cross
+// PCIe on the copy stream; the host learns each chunk's row count from a pinned word before it issues that copy.
+int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
+                     int32_t gait_cycles, fhp_foothold* out_rows, int64_t capacity_rows, int64_t* row_offsets,
+                     fhp_query_status* status) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 || capacity_rows < 0 || !row_offsets ||
+      (n_queries > 0 && (!queries || !out_rows || !status)))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments (gait_cycles is a uint8 in the service request)");
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan_compact before fhp_set_map");
+  for (int64_t i = 0; i < n_queries; ++i)
+    if (queries[i].param_id < 0 || queries[i].param_id >= n_params)
+      return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
+  CU(cudaSetDevice(ctx->device));
+  row_offsets[0] = 0;
+  if (n_queries == 0) return FHP_OK;
+  const size_t R = FHP_ROWS_PER_QUERY(gait_cycles);
+  int rc = prepare_params(ctx, params, n_params, ctx->stream);
+  if (rc != FHP_OK) return rc;
+  rc = ensure_err_word(ctx);
+  if (rc != FHP_OK) return rc;
+  // chunks of a third of a wave: small enough that the first chunk's kernel (the only one PCIe cannot hide) is short,
+  // large enough that launches and event waits stay negligible (measured: 1/3..1/4 of a wave is the flat optimum)
+  const int64_t wave = chunk_queries(ctx, false);
+  int64_t nChunks = std::max<int64_t>(1, (n_queries + wave - 1) / wave);
+  const int64_t per = ((n_queries + nChunks - 1) / nChunks + 31) / 32 * 32;
+  nChunks = (n_queries + per - 1) / per;
+  CU(ctx->dQ.reserve(sizeof(fhp_query) * n_queries));
+  CU(ctx->dOutN.reserve(sizeof(fhp_foothold) * R * n_queries));
+  CU(ctx->dCompact.reserve(sizeof(fhp_foothold) * R * n_queries));
+  CU(ctx->dSt.reserve(sizeof(fhp_query_status) * n_queries));
+  CU(ctx->dOffs.reserve(sizeof(long long) * (n_queries + nChunks)));
+  if (!ctx->copyStream) CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  if (ctx->hTotalsCap < nChunks) {
+    if (ctx->hTotals) cudaFreeHost(ctx->hTotals);
+    ctx->hTotals = nullptr;
+    void* h = nullptr;
+    CU(cudaHostAlloc(&h, sizeof(long long) * nChunks, cudaHostAllocDefault));
+    ctx->hTotals = static_cast<long long*>(h);
+    ctx->hTotalsCap = static_cast<int>(nChunks);
+  }
+  while (static_cast<int64_t>(ctx->chunkEv.size()) < nChunks) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunkEv.push_back(e);
+  }
+  fhp_query* dq = static_cast<fhp_query*>(ctx->dQ.p);
+  fhp_foothold* dN = static_cast<fhp_foothold*>(ctx->dOutN.p);
+  fhp_foothold* dC = static_cast<fhp_foothold*>(ctx->dCompact.p);
+  fhp_query_status* dS = static_cast<fhp_query_status*>(ctx->dSt.p);
+  long long* dO = static_cast<long long*>(ctx->dOffs.p);
+  // enqueue every chunk's device work up front (two alternating streams)
+  int64_t c = 0;
+  for (int64_t lo = 0; lo < n_queries; lo += per, ++c) {
+    const int64_t n = std::min<int64_t>(per, n_queries - lo);
+    cudaStream_t cs = (c & 1) ? ctx->stream2 : ctx->stream;
+    long long* offs = dO + lo + c;  // n + 1 entries per chunk
+    CU(cudaMemcpyAsync(dq + lo, queries + lo, sizeof(fhp_query) * n, cudaMemcpyHostToDevice, cs));
+    rc = plan_launch(ctx, n_params, dq + lo, n, gait_cycles, dN + lo * R, nullptr, dS + lo, cs);
+    if (rc != FHP_OK) return rc;
+    CU(launch_compact(dN + lo * R, dS + lo, n, static_cast<int>(R), offs, dC + lo * R, cs));
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(&ctx->hTotals[c], offs + n, sizeof(long long), cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(row_offsets + lo, offs, sizeof(long long) * n, cudaMemcpyDeviceToHost, cs));  // chunk-local
+    CU(cudaMemcpyAsync(status + lo, dS + lo, sizeof(fhp_query_status) * n, cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(ctx->chunkEv[c], cs));
+  }
+  // as each chunk finishes: place its rows behind those of the chunks before it
+  int64_t base = 0;
+  int err = FHP_OK;
+  c = 0;
+  for (int64_t lo = 0; lo < n_queries; lo += per, ++c) {
+    const int64_t n = std::min<int64_t>(per, n_queries - lo);
+    CU(cudaEventSynchronize(ctx->chunkEv[c]));
+    const int64_t total = ctx->hTotals[c];
+    if (base + total > capacity_rows) {
+      err = FHP_ERR_INVALID_ARG;
+    } else if (total > 0 && err == FHP_OK) {
+      CU(cudaMemcpyAsync(out_rows + base, dC + lo * R, sizeof(fhp_foothold) * total, cudaMemcpyDeviceToHost, ctx->copyStream));
+    }
+    if (base != 0)
+      for (int64_t i = 0; i < n; ++i) row_offsets[lo + i] += base;  // chunk-local -> global
+    base += total;
+  }
+  row_offsets[n_queries] = base;
+  CU(cudaStreamSynchronize(ctx->copyStream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream2));
+  if (err != FHP_OK) return fail(ctx, err, "capacity_rows is smaller than the rows the queries produced (row_offsets[n] holds the need)");
   return check_dev_err(ctx);
 }
 

@@ -383,6 +383,69 @@ cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* ma
   return cudaGetLastError();
 }
 
+// ---- compact response: the rows each query actually produced, back to back --------------------------------------
+// offs[q] = sum of n_rows of the queries before q (exclusive scan; offs[n] = total).  One block; a wave-sized chunk
+// is a few tens of thousands of queries.
+__global__ void __launch_bounds__(1024) scan_rows_kernel(const fhp_query_status* __restrict__ st, long long n,
+                                                         long long* __restrict__ offs) {
+  __shared__ long long warpSum[32];
+  __shared__ long long carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const long long v = i < n ? st[i].n_rows : 0;
+    long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(kFull, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warpSum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = warpSum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const long long y = __shfl_up_sync(kFull, w, d);
+        if (lane >= d) w += y;
+      }
+      warpSum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const long long before = carry + (warp ? warpSum[warp - 1] : 0) + (x - v);
+    if (i < n) offs[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offs[n] = carry;
+}
+
+// One warp per query: its n_rows rows (40 bytes = five 8-byte words each) move from the fixed-pitch plan output to
+// out + offs[q].
+__global__ void __launch_bounds__(256) compact_rows_kernel(const fhp_foothold* __restrict__ rows,
+                                                           const long long* __restrict__ offs, long long n, int R,
+                                                           fhp_foothold* __restrict__ out) {
+  const long long q = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n) return;
+  const int lane = threadIdx.x & 31;
+  const long long o = offs[q];
+  const int words = static_cast<int>(offs[q + 1] - o) * 5;
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(rows + q * R);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + o);
+  for (int w = lane; w < words; w += 32) dst[w] = src[w];
+}
+
+cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st, long long n, int R, long long* offs,
+                           fhp_foothold* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  scan_rows_kernel<<<1, 1024, 0, stream>>>(st, n, offs);
+  compact_rows_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(rows, offs, n, R, out);
+  return cudaGetLastError();
+}
+
 typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
 // the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
 template <int STAGE>

@@ -298,3 +298,34 @@ def test_mask_planes_lifecycle_and_fallbacks(fhp, oracle):
     got, exp = _run_both(fhp, oracle, mi, pa, q, 8)
     assert compare_plans(got, exp, "inf cells") <= XYZ_TOL
     assert (got[2]["n_rows"] > 4).sum() > 20  # the case still plans something
+
+
+def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
+    """fhp_plan_compact returns exactly the rows fhp_plan produces, back to back, for one chunk and for several."""
+    p = _abi.yaml_params()
+    m = synth.rough_map(1200, 1200, 0.02, seed=71, start=(100, 900))
+    fhp.set_map(m)
+    for nq in (1, 37, 50000):  # 50,000 queries span more than one wave-sized chunk
+        q = synth.uniform_queries(nq, (-10.0, 7.0), (-10.0, 10.0), seed=nq)
+        nom, _, st = fhp.plan(p, q, 12)
+        rows, offs, st2 = fhp.plan_compact(p, q, 12)
+        assert np.array_equal(st, st2)
+        assert offs[0] == 0 and np.array_equal(np.diff(offs), st["n_rows"]) and len(rows) == offs[-1]
+        keep = np.arange(nom.shape[1])[None, :] < st["n_rows"][:, None]
+        assert np.array_equal(rows, nom[keep])
+    # against the oracle directly, and the capacity contract
+    q = synth.uniform_queries(300, (-10.0, 7.0), (-10.0, 10.0), seed=5)
+    exp = oracle.plan(m, p, q, 12)
+    rows, offs, st = fhp.plan_compact(p, q, 12)
+    for i in range(len(q)):
+        got_i, exp_i = rows[offs[i]:offs[i + 1]], exp[0][i][: exp[2][i]["n_rows"]]
+        assert len(got_i) == len(exp_i)
+        for f in ("x", "y", "z"):
+            assert np.max(np.abs(got_i[f] - exp_i[f]), initial=0.0) <= XYZ_TOL
+        for f in ("row", "col", "foot_id", "gait_cycle_id", "kind"):
+            assert np.array_equal(got_i[f], exp_i[f])
+    from quadrupedal_foothold_planner_b200.planner import FhpError
+    with pytest.raises(FhpError, match="capacity_rows"):
+        fhp.plan_compact(p, q, 12, capacity_rows=int(offs[-1]) - 1)
+    rows0, offs0, _ = fhp.plan_compact(p, q[:0], 12)
+    assert len(rows0) == 0 and offs0.tolist() == [0]
