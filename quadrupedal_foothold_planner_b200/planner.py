@@ -336,9 +336,18 @@ class FootholdPlanner:
         self.nominalGlobalFootholdsMsg_ = GlobalFootholds()
         self.centroidGlobalFootholdsMsg_ = GlobalFootholds()
 
-    # FP.cpp:504-536
-    def gridmapCallback(self, msg: HostMap):
-        self.fhp.set_map(msg)
+    # FP.cpp:504-536 — accepts what a subscriber can hold: the message (gridmap_msg.GridMapMessage), its ROS1 wire
+    # bytes, or an already converted map (HostMap = grid_map::GridMap geometry + layers)
+    def gridmapCallback(self, msg):
+        if isinstance(msg, (bytes, bytearray, memoryview)):
+            self.fhp.set_map_wire(bytes(msg))
+        elif isinstance(msg, HostMap):
+            self.fhp.set_map(msg)
+        else:
+            self.fhp.set_map_msg(msg)
+        d = self.fhp.map_info()  # gridMapInfo_ (FP.cpp:508-515)
+        self.gridMapInfo_ = {"x": d.pos_x, "y": d.pos_y, "length": d.length_x, "width": d.length_y, "row": d.rows,
+                             "col": d.cols, "resolution": d.resolution}
 
     # FP.cpp:539-1602; returns the service's bool, fills `response`
     def globalFootholdPlan(self, request: GlobalFootholdPlanRequest, response: GlobalFootholdPlanResponse) -> bool:
