@@ -367,6 +367,10 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
     }
   G.nSten = ns;
   G.ra = ra;
+  // a member cell of the disc around a continuous centre is at most floor(r/res + 1/2) indices from the centre's cell
+  // (see disc_window); the 1e-6 guard band covers the rounding of the index conversion at cell edges
+  G.discK = static_cast<int>(std::floor(r / res + 0.5 + 1e-6));
+  if (2 * G.discK + 1 > 8) G.discK = -1;
   // Rings whose every cell is farther than searchRadius from ANY centre that maps to the centre cell can never pass
   // SpiralIterator's last-two-rings distance filter: ring d holds offsets with |offset| >= d cells and the centre is
   // within sqrt(2)/2 cell of its cell centre (farther, and on the far side, when it lies outside the map).  Not

@@ -501,17 +501,25 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
   __syncwarp();
 }
 
-// CircleIterator::findSubmapParameters: bounded corners -> unwrapped index window [tl, br] of the foot disc, plus
-// the membership of every window cell decided ONCE with the iterator's arithmetic (squared centre distance <= r^2 and
-// cell inside the map): bit (8*i1 + i0) of `m` <-> cell (tl0+i0, tl1+i1).  The default test, the height mean and the
-// prefetch all walk the same disc, so none of them repeats the double-precision work.  Windows wider than 8 cells
-// (footRadius > ~3 cells) keep m = 0 and take the generic loops.
+// The cells a grid_map::CircleIterator(centre, r) visits, decided ONCE per foothold: bit (8*i1 + i0) of `m` <-> cell
+// (tl0+i0, tl1+i1) is inside the map and its centre is within r of (cx,cy) (squared-distance test with the
+// iterator's arithmetic).  The default test, the height mean and the prefetch all walk the same disc, so none of them
+// repeats the double-precision work.
+//
+// Upstream restricts the walk to the index window [index(bound(c + r)), index(bound(c - r))]
+// (CircleIterator::findSubmapParameters).  That window is redundant for membership: a cell whose centre is within r of
+// the centre lies at most k = floor(r/res + 1/2) indices from the centre's own cell (uc0,uc1) — a cell d indices away
+// has its centre at least (d - 1/2)*res away — and every such in-map cell is inside upstream's window (the window ends
+// are the cells containing c +- r; positions outside the map are clamped towards it, cells outside it are never
+// visited).  So the disc is tested on the (2k+1)^2 cells around (uc0,uc1) with no index conversion at all; the host
+// picks k with a guard band and hands k = -1 (=> the generic, window-based walk below) when 2k+1 > 8.
 struct DiscWin {
   int tl0, tl1, br0, br1;
   unsigned long long m;
-  __device__ __forceinline__ bool small() const { return br0 - tl0 < 8 && br1 - tl1 < 8; }
+  int generic;  // 1: m is not filled, consumers walk [tl, br] with the distance test themselves
+  __device__ __forceinline__ bool small() const { return generic == 0; }
 };
-__device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, double cy, double r, double r2) {
+__device__ __noinline__ DiscWin disc_window_generic(const MapDev& M, double cx, double cy, double r) {
   DiscWin d;
   const double tlx = bound_axis(cx + r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + r, M.leny, M.posy, M.halfy);
   const double brx = bound_axis(cx - r, M.lenx, M.posx, M.halfx), bry = bound_axis(cy - r, M.leny, M.posy, M.halfy);
@@ -520,18 +528,33 @@ __device__ __forceinline__ DiscWin disc_window(const MapDev& M, double cx, doubl
   d.br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv);
   d.br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
   d.m = 0ull;
-  if (d.small()) {
-    for (int u1 = d.tl1; u1 <= d.br1; ++u1) {
-      if (u1 < 0 || u1 >= M.cols) continue;
-      const double dy = pos_axis(M.fcy, M.res, u1) - cy;
-      const double dy2 = dy * dy;
-      unsigned colBits = 0;
-      for (int u0 = d.tl0; u0 <= d.br0; ++u0) {
-        const double dx = pos_axis(M.fcx, M.res, u0) - cx;
-        if (dx * dx + dy2 <= r2 && u0 >= 0 && u0 < M.rows) colBits |= 1u << (u0 - d.tl0);
-      }
-      d.m |= static_cast<unsigned long long>(colBits) << (8 * (u1 - d.tl1));
+  d.generic = 1;
+  return d;
+}
+__device__ __forceinline__ DiscWin disc_window(const MapDev& M, const GeoDev& G, double cx, double cy, int uc0, int uc1,
+                                               double r, double r2) {
+  // wide discs: upstream's window, membership decided by the consumers' generic loops
+  if (G.discK < 0) return disc_window_generic(M, cx, cy, r);
+  DiscWin d;
+  d.generic = 0;
+  const int k = G.discK;
+  d.tl0 = uc0 - k;
+  d.tl1 = uc1 - k;
+  d.br0 = uc0 + k;
+  d.br1 = uc1 + k;
+  d.m = 0ull;
+  for (int i1 = 0; i1 <= 2 * k; ++i1) {
+    const int u1 = d.tl1 + i1;
+    if (u1 < 0 || u1 >= M.cols) continue;
+    const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+    const double dy2 = dy * dy;
+    unsigned colBits = 0;
+    for (int i0 = 0; i0 <= 2 * k; ++i0) {
+      const int u0 = d.tl0 + i0;
+      const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+      if (dx * dx + dy2 <= r2 && u0 >= 0 && u0 < M.rows) colBits |= 1u << i0;
     }
+    d.m |= static_cast<unsigned long long>(colBits) << (8 * i1);
   }
   return d;
 }
@@ -583,8 +606,9 @@ __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, doub
   }
   return static_cast<float>(static_cast<double>(meanHeight) + P.h);
 }
-__device__ __forceinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy) {
-  return mean_height(M, P, cx, cy, disc_window(M, cx, cy, P.r, P.r2));
+__device__ __forceinline__ float mean_height(const MapDev& M, const GeoDev& G, const ParDev& P, double cx, double cy) {
+  const int uc0 = raw_index_axis(cx, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(cy, M.halfy, M.posy, M.res, M.rinv);
+  return mean_height(M, P, cx, cy, disc_window(M, G, cx, cy, uc0, uc1, P.r, P.r2));
 }
 
 // Rare path of the centroid method: whole-window test and edge rows counted from global memory (submap rows

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
                      dcx, dcy);
       dnx = (dcx + P.stepLength) + bx;
       dny = nextY + by;
-      if (active) dnz = static_cast<double>(mean_height(M, P, dnx, dny));
+      if (active) dnz = static_cast<double>(mean_height(M, G, P, dnx, dny));
     }
     const double px = (ccx + P.stepLength) + bx, py = nextY + by;     // centroid-chain next foothold (:2199,:2414)
     const double rx = (ncx + P.stepLength) + bx, ry = nextY + by;     // nominal-chain next foothold = rectangle centre
@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
       if (c0 >= M.rows) c0 -= M.rows;
       w0 -= c0 & 3;
     }
-    DiscWin dw = {0, 0, -1, -1, 0ull};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
+    DiscWin dw = {0, 0, -1, -1, 0ull, 0};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
     if (active) {
-      dw = disc_window(M, px, py, P.r, P.r2);
+      dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
       prefetch_disc(M, M.elev, dw);
     }
     // A query that failed keeps its chains (FP.cpp:1571-1576) and only drifts 7 mm sideways per cycle, so its next
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
 #endif
     if (active) {
       if (ok) nz = static_cast<double>(mean_height(M, P, px, py, dw));  // at the CENTRE (FP.cpp:2029)
-      if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, P, co.x, co.y));
+      if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, G, P, co.x, co.y));
     }
     // footholdValidation_ = RF & RH & LH & LF (FP.cpp:1323)
     const unsigned okb = __ballot_sync(kFull, ok);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   }
   unsigned err = 0;
   if (MODE == 2) {
-    if (active) A.z[i] = mean_height(M, P, px, py);
+    if (active) A.z[i] = mean_height(M, G, P, px, py);
     return;
   }
   const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
   Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
   if (MODE == 0 || MODE == 3) {
-    DiscWin dw = {0, 0, -1, -1, 0ull};
-    if (active) dw = disc_window(M, px, py, P.r, P.r2);
+    DiscWin dw = {0, 0, -1, -1, 0ull, 0};
+    if (active) dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
     NominalOut no;
     if (MODE == 0)
       no = nominal_eval<false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   if (MODE == 1) {
     CentroidOut co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);
     double z = 0.0;
-    if (co.ccase >= 0 && co.ccase <= 3) z = static_cast<double>(mean_height(M, P, co.x, co.y));
+    if (co.ccase >= 0 && co.ccase <= 3) z = static_cast<double>(mean_height(M, G, P, co.x, co.y));
     int r0, c0;
     cell_of_position(M, co.x, co.y, r0, c0);
     write_row(A.out + i, co.x, co.y, z, r0, c0, 0, 0, FHP_KIND_DEFAULT);

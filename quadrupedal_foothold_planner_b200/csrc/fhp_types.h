@@ -33,6 +33,7 @@ struct MapDev {
 struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int nRings;    // ceil(searchRadius / res)                 SpiralIterator ctor
   int ra;        // foot-disc stencil half width (cells)
+  int discK;     // foot disc of a CONTINUOUS centre: member cells lie within discK indices of the centre's cell (-1: generic walk)
   int HW;        // window half width = nRings + ra
   int WIN;       // 2*HW + 1 (<= 32)
   int pack;      // window columns per warp load: 1 (WIN<=32), 2 (WIN<=16), 4 (WIN<=8)

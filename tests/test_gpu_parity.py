@@ -329,3 +329,23 @@ def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
         fhp.plan_compact(p, q, 12, capacity_rows=int(offs[-1]) - 1)
     rows0, offs0, _ = fhp.plan_compact(p, q[:0], 12)
     assert len(rows0) == 0 and offs0.tolist() == [0]
+
+
+@pytest.mark.parametrize("foot_radius", [0.031, 0.05, 0.085])
+def test_wide_foot_discs(fhp, oracle, foot_radius):
+    """Foot discs of 1.5 / 2.5 / 4.25 cells: the disc-membership fast path (k = 2, 3) and, for the widest, the generic
+    window walk of CircleIterator (k = 5 exceeds the 8x8 membership mask)."""
+    m = synth.rough_map(500, 500, 0.02, seed=81, start=(9, 333))
+    # smoother acceptance so that wide discs still plan something
+    t = np.clip(m.layers["traversability"] * 1.6, 0, 1).astype(np.float32)
+    m.set_layer("traversability", t)
+    q = synth.uniform_queries(256, (-4.0, 1.0), (-4.0, 4.0), seed=3)
+    hx = 500 * 0.02 / 2
+    q = np.concatenate([q, _abi.make_queries([[-hx + 0.03, 0.0, 0.0], [hx - 0.4, hx - 0.02, 0.0], [hx + 0.05, 0.0, 0.0]])])
+    p = _abi.yaml_params(foot_radius=foot_radius, thr_default=0.5, thr_candidate=0.3)
+    got, exp = _run_both(fhp, oracle, m, p, q, 8)
+    assert compare_plans(got, exp, f"foot radius {foot_radius}") <= XYZ_TOL
+    assert (got[2]["n_rows"] > 4).sum() > 10
+    c = np.stack([q["x"][:64] + 0.2, q["y"][:64]], axis=1)
+    assert np.array_equal(fhp.mean_height(p, c).view(np.uint32), oracle.mean_height(m, p, c).view(np.uint32))
+    assert np.array_equal(fhp.check_default(p, c), oracle.check_default(m, p, c))
