@@ -501,7 +501,7 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
   __syncwarp();
 }
 
-// The cells a grid_map::CircleIterator(centre, r) visits, decided ONCE per foothold: bit (8*i1 + i0) of `m` <-> cell
+// The cells a grid_map::CircleIterator(centre, r) visits, decided ONCE per foothold: bit (8*i0 + i1) of `m` <-> cell
 // (tl0+i0, tl1+i1) is inside the map and its centre is within r of (cx,cy) (squared-distance test with the
 // iterator's arithmetic).  The default test, the height mean and the prefetch all walk the same disc, so none of them
 // repeats the double-precision work.
@@ -543,30 +543,52 @@ __device__ __forceinline__ DiscWin disc_window(const MapDev& M, const GeoDev& G,
   d.br0 = uc0 + k;
   d.br1 = uc1 + k;
   d.m = 0ull;
-  for (int i1 = 0; i1 <= 2 * k; ++i1) {
-    const int u1 = d.tl1 + i1;
-    if (u1 < 0 || u1 >= M.cols) continue;
-    const double dy = pos_axis(M.fcy, M.res, u1) - cy;
-    const double dy2 = dy * dy;
-    unsigned colBits = 0;
-    for (int i0 = 0; i0 <= 2 * k; ++i0) {
-      const int u0 = d.tl0 + i0;
-      const double dx = pos_axis(M.fcx, M.res, u0) - cx;
-      if (dx * dx + dy2 <= r2 && u0 >= 0 && u0 < M.rows) colBits |= 1u << i0;
+  for (int i0 = 0; i0 <= 2 * k; ++i0) {  // row-major bit order = the iterator's visiting order
+    const int u0 = d.tl0 + i0;
+    if (u0 < 0 || u0 >= M.rows) continue;
+    const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+    const double dx2 = dx * dx;
+    unsigned rowBits = 0;
+    for (int i1 = 0; i1 <= 2 * k; ++i1) {
+      const int u1 = d.tl1 + i1;
+      const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+      if (dx2 + dy * dy <= r2 && u1 >= 0 && u1 < M.cols) rowBits |= 1u << i1;
     }
-    d.m |= static_cast<unsigned long long>(colBits) << (8 * i1);
+    d.m |= static_cast<unsigned long long>(rowBits) << (8 * i0);
   }
   return d;
 }
 
-// Pull the elevation cells of a foot disc towards L1 long before mean_height sums them (the loads are otherwise
-// the only exposed global latency of the scalar phase).
-__device__ __forceinline__ void prefetch_disc(const MapDev& M, const float* layer, const DiscWin& dw) {
-  for (unsigned long long t = dw.m; t; t &= t - 1) {
-    const int bit = __ffsll(static_cast<long long>(t)) - 1;
-    const int b0 = wrap_add(dw.tl0 + (bit & 7), M.start0, M.rows), b1 = wrap_add(dw.tl1 + (bit >> 3), M.start1, M.cols);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(layer + static_cast<size_t>(b1) * M.rows + b0));
+// The elevation cells of a foot disc are the only global loads of the scalar phase whose latency nothing hides (the L1
+// beside the shared-memory carve-out is too small for a prefetch to survive until they are summed).  The first four
+// member cells — all of them for footRadius <= resolution — are therefore LOADED right after the disc is known, before
+// the window staging, and summed after it.
+struct DiscElev {
+  float e0, e1, e2, e3;
+};
+__device__ __forceinline__ DiscElev load_disc_elev(const MapDev& M, const DiscWin& dw) {
+  DiscElev v = {0.0f, 0.0f, 0.0f, 0.0f};
+  unsigned long long t = dw.m;
+  if (t) {
+    int bit = __ffsll(static_cast<long long>(t)) - 1;
+    v.e0 = load_cell(M, M.elev, dw.tl0 + (bit >> 3), dw.tl1 + (bit & 7));
+    t &= t - 1;
+    if (t) {
+      bit = __ffsll(static_cast<long long>(t)) - 1;
+      v.e1 = load_cell(M, M.elev, dw.tl0 + (bit >> 3), dw.tl1 + (bit & 7));
+      t &= t - 1;
+      if (t) {
+        bit = __ffsll(static_cast<long long>(t)) - 1;
+        v.e2 = load_cell(M, M.elev, dw.tl0 + (bit >> 3), dw.tl1 + (bit & 7));
+        t &= t - 1;
+        if (t) {
+          bit = __ffsll(static_cast<long long>(t)) - 1;
+          v.e3 = load_cell(M, M.elev, dw.tl0 + (bit >> 3), dw.tl1 + (bit & 7));
+        }
+      }
+    }
   }
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------ a9 mean height
@@ -587,7 +609,7 @@ __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, doub
   if (dw.small()) {  // membership already decided (disc_window); same row-major visiting order
     for (int i0 = 0; i0 <= br0 - tl0; ++i0)
       for (int i1 = 0; i1 <= br1 - tl1; ++i1)
-        if ((dw.m >> (8 * i1 + i0)) & 1ull) height_cell(M, tl0 + i0, tl1 + i1, iHeight, meanHeight, i);
+        if ((dw.m >> (8 * i0 + i1)) & 1ull) height_cell(M, tl0 + i0, tl1 + i1, iHeight, meanHeight, i);
   } else {
     for (int u0 = tl0; u0 <= br0; ++u0) {
       const double dx = pos_axis(M.fcx, M.res, u0) - cx;
@@ -599,6 +621,32 @@ __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, doub
       }
     }
   }
+  if (i != 0) {
+    meanHeight = meanHeight / static_cast<float>(i);
+  } else {
+    meanHeight = iHeight;
+  }
+  return static_cast<float>(static_cast<double>(meanHeight) + P.h);
+}
+// getFootholdMeanHeight from the pre-loaded cells (same accumulation order); discs with more than four member cells
+// or on the generic walk take the loop above.
+__device__ __forceinline__ void height_value(float e, float& iHeight, float& meanHeight, int& i) {
+  iHeight = (fabsf(e) < __int_as_float(0x7f800000)) ? e : 0.0f;
+  if (iHeight < 10.0f) {
+    i++;
+    meanHeight = meanHeight + iHeight;
+  }
+}
+__device__ __forceinline__ float mean_height_loaded(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw,
+                                                    const DiscElev& v) {
+  const int n = __popcll(dw.m);
+  if (!dw.small() || n > 4) return mean_height(M, P, cx, cy, dw);
+  float iHeight = 0.0f, meanHeight = 0.0f;
+  int i = 0;
+  if (n > 0) height_value(v.e0, iHeight, meanHeight, i);
+  if (n > 1) height_value(v.e1, iHeight, meanHeight, i);
+  if (n > 2) height_value(v.e2, iHeight, meanHeight, i);
+  if (n > 3) height_value(v.e3, iHeight, meanHeight, i);
   if (i != 0) {
     meanHeight = meanHeight / static_cast<float>(i);
   } else {
@@ -792,10 +840,10 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
     return false;
   }
   uint32_t below = 0;
-  int b = b0;
-  for (unsigned long long t = dw.m; t; t >>= 8, ++b) {  // one byte of membership per window column
-    const uint32_t colMem = static_cast<uint32_t>(t) & 0xffu;
-    if (colMem) below |= ((pl.col(PL_D, b) & pl.col(PL_F, b)) >> a0) & colMem;
+  for (unsigned long long t = dw.m; t; t &= t - 1) {  // <= 4 member cells for footRadius <= resolution
+    const int bit = __ffsll(static_cast<long long>(t)) - 1;
+    const int a = a0 + (bit >> 3), b = b0 + (bit & 7);
+    below |= ((pl.col(PL_D, b) & pl.col(PL_F, b)) >> a) & 1u;
   }
   return below == 0u;
 }
@@ -1017,7 +1065,7 @@ template <bool DEFAULT_ONLY, bool PAD>
 __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P,
                                                    const uint16_t* sSpiral, uint32_t smemWarp, int lane,
                                                    bool active, int uc0, int uc1, int w0, int w1, double cx, double cy,
-                                                   double rx, double ry, const DiscWin& dw, unsigned& err) {
+                                                   double rx, double ry, bool okDefault, unsigned& err) {
   NominalOut o;
   o.x = cx;  // FP.cpp:2016-2017
   o.y = cy;
@@ -1031,7 +1079,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
                                in_map(M, uc0, uc1);
     o.row = centre_in_map ? wrap_add(uc0, M.start0, M.rows) : -1;
     o.col = centre_in_map ? wrap_add(uc1, M.start1, M.cols) : -1;
-    o.ok = default_eval(M, G, P, pl, w0, w1, cx, cy, dw, err);
+    o.ok = okDefault;  // checkDefaultFoothold (default_eval), evaluated by the caller
   }
   if (DEFAULT_ONLY) return o;
 

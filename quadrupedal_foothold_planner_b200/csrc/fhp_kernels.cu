@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     DiscWin dw = {0, 0, -1, -1, 0ull, 0};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
     if (active) {
       dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
-      prefetch_disc(M, M.elev, dw);
     }
+    const DiscElev de = load_disc_elev(M, dw);  // in flight during the staging below
     // A query that failed keeps its chains (FP.cpp:1571-1576) and only drifts 7 mm sideways per cycle, so its next
     // window is usually the SAME cells: the bit-planes are still in this lane's slot, nothing to stage.
     const bool restage = active && !(w0 == prevW0 && w1 == prevW1);
@@ -193,21 +193,25 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     co.x = co.y = 0.0;
     co.ccase = -1;
     double nz = 0.0, cz = 0.0;
+    bool okDef = false;
+    float zCentre = 0.0f;
     if (active) {
       Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, STAGE == kStageMask ? 1 : G.pack, G.rpShift);
+      zCentre = mean_height_loaded(M, P, px, py, dw, de);                // FP.cpp:2029 (used when the leg is valid)
+      okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
     }
 #if FHP_SYNC_LEVEL >= 4
     __syncthreads();
 #endif
     const NominalOut no =
-        nominal_eval<false, STAGE == kStageMask>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);  // :863-903
+        nominal_eval<false, STAGE == kStageMask>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
     const bool ok = no.ok;
 #if FHP_SYNC_LEVEL >= 3
     __syncthreads();
 #endif
     if (active) {
-      if (ok) nz = static_cast<double>(mean_height(M, P, px, py, dw));  // at the CENTRE (FP.cpp:2029)
+      if (ok) nz = static_cast<double>(zCentre);  // at the CENTRE (FP.cpp:2029)
       if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, G, P, co.x, co.y));
     }
     // footholdValidation_ = RF & RH & LH & LF (FP.cpp:1323)
@@ -292,10 +296,11 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     DiscWin dw = {0, 0, -1, -1, 0ull, 0};
     if (active) dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
     NominalOut no;
+    const bool okDef = active && default_eval(M, G, P, pl, w0, w1, px, py, dw, err);
     if (MODE == 0)
-      no = nominal_eval<false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
+      no = nominal_eval<false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     else
-      no = nominal_eval<true, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, dw, err);
+      no = nominal_eval<true, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     if (active) {
       if (MODE == 0) {
         double z = 0.0;
