@@ -437,8 +437,9 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
 // {e0 rows 32k..32k+31, e0 rows 32k+32..32k+63, e1 same, e1 same} of buffer column c, stored k-major (index
 // k*cols + c): ONE 16-byte load holds the 32 window rows starting at any row of word k, and neighbouring columns
 // are contiguous.  Staging a window column = 1 load, 2 funnel shifts, D = e1, C = e0 & e1, F = e0 | e1, 1 store.
-// 2^lpwShift lanes serve one window (consecutive columns -> one or two 128-byte lines per load instruction) and
-// write straight into the owner's slot (pack = 1 layout: 16 bytes {D, C, F, pad} per column).
+// 8 lanes serve one window, two columns each per step (consecutive columns -> one or two 128-byte lines per load
+// instruction), 4 windows per pass, and write straight into the owner's slot (pack = 1 layout: 16 bytes {D, C, F, pad}
+// per column).
 // Fast = the window lies inside the map and does not cross the circular-buffer ROW seam (the column seam is
 // handled per column); everything else takes stage_slow on the float layer, exactly like the other paths.
 __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev& G, const uint4* __restrict__ mask,
@@ -464,36 +465,32 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
   if (fastMask) {
     const int org = (bb0 >> 5) * M.cols;          // entry index of (row word, column 0); < 2^27
     const int b1s = bb1 | ((bb0 & 31) << 26);     // first buffer column | row shift (cols < 2^26)
-    const int lpw = 1 << G.lpwShift;              // lanes per window
-    const int c = lane & (lpw - 1);
-    const int grp = lane >> G.lpwShift;
-    const int wpp = 32 >> G.lpwShift;             // windows per pass
-    const unsigned passBits = (wpp >= 32) ? 0xffffffffu : ((1u << wpp) - 1u);
-    const bool cIn = c < G.WIN;
-    for (int j0 = 0; j0 < 32; j0 += 2 * wpp) {    // two passes per iteration: two independent loads in flight
-      const bool anyA = ((fastMask >> j0) & passBits) != 0u;
-      const bool anyB = (j0 + wpp < 32) && ((fastMask >> (j0 + wpp)) & passBits) != 0u;
-      if (!anyA && !anyB) continue;  // warp-uniform
-      const int ja = j0 + grp, jb = (j0 + wpp + grp) & 31;
-      const int orgA = __shfl_sync(kFull, org, ja), bsA = __shfl_sync(kFull, b1s, ja);
-      const int orgB = __shfl_sync(kFull, org, jb), bsB = __shfl_sync(kFull, b1s, jb);
-      const bool fa = cIn && ((fastMask >> ja) & 1u);
-      const bool fb = cIn && anyB && ((fastMask >> jb) & 1u);
-      int colA = (bsA & 0x3ffffff) + c, colB = (bsB & 0x3ffffff) + c;
-      if (colA >= M.cols) colA -= M.cols;
-      if (colB >= M.cols) colB -= M.cols;
-      // (lanes without a column load entry 0: valid memory, result unused — cheaper than predicated zero-fills)
-      const uint4 ea = __ldg(mask + (fa ? orgA + colA : 0));
-      const uint4 eb = __ldg(mask + (fb ? orgB + colB : 0));
-      if (fa) {
-        const int s = static_cast<unsigned>(bsA) >> 26;
-        const uint32_t e0 = __funnelshift_r(ea.x, ea.y, s), e1 = __funnelshift_r(ea.z, ea.w, s);
-        sts_v4(smemWarp + static_cast<uint32_t>(ja * G.stride + c * 4) * 4u, e1, e0 & e1, e0 | e1, 0u);
-      }
-      if (fb) {
-        const int s = static_cast<unsigned>(bsB) >> 26;
-        const uint32_t e0 = __funnelshift_r(eb.x, eb.y, s), e1 = __funnelshift_r(eb.z, eb.w, s);
-        sts_v4(smemWarp + static_cast<uint32_t>(jb * G.stride + c * 4) * 4u, e1, e0 & e1, e0 | e1, 0u);
+    const int c = lane & 7, grp = lane >> 3;      // 8 lanes per window, 4 windows per pass
+    for (int pass = 0; pass < 8; ++pass) {
+      if (((fastMask >> (pass * 4)) & 0xfu) == 0u) continue;  // warp-uniform
+      const int j = pass * 4 + grp;
+      const int jorg = __shfl_sync(kFull, org, j), jbs = __shfl_sync(kFull, b1s, j);
+      const bool jf = (fastMask >> j) & 1u;
+      const int s = static_cast<unsigned>(jbs) >> 26;
+      const int jb1 = jbs & 0x3ffffff;
+      const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
+      for (int ca = c; ca < G.WIN; ca += 16) {  // two columns per lane and iteration: two independent loads in flight
+        const int cb = ca + 8;
+        const bool fa = jf, fb = jf && cb < G.WIN;
+        int colA = jb1 + ca, colB = jb1 + cb;
+        if (colA >= M.cols) colA -= M.cols;
+        if (colB >= M.cols) colB -= M.cols;
+        // (lanes without a column load entry 0: valid memory, result unused — cheaper than predicated zero-fills)
+        const uint4 ea = __ldg(mask + (fa ? jorg + colA : 0));
+        const uint4 eb = __ldg(mask + (fb ? jorg + colB : 0));
+        if (fa) {
+          const uint32_t e0 = __funnelshift_r(ea.x, ea.y, s), e1 = __funnelshift_r(ea.z, ea.w, s);
+          sts_v4(dst + static_cast<uint32_t>(ca) * 16u, e1, e0 & e1, e0 | e1, 0u);
+        }
+        if (fb) {
+          const uint32_t e0 = __funnelshift_r(eb.x, eb.y, s), e1 = __funnelshift_r(eb.z, eb.w, s);
+          sts_v4(dst + static_cast<uint32_t>(cb) * 16u, e1, e0 & e1, e0 | e1, 0u);
+        }
       }
     }
   }
