@@ -870,6 +870,12 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.q = d_queries;
   A.nq = n_queries;
   A.cycles = gait_cycles;
+  {  // queries per warp: the smallest power of two that still fits the batch into one resident wave of warps
+    const long long waveWarps = std::max<long long>(1, plan_wave_queries(ctx->G, d_outC != nullptr) / 8);
+    const long long need = (n_queries + waveWarps - 1) / waveWarps;
+    A.qpwShift = need <= 1 ? 0 : (need <= 2 ? 1 : (need <= 4 ? 2 : 3));
+    if (const char* e = std::getenv("FHP_QPW_SHIFT")) A.qpwShift = std::max(0, std::min(3, atoi(e)));
+  }
   A.outN = d_outN;
   A.outC = d_outC;
   A.outD = d_outD;

@@ -21,6 +21,7 @@ struct PlanArgs {
   const fhp_query* q;
   long long nq;
   int cycles;
+  int qpwShift;  // log2 of the queries one warp plans (8 = every quad busy; fewer for batches that cannot fill the GPU)
   fhp_foothold* outN;
   fhp_foothold* outC;
   fhp_foothold* outD;  // optional: "default" chain rows

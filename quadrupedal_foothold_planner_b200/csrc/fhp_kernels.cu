@@ -90,10 +90,14 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
   const uint16_t* sSpiral = load_spiral_table(G, smem);  // ends with __syncthreads (also publishes the mbarriers)
   const uint32_t sw = smem_u32(smem + G.spiralWords + warpInBlock * 32 * G.stride);
   const long long gwarp = static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock;
-  const long long q = gwarp * 8 + (lane >> 2);
+  // A warp plans 2^qpwShift queries (its first quads).  Eight keeps every lane busy; batches too small to fill the GPU
+  // spread over more warps instead, because the warp-cooperative steps (staging passes, spiral scans) serve a warp's
+  // lanes one after the other and the gait cycles are sequential: fewer queries per warp = shorter critical path.
+  const int quad = lane >> 2;
+  const long long q = (gwarp << A.qpwShift) + quad;
   const int f = lane & 3;           // RF,RH,LH,LF
   const int quad0 = lane & ~3;
-  const bool active = q < A.nq;
+  const bool active = quad < (1 << A.qpwShift) && q < A.nq;
   // (a whole-idle warp of the last block keeps running with active == false: the block synchronises every cycle)
   const MapDev& M = A.M;
 
@@ -468,7 +472,8 @@ static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef) {
 cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream) {
   if (A.nq <= 0) return cudaSuccess;
   const int warps = kPlanThreads / 32;
-  const long long nWarps = (A.nq + 7) / 8;
+  const int qpw = 1 << A.qpwShift;
+  const long long nWarps = (A.nq + qpw - 1) / qpw;
   const long long blocks = (nWarps + warps - 1) / warps;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
   void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr);
