@@ -79,6 +79,10 @@ struct fhp_ctx {
   long long maskBuilds = 0;
   // scratch
   DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD, dCompact, dOffs;
+  // zero-copy scratch for latency-bound calls (a robot's single plan): the kernel reads the queries from and writes the
+  // rows to mapped pinned host memory, so the call is one launch and one stream sync with no copy engine involved
+  void* hSmall = nullptr;
+  void* dSmall = nullptr;
   cudaStream_t copyStream = nullptr;   // response rows of fhp_plan_compact travel here while the next chunk plans
   long long* hTotals = nullptr;        // pinned: rows per chunk (fhp_plan_compact)
   int hTotalsCap = 0;
@@ -143,6 +147,7 @@ int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
 // through two pinned chunks owned by the context: chunk i+1 is filled by a few host threads while chunk i is in
 // flight, so the upload runs at min(host memcpy, PCIe) rather than at their sum.  Already-pinned sources and small
 // layers are copied directly.
+constexpr size_t kSmallBytes = 256u << 10;  // fhp_plan* calls whose buffers fit here take the zero-copy latency path
 constexpr size_t kPinChunk = 8u << 20;
 constexpr size_t kDirectBytes = 1u << 20;
 constexpr int kCopyThreads = 4;
@@ -607,6 +612,7 @@ void fhp_destroy(fhp_ctx* ctx) {
     b->release();
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
   if (ctx->hTotals) cudaFreeHost(ctx->hTotals);
+  if (ctx->hSmall) cudaFreeHost(ctx->hSmall);
   for (cudaEvent_t e : ctx->chunkEv) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   for (int b = 0; b < 2; ++b) {
@@ -881,7 +887,15 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.outD = d_outD;
   A.st = d_st;
   A.err = ctx->dErrMapped;
-  CU(launch_plan(A, ctx->G, d_outC != nullptr, s));
+  {
+    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, s);
+    if (e != cudaSuccess) {
+      char b[256];
+      snprintf(b, sizeof b, "plan kernel launch failed: %s (queries %lld, queries/warp %d, shared memory %d B)",
+               cudaGetErrorString(e), static_cast<long long>(n_queries), 1 << A.qpwShift, ctx->G.smemWords * 4 + 128);
+      return fail(ctx, FHP_ERR_CUDA, b);
+    }
+  }
   if (n_queries > 0) ctx->launches += 1;
   return FHP_OK;
 }
@@ -927,6 +941,41 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
   const size_t R = FHP_ROWS_PER_QUERY(gait_cycles);
   const size_t qB = sizeof(fhp_query) * n_queries, oB = sizeof(fhp_foothold) * R * n_queries,
                sB = sizeof(fhp_query_status) * n_queries;
+  // Latency path: everything fits the mapped scratch -> no memcpy calls, the kernel talks to host memory directly.
+  {
+    const size_t nOut = 1 + (out_centroid || out_default ? 1 : 0) + (out_default ? 1 : 0);
+    const size_t need = qB + nOut * oB + sB;
+    if (need <= kSmallBytes) {
+      int rc = prepare_params(ctx, params, n_params, s);
+      if (rc != FHP_OK) return rc;
+      rc = ensure_err_word(ctx);
+      if (rc != FHP_OK) return rc;
+      if (!ctx->hSmall) {
+        CU(cudaHostAlloc(&ctx->hSmall, kSmallBytes, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer(&ctx->dSmall, ctx->hSmall, 0));
+      }
+      char* h = static_cast<char*>(ctx->hSmall);
+      char* d = static_cast<char*>(ctx->dSmall);
+      size_t off = 0;
+      const size_t oQ = off;  off += qB;
+      const size_t oN = off;  off += oB;
+      const size_t oC = off;  off += (nOut >= 2 ? oB : 0);
+      const size_t oD = off;  off += (nOut >= 3 ? oB : 0);
+      const size_t oS = off;
+      std::memcpy(h + oQ, queries, qB);
+      rc = plan_launch(ctx, n_params, reinterpret_cast<const fhp_query*>(d + oQ), n_queries, gait_cycles,
+                       reinterpret_cast<fhp_foothold*>(d + oN), nOut >= 2 ? reinterpret_cast<fhp_foothold*>(d + oC) : nullptr,
+                       reinterpret_cast<fhp_query_status*>(d + oS), s,
+                       nOut >= 3 ? reinterpret_cast<fhp_foothold*>(d + oD) : nullptr);
+      if (rc != FHP_OK) return rc;
+      CU(cudaStreamSynchronize(s));
+      std::memcpy(out_nominal, h + oN, oB);
+      if (out_centroid) std::memcpy(out_centroid, h + oC, oB);
+      if (out_default) std::memcpy(out_default, h + oD, oB);
+      std::memcpy(status, h + oS, sB);
+      return check_dev_err(ctx);
+    }
+  }
   CU(ctx->dQ.reserve(qB));
   CU(ctx->dOutN.reserve(oB));
   if (out_centroid || out_default) CU(ctx->dOutC.reserve(oB));  // the default-chain kernel variant also writes centroid rows

@@ -25,8 +25,7 @@ def compare_plans(got, exp, what=""):
                 qi, ri = np.argwhere(neq)[0]
                 raise AssertionError(f"{what}: {name}.{f} differs at query {qi} row {ri}: got {g[qi, ri]} exp {e[qi, ri]}")
         for f in ("x", "y", "z"):
-            d = np.abs(g[f] - e[f])
-            d = np.where(owned, d, 0.0)
+            d = np.abs(np.where(owned, g[f], 0.0) - np.where(owned, e[f], 0.0))  # rows beyond n_rows are unspecified
             assert not np.isnan(d).any(), f"{what}: NaN in {name}.{f}"
             m = float(d.max()) if d.size else 0.0
             if m > XYZ_TOL:
