@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1"])
     ap.add_argument("--ref-sample", type=int, default=16384, help="queries per step of the CPU arm")
-    ap.add_argument("--cpu-sample", type=int, default=16384, help="queries of the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=65536, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-as-written", action="store_true", help="skip timing oracle/_ref in --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
