@@ -350,3 +350,30 @@ def test_wide_foot_discs(fhp, oracle, foot_radius):
     c = np.stack([q["x"][:64] + 0.2, q["y"][:64]], axis=1)
     assert np.array_equal(fhp.mean_height(p, c).view(np.uint32), oracle.mean_height(m, p, c).view(np.uint32))
     assert np.array_equal(fhp.check_default(p, c), oracle.check_default(m, p, c))
+
+
+@pytest.mark.parametrize("nq", [5, 3000, 40000])  # 1, 1 and 8 queries per warp on a B200
+def test_device_resident_plan_equals_host_plan(fhp, nq):
+    """fhp_plan_device (device-resident queries and rows, caller's stream) writes exactly what fhp_plan returns."""
+    import torch
+    m = synth.rough_map(900, 900, 0.02, seed=91, start=(11, 800))
+    fhp.set_map(m)
+    p = _abi.yaml_params()
+    q = synth.uniform_queries(nq, (-7.0, 4.0), (-7.0, 7.0), seed=nq)
+    nom, cen, st = fhp.plan(p, q, 10, centroid=True)
+    R = _abi.rows_per_query(10)
+    d_q = torch.from_numpy(np.ascontiguousarray(q).view(np.uint8)).cuda()
+    d_nom = torch.zeros(nq * R * 40, dtype=torch.uint8, device="cuda")
+    d_cen = torch.zeros(nq * R * 40, dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros(nq * 8, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    parr, npar = fhp._params_array(p)
+    fhp.plan_device(parr, npar, d_q, nq, 10, d_nom, d_cen, d_st, stream=stream.cuda_stream)
+    stream.synchronize()
+    fhp.synchronize()
+    st2 = d_st.cpu().numpy().view(_abi.STATUS_DTYPE)
+    assert np.array_equal(st, st2)
+    keep = np.arange(R)[None, :] < st["n_rows"][:, None]
+    for got, exp in ((d_nom, nom), (d_cen, cen)):
+        g = got.cpu().numpy().view(_abi.FOOTHOLD_DTYPE).reshape(nq, R)
+        assert np.array_equal(g[keep], exp[keep])
