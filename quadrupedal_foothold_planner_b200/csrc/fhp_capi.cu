@@ -395,7 +395,6 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   G.rpShift = G.pack == 4 ? 3 : (G.pack == 2 ? 4 : 5);
   G.nIter = (G.WIN + G.pack - 1) / G.pack;
   G.stride = 4 * G.nIter;
-  G.lpwShift = G.WIN <= 8 ? 3 : (G.WIN <= 16 ? 4 : 5);
 
   // ---- SpiralIterator order: centre, then ring d = 1..nRings generated by the upstream walk and consumed from
   // the BACK of the ring vector (pointsRing_.back()/pop_back()).

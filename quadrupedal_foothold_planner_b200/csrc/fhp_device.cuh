@@ -1,20 +1,23 @@
-// libfhp device code (sm_100a).  One LANE owns one query (or one fine-grained task); the 32 lanes of a warp
-// cooperate only to stage each lane's search window as bit-planes in shared memory.
+// libfhp device code (sm_100a).  One LANE owns one (query, leg) — or one fine-grained task — and carries its state in
+// registers; the 32 lanes of a warp cooperate only where the work is wide: staging each lane's search window into
+// shared memory and scanning a spiral's ranks 32 at a time.
 //
 // Why this shape: the per-foothold work is ~100 map cells and a few hundred double-precision
-// scalar operations that must reproduce grid_map_core's arithmetic bit for bit.  Lane-per-query makes that
-// scalar restatement cost 1/32 of a warp instruction per query; the only wide, coalescable part — reading the
-// (2*HW+1)^2 traversability window around the search centre — is done by all 32 lanes for one query at a time
-// (rows of the column-major layer are contiguous, so a warp load covers whole columns of the window) and
-// reduced with __ballot_sync into three bit-planes per window column:
+// scalar operations that must reproduce grid_map_core's arithmetic bit for bit.  Lane-per-leg makes that scalar
+// restatement cost 1/32 of a warp instruction per foothold.  Every map-cell predicate of the path is a per-call
+// constant, so the (2*HW+1)^2 traversability window around the search centre lives in shared memory as three
+// bit-planes per window column:
 //     D: cell < defaultFootholdThreshold      (raw compare; NaN -> 0)          FP.cpp:1653, :1736, :2057
 //     C: cell < candidateFootholdThreshold                                      FP.cpp:2138
 //     F: isfinite(cell)                        GridMap::isValid                 FP.cpp:2055, :2132
-// Every decision of the reference (centroid row scan, foot-disc test, spiral candidates, polygon test) then
-// becomes bit arithmetic on those planes in the owning lane.
+// filled either from the per-map cell-class planes (stage_windows_mask: one 16-byte load per column, the default) or
+// from the float layer (stage_windows_tma: 2-D TMA boxes; stage_windows: coalesced loads; both reduced with
+// __ballot_sync).  Every decision of the reference (centroid row scan, foot-disc test, spiral candidates, polygon
+// test) then becomes bit arithmetic on those planes in the owning lane.
 //
 // All double arithmetic follows the operand order of grid_map_core / FootholdPlanner.cpp; this translation unit
-// is compiled with -fmad=false so no multiply-add is ever contracted (x86-64 reference builds have no FMA).
+// is compiled with -fmad=false so no multiply-add is ever contracted (x86-64 reference builds have no FMA); the few
+// fused operations (div3_rn) are explicit and proven to round like the expression they replace.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

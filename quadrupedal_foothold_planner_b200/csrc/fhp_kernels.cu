@@ -2,9 +2,12 @@
 //
 // plan_kernel: one LANE per (query, leg); the 4 lanes of a quad own the RF,RH,LH,LF feet of one query and carry
 // BOTH chains of the reference's cycle loop (FP.cpp:762-1579) in registers across all gait cycles, so one launch
-// plans every cycle of every query (the sequential gait-cycle dependency never leaves the SM).  A warp = 8
-// queries; the only cross-lane traffic is quad shuffles (stance centroid, 4-way AND) and the warp-cooperative
-// window staging.
+// plans every cycle of every query (the sequential gait-cycle dependency never leaves the SM).  A warp = up to 8
+// queries (fewer when the batch cannot fill the GPU); the only cross-lane traffic is quad shuffles (stance centroid,
+// 4-way AND), the warp-cooperative window staging and the cooperative spiral rank scan.
+// mask_build_kernel: the per-map cell-class planes the default staging path reads.
+// scan_rows_kernel / compact_rows_kernel: the compact (service-shaped) response of fhp_plan_compact.
+// task_kernel: the reference's fine-grained public members, one lane per call.
 #include "fhp_device.cuh"
 #include "fhp_host.h"
 

@@ -41,7 +41,6 @@ struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int nIter;     // ceil(WIN / pack) = words per bit-plane
   int stride;    // shared-memory words per query (4 per load iteration: D, C, F, pad)
   int stageMode; // kStageLdg / kStageTma / kStageMask: how plan_kernel fills the planes
-  int lpwShift;  // mask staging: log2 of the lanes that serve one window (8, 16 or 32 lanes for WIN <= 8, 16, 32)
   int winRows;   // window rows a consumer may read: WIN, plus the TMA row-alignment shift (<= 3) in TMA mode
   int spiralWords;  // 32-bit words reserved at the start of shared memory for the spiral table (16-byte multiple)
   // TMA staging (plan_kernel): each window is fetched as one 2-D box of boxWords floats (32 rows*cols per load
