@@ -519,6 +519,33 @@ struct DiscWin {
   int generic;  // 1: m is not filled, consumers walk [tl, br] with the distance test themselves
   __device__ __forceinline__ bool small() const { return generic == 0; }
 };
+template <int K>
+__device__ __forceinline__ unsigned long long disc_members(const MapDev& M, double cx, double cy, int tl0, int tl1,
+                                                            double r2) {
+  constexpr int N = 2 * K + 1;
+  double dy2[N];
+  unsigned colsIn = 0;
+#pragma unroll
+  for (int i1 = 0; i1 < N; ++i1) {
+    const int u1 = tl1 + i1;
+    const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+    dy2[i1] = dy * dy;
+    if (u1 >= 0 && u1 < M.cols) colsIn |= 1u << i1;
+  }
+  unsigned long long m = 0ull;
+#pragma unroll
+  for (int i0 = 0; i0 < N; ++i0) {  // row-major bit order = the iterator's visiting order
+    const int u0 = tl0 + i0;
+    const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+    const double dx2 = dx * dx;
+    unsigned rowBits = 0;
+#pragma unroll
+    for (int i1 = 0; i1 < N; ++i1)
+      if (dx2 + dy2[i1] <= r2) rowBits |= 1u << i1;
+    if (u0 >= 0 && u0 < M.rows) m |= static_cast<unsigned long long>(rowBits & colsIn) << (8 * i0);
+  }
+  return m;
+}
 __device__ __noinline__ DiscWin disc_window_generic(const MapDev& M, double cx, double cy, double r) {
   DiscWin d;
   const double tlx = bound_axis(cx + r, M.lenx, M.posx, M.halfx), tly = bound_axis(cy + r, M.leny, M.posy, M.halfy);
@@ -542,19 +569,25 @@ __device__ __forceinline__ DiscWin disc_window(const MapDev& M, const GeoDev& G,
   d.tl1 = uc1 - k;
   d.br0 = uc0 + k;
   d.br1 = uc1 + k;
-  d.m = 0ull;
-  for (int i0 = 0; i0 <= 2 * k; ++i0) {  // row-major bit order = the iterator's visiting order
-    const int u0 = d.tl0 + i0;
-    if (u0 < 0 || u0 >= M.rows) continue;
-    const double dx = pos_axis(M.fcx, M.res, u0) - cx;
-    const double dx2 = dx * dx;
-    unsigned rowBits = 0;
-    for (int i1 = 0; i1 <= 2 * k; ++i1) {
-      const int u1 = d.tl1 + i1;
-      const double dy = pos_axis(M.fcy, M.res, u1) - cy;
-      if (dx2 + dy * dy <= r2 && u1 >= 0 && u1 < M.cols) rowBits |= 1u << i1;
+  if (k == 1) {  // footRadius < 1.5 cells (the yaml geometry at 0.02 m): 3 x 3, straight-line
+    d.m = disc_members<1>(M, cx, cy, d.tl0, d.tl1, r2);
+  } else if (k == 2) {  // < 2.5 cells (0.01 m): 5 x 5
+    d.m = disc_members<2>(M, cx, cy, d.tl0, d.tl1, r2);
+  } else {
+    d.m = 0ull;
+    for (int i0 = 0; i0 <= 2 * k; ++i0) {  // row-major bit order = the iterator's visiting order
+      const int u0 = d.tl0 + i0;
+      if (u0 < 0 || u0 >= M.rows) continue;
+      const double dx = pos_axis(M.fcx, M.res, u0) - cx;
+      const double dx2 = dx * dx;
+      unsigned rowBits = 0;
+      for (int i1 = 0; i1 <= 2 * k; ++i1) {
+        const int u1 = d.tl1 + i1;
+        const double dy = pos_axis(M.fcy, M.res, u1) - cy;
+        if (dx2 + dy * dy <= r2 && u1 >= 0 && u1 < M.cols) rowBits |= 1u << i1;
+      }
+      d.m |= static_cast<unsigned long long>(rowBits) << (8 * i0);
     }
-    d.m |= static_cast<unsigned long long>(rowBits) << (8 * i0);
   }
   return d;
 }
