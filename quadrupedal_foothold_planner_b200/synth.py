@@ -169,3 +169,23 @@ def config_c3(n_queries=65536, rows=4000, cols=4000, seed_map=3, seed_q=4, start
     # 16 cycles advance 2.9 m; keep every window >= 0.5 m inside the map
     q = uniform_queries(n_queries, (-half + 1.0, half - 4.5), (-half + 1.0, half - 1.0), seed=seed_q)
     return m, q, 16
+
+
+def config_c4(n_poses=64, n_steps=64, rows=1500, cols=1500, seed_map=5, seed_q=6):
+    """The heading-0 slice of BASELINE config 4: {trot, walk} x n_steps step lengths in [0.10, 0.26] (skew =
+    stepLength/4, yaml:44) x n_poses start poses, 8 cycles, on a C3-style rough map with start index (0,0).
+    -> (map, params list [2*n_steps], queries [2*n_steps*n_poses] with param_id, cycles).
+    The heading sweep itself is an extension the reference does not have (the body always advances along +x,
+    FP.cpp:2199-2202) and is not implemented."""
+    from ._abi import FHP_GAIT_TROT, FHP_GAIT_WALK, yaml_params
+    m = rough_map(rows, cols, 0.02, seed=seed_map, start=(0, 0))
+    params = []
+    for gait in (FHP_GAIT_TROT, FHP_GAIT_WALK):
+        for sl in np.linspace(0.10, 0.26, n_steps):
+            sl32 = float(np.float32(sl))
+            params.append(yaml_params(gait=gait, step_length=sl32, skew=float(np.float32(sl32 / 4))))
+    half = rows * 0.02 / 2
+    poses = uniform_queries(n_poses, (-half + 1.0, half - 3.5), (-half + 1.0, half - 1.0), seed=seed_q)
+    q = np.tile(poses, len(params))
+    q["param_id"] = np.repeat(np.arange(len(params), dtype=np.int32), n_poses)
+    return m, params, q, 8

@@ -377,3 +377,15 @@ def test_device_resident_plan_equals_host_plan(fhp, nq):
     for got, exp in ((d_nom, nom), (d_cen, cen)):
         g = got.cpu().numpy().view(_abi.FOOTHOLD_DTYPE).reshape(nq, R)
         assert np.array_equal(g[keep], exp[keep])
+
+
+def test_c4_parameter_sweep_heading_zero(fhp, oracle):
+    """BASELINE config 4 at heading 0 (the slice the reference defines): 128 parameter sets ({trot, walk} x 64 step
+    lengths, skew = stepLength/4) x 64 poses in ONE call, every query against the oracle."""
+    m, params, q, N = synth.config_c4()
+    assert len(params) == 128 and len(q) == 128 * 64
+    got, exp = _run_both(fhp, oracle, m, params, q, N)
+    assert compare_plans(got, exp, "C4 heading 0") <= XYZ_TOL
+    # different step lengths really produce different plans
+    first = got[0][:, 4]["x"].reshape(128, 64)
+    assert np.unique(np.round(first[:64, 0] - first[0, 0], 9)).size > 32
