@@ -328,8 +328,8 @@ def main():
     def step_resident():
         fhp.plan_device(parr, npar, d_q, nq, cycles, d_nom, None, d_st, stream=stream.cuda_stream)
 
-    def step_e2e():  # the service-shaped call: every query returns the rows it produced (fhp_plan_compact)
-        fhp.plan_compact_raw(parr, npar, h_q, nq, cycles, h_nom, nq * R, h_offs, h_st)
+    def step_e2e():  # the service-shaped call: every query returns the rows it produced, 32 bytes each
+        fhp.plan_compact_raw(parr, npar, h_q, nq, cycles, h_nom, nq * R, h_offs, h_st, packed=True)
 
     def step_e2e_fixed():  # fixed-pitch rows (fhp_plan): all nq*R row slots cross PCIe
         fhp.plan_raw(parr, npar, h_q, nq, cycles, h_nom, None, h_st)
@@ -429,9 +429,10 @@ def main():
                            sum(t.numel() * 4 for t in layers) / (bcast_ms * 1e-3) / 1e9, 1))},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_q.numel()),
-                    "d2h_bytes_per_step": int(rows_written * _abi.FOOTHOLD_DTYPE.itemsize + h_st.numel() + 8 * nq + 64),
+                    "d2h_bytes_per_step": int(rows_written * _abi.FOOTHOLD_PACKED_DTYPE.itemsize + h_st.numel() + 8 * nq + 64),
                     "steps": e2e_steps,
-                    "call": "fhp_plan_compact on pinned host buffers (queries H2D, produced rows + offsets + status D2H)",
+                    "call": "fhp_plan_compact_packed on pinned host buffers (queries H2D; produced 32-byte rows + "
+                            "offsets + status D2H)",
                     "fixed_pitch": {"value": e2e_fixed_value, "d2h_bytes_per_step": int(h_nom.numel() + h_st.numel()),
                                     "call": "fhp_plan (every row slot returned)"}},
             "gpu_launches": int(launches),

@@ -215,6 +215,20 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
 int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
                      int64_t n_queries, int32_t gait_cycles, fhp_foothold* out_rows, int64_t capacity_rows,
                      int64_t* row_offsets, fhp_query_status* status);
+/* The compact response with 32-byte rows: the same information as fhp_foothold with the cell index as two uint16
+ * (0xFFFF = outside the map) — 20 % fewer bytes over PCIe.  FHP_ERR_UNSUPPORTED for maps with more than 65,534 rows or
+ * columns (the grid_map message itself carries uint16 start indices). */
+typedef struct fhp_foothold_packed {
+  double x, y, z;        /* point */
+  uint16_t row, col;     /* buffer index of the cell containing (x,y); 0xFFFF when outside the map */
+  uint8_t foot_id;
+  uint8_t gait_cycle_id;
+  uint8_t kind;
+  uint8_t reserved;
+} fhp_foothold_packed;
+int fhp_plan_compact_packed(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                            int64_t n_queries, int32_t gait_cycles, fhp_foothold_packed* out_rows,
+                            int64_t capacity_rows, int64_t* row_offsets, fhp_query_status* status);
 /* KPIs the reference logs per successful cycle (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623): pure
  * host-side functions of ONE query's response rows (nominal or centroid chain).  feet_distance / cog_speed receive
  * 2 values per successful cycle (n_rows/4 - 1 cycles). */

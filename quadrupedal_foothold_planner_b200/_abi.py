@@ -63,9 +63,14 @@ FOOTHOLD_DTYPE = np.dtype([
     ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("row", "<i4"), ("col", "<i4"),
     ("foot_id", "u1"), ("gait_cycle_id", "u1"), ("kind", "u1"), ("reserved0", "u1"), ("reserved1", "<u4"),
 ])
+FOOTHOLD_PACKED_DTYPE = np.dtype([  # fhp_foothold_packed (32 bytes)
+    ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("row", "<u2"), ("col", "<u2"),
+    ("foot_id", "u1"), ("gait_cycle_id", "u1"), ("kind", "u1"), ("reserved", "u1"),
+])
 STATUS_DTYPE = np.dtype([("success", "u1"), ("gait_cycles", "u1"), ("gait_cycles_succeed", "u1"), ("reserved", "u1"),
                          ("n_rows", "<i4")])
 assert QUERY_DTYPE.itemsize == 32 and FOOTHOLD_DTYPE.itemsize == 40 and STATUS_DTYPE.itemsize == 8
+assert FOOTHOLD_PACKED_DTYPE.itemsize == 32
 
 
 def rows_per_query(gait_cycles: int) -> int:

@@ -84,7 +84,8 @@ struct fhp_ctx {
   void* hSmall = nullptr;
   void* dSmall = nullptr;
   cudaStream_t copyStream = nullptr;   // response rows of fhp_plan_compact travel here while the next chunk plans
-  long long* hTotals = nullptr;        // pinned: rows per chunk (fhp_plan_compact)
+  long long* hTotals = nullptr;        // mapped pinned: rows per chunk + 1, written by the scan kernel (fhp_plan_compact)
+  long long* dTotals = nullptr;        // device alias
   int hTotalsCap = 0;
   std::vector<cudaEvent_t> chunkEv;
   long long launches = 0;
@@ -1017,9 +1018,28 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
 // The same plan with a COMPACT response: like the service, every query returns only the rows it produced.
 // Chunk i plans, scans its n_rows and packs its rows on one of two streams while the packed rows of chunk i-1 cross
 // PCIe on the copy stream; the host learns each chunk's row count from a pinned word before it issues that copy.
+static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                             int64_t n_queries, int32_t gait_cycles, void* out_rows, bool packed, int64_t capacity_rows,
+                             int64_t* row_offsets, fhp_query_status* status);
+
 int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
                      int32_t gait_cycles, fhp_foothold* out_rows, int64_t capacity_rows, int64_t* row_offsets,
                      fhp_query_status* status) {
+  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, false, capacity_rows,
+                           row_offsets, status);
+}
+int fhp_plan_compact_packed(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                            int64_t n_queries, int32_t gait_cycles, fhp_foothold_packed* out_rows, int64_t capacity_rows,
+                            int64_t* row_offsets, fhp_query_status* status) {
+  if (ctx && ctx->haveMap && (ctx->M.rows > 65534 || ctx->M.cols > 65534))
+    return fail(ctx, FHP_ERR_UNSUPPORTED, "packed rows hold the cell index as uint16: map has more than 65534 rows or columns");
+  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, true, capacity_rows,
+                           row_offsets, status);
+}
+
+static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                             int64_t n_queries, int32_t gait_cycles, void* out_rows, bool packed, int64_t capacity_rows,
+                             int64_t* row_offsets, fhp_query_status* status) {
   if (!ctx) return FHP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 || capacity_rows < 0 || !row_offsets ||
@@ -1037,12 +1057,20 @@ int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, c
   if (rc != FHP_OK) return rc;
   rc = ensure_err_word(ctx);
   if (rc != FHP_OK) return rc;
-  // chunks of a third of a wave: small enough that the first chunk's kernel (the only one PCIe cannot hide) is short,
-  // large enough that launches and event waits stay negligible (measured: 1/3..1/4 of a wave is the flat optimum)
-  const int64_t wave = chunk_queries(ctx, false);
-  int64_t nChunks = std::max<int64_t>(1, (n_queries + wave - 1) / wave);
-  const int64_t per = ((n_queries + nChunks - 1) / nChunks + 31) / 32 * 32;
-  nChunks = (n_queries + per - 1) / per;
+  // Chunks of a third of a wave: small enough that the first chunk's kernel (the only one PCIe cannot hide) is short,
+  // large enough that launches stay negligible and kernels still overlap the copies (measured: 1/3..1/4 of a wave is
+  // the flat optimum; a graduated schedule with a small first chunk is slower).
+  const int64_t cap = chunk_queries(ctx, false);
+  std::vector<int64_t> chunkLo, chunkN;
+  {
+    const int64_t k = std::max<int64_t>(1, (n_queries + cap - 1) / cap);
+    const int64_t per = ((n_queries + k - 1) / k + 31) / 32 * 32;  // whole blocks per chunk
+    for (int64_t lo = 0; lo < n_queries; lo += per) {
+      chunkLo.push_back(lo);
+      chunkN.push_back(std::min<int64_t>(per, n_queries - lo));
+    }
+  }
+  const int64_t nChunks = static_cast<int64_t>(chunkLo.size());
   CU(ctx->dQ.reserve(sizeof(fhp_query) * n_queries));
   CU(ctx->dOutN.reserve(sizeof(fhp_foothold) * R * n_queries));
   CU(ctx->dCompact.reserve(sizeof(fhp_foothold) * R * n_queries));
@@ -1053,8 +1081,11 @@ int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, c
     if (ctx->hTotals) cudaFreeHost(ctx->hTotals);
     ctx->hTotals = nullptr;
     void* h = nullptr;
-    CU(cudaHostAlloc(&h, sizeof(long long) * nChunks, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&h, sizeof(long long) * nChunks, cudaHostAllocMapped));
     ctx->hTotals = static_cast<long long*>(h);
+    void* d = nullptr;
+    CU(cudaHostGetDevicePointer(&d, h, 0));
+    ctx->dTotals = static_cast<long long*>(d);
     ctx->hTotalsCap = static_cast<int>(nChunks);
   }
   while (static_cast<int64_t>(ctx->chunkEv.size()) < nChunks) {
@@ -1068,42 +1099,63 @@ int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, c
   fhp_query_status* dS = static_cast<fhp_query_status*>(ctx->dSt.p);
   long long* dO = static_cast<long long*>(ctx->dOffs.p);
   // enqueue every chunk's device work up front (two alternating streams)
-  int64_t c = 0;
-  for (int64_t lo = 0; lo < n_queries; lo += per, ++c) {
-    const int64_t n = std::min<int64_t>(per, n_queries - lo);
+  for (int64_t i = 0; i < nChunks; ++i) ctx->hTotals[i] = 0;
+  for (int64_t c = 0; c < nChunks; ++c) {
+    const int64_t lo = chunkLo[static_cast<size_t>(c)], n = chunkN[static_cast<size_t>(c)];
     cudaStream_t cs = (c & 1) ? ctx->stream2 : ctx->stream;
     long long* offs = dO + lo + c;  // n + 1 entries per chunk
     CU(cudaMemcpyAsync(dq + lo, queries + lo, sizeof(fhp_query) * n, cudaMemcpyHostToDevice, cs));
     rc = plan_launch(ctx, n_params, dq + lo, n, gait_cycles, dN + lo * R, nullptr, dS + lo, cs);
     if (rc != FHP_OK) return rc;
-    CU(launch_compact(dN + lo * R, dS + lo, n, static_cast<int>(R), offs, dC + lo * R, cs));
+    CU(launch_compact(dN + lo * R, dS + lo, n, static_cast<int>(R), offs, dC + lo * R, packed, ctx->dTotals + c, cs));
     ctx->launches += 2;
-    CU(cudaMemcpyAsync(&ctx->hTotals[c], offs + n, sizeof(long long), cudaMemcpyDeviceToHost, cs));
-    CU(cudaMemcpyAsync(row_offsets + lo, offs, sizeof(long long) * n, cudaMemcpyDeviceToHost, cs));  // chunk-local
-    CU(cudaMemcpyAsync(status + lo, dS + lo, sizeof(fhp_query_status) * n, cudaMemcpyDeviceToHost, cs));
     CU(cudaEventRecord(ctx->chunkEv[c], cs));
   }
-  // as each chunk finishes: place its rows behind those of the chunks before it
+  // As each chunk's row count appears in the mapped word (written by its scan kernel), queue its copies on the copy
+  // stream behind the chunk's event: the host never sleeps on an event, so the copy engine always has the next chunk
+  // queued.  Rows land behind those of the chunks before; offsets are chunk-local until the end.
   int64_t base = 0;
   int err = FHP_OK;
-  c = 0;
-  for (int64_t lo = 0; lo < n_queries; lo += per, ++c) {
-    const int64_t n = std::min<int64_t>(per, n_queries - lo);
-    CU(cudaEventSynchronize(ctx->chunkEv[c]));
-    const int64_t total = ctx->hTotals[c];
+  std::vector<int64_t> bases(static_cast<size_t>(nChunks), 0);
+  const size_t rowB = packed ? sizeof(fhp_foothold_packed) : sizeof(fhp_foothold);
+  for (int64_t c = 0; c < nChunks; ++c) {
+    const int64_t lo = chunkLo[static_cast<size_t>(c)], n = chunkN[static_cast<size_t>(c)];
+    cudaStream_t cs = (c & 1) ? ctx->stream2 : ctx->stream;
+    volatile long long* word = ctx->hTotals + c;
+    long long t = 0;
+    for (unsigned spins = 0; (t = *word) == 0; ++spins) {
+      if ((spins & 0x3ff) == 0x3ff) {
+        const cudaError_t q = cudaStreamQuery(cs);
+        if (q == cudaSuccess) {  // the stream drained: the word must be there now
+          t = *word;
+          if (t == 0) return fail(ctx, FHP_ERR_CUDA, "compact response: the chunk finished without reporting its row count");
+          break;
+        }
+        if (q != cudaErrorNotReady) return fail(ctx, FHP_ERR_CUDA, std::string("compact response: ") + cudaGetErrorString(q));
+      }
+    }
+    const int64_t total = t - 1;
+    bases[static_cast<size_t>(c)] = base;
+    CU(cudaStreamWaitEvent(ctx->copyStream, ctx->chunkEv[c], 0));
     if (base + total > capacity_rows) {
       err = FHP_ERR_INVALID_ARG;
     } else if (total > 0 && err == FHP_OK) {
-      CU(cudaMemcpyAsync(out_rows + base, dC + lo * R, sizeof(fhp_foothold) * total, cudaMemcpyDeviceToHost, ctx->copyStream));
+      CU(cudaMemcpyAsync(static_cast<char*>(out_rows) + base * rowB, dC + lo * R, rowB * total, cudaMemcpyDeviceToHost,
+                         ctx->copyStream));
     }
-    if (base != 0)
-      for (int64_t i = 0; i < n; ++i) row_offsets[lo + i] += base;  // chunk-local -> global
+    CU(cudaMemcpyAsync(row_offsets + lo, dO + lo + c, sizeof(long long) * n, cudaMemcpyDeviceToHost, ctx->copyStream));
+    CU(cudaMemcpyAsync(status + lo, dS + lo, sizeof(fhp_query_status) * n, cudaMemcpyDeviceToHost, ctx->copyStream));
     base += total;
   }
-  row_offsets[n_queries] = base;
   CU(cudaStreamSynchronize(ctx->copyStream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream2));
+  for (int64_t c = 0; c < nChunks; ++c) {  // chunk-local -> global offsets
+    const int64_t lo = chunkLo[static_cast<size_t>(c)], n = chunkN[static_cast<size_t>(c)], b = bases[static_cast<size_t>(c)];
+    if (b != 0)
+      for (int64_t i = 0; i < n; ++i) row_offsets[lo + i] += b;
+  }
+  row_offsets[n_queries] = base;
   if (err != FHP_OK) return fail(ctx, err, "capacity_rows is smaller than the rows the queries produced (row_offsets[n] holds the need)");
   return check_dev_err(ctx);
 }

@@ -399,7 +399,7 @@ cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* ma
 // offs[q] = sum of n_rows of the queries before q (exclusive scan; offs[n] = total).  One block; a wave-sized chunk
 // is a few tens of thousands of queries.
 __global__ void __launch_bounds__(1024) scan_rows_kernel(const fhp_query_status* __restrict__ st, long long n,
-                                                         long long* __restrict__ offs) {
+                                                         long long* __restrict__ offs, long long* hostTotal) {
   __shared__ long long warpSum[32];
   __shared__ long long carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -432,29 +432,55 @@ __global__ void __launch_bounds__(1024) scan_rows_kernel(const fhp_query_status*
     if (threadIdx.x == 1023) carry = before + v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) offs[n] = carry;
+  if (threadIdx.x == 0) {
+    offs[n] = carry;
+    if (hostTotal) {  // mapped host word: the host sizes the chunk's row copy from it without waiting for an event
+      *reinterpret_cast<volatile long long*>(hostTotal) = carry + 1;  // + 1: zero means "not yet"
+      __threadfence_system();
+    }
+  }
 }
 
-// One warp per query: its n_rows rows (40 bytes = five 8-byte words each) move from the fixed-pitch plan output to
-// out + offs[q].
+// One warp per query: its n_rows rows move from the fixed-pitch plan output to out + offs[q] — as they are (40 bytes =
+// five 8-byte words each) or PACKED to 32 bytes (x, y, z, then row/col as uint16 and the three id bytes in one word).
+template <bool PACKED>
 __global__ void __launch_bounds__(256) compact_rows_kernel(const fhp_foothold* __restrict__ rows,
                                                            const long long* __restrict__ offs, long long n, int R,
-                                                           fhp_foothold* __restrict__ out) {
+                                                           void* __restrict__ out) {
   const long long q = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= n) return;
   const int lane = threadIdx.x & 31;
   const long long o = offs[q];
-  const int words = static_cast<int>(offs[q + 1] - o) * 5;
+  const int nr = static_cast<int>(offs[q + 1] - o);
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(rows + q * R);
-  unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + o);
-  for (int w = lane; w < words; w += 32) dst[w] = src[w];
+  if (!PACKED) {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(static_cast<fhp_foothold*>(out) + o);
+    for (int w = lane; w < nr * 5; w += 32) dst[w] = src[w];
+  } else {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(static_cast<fhp_foothold_packed*>(out) + o);
+    for (int w = lane; w < nr * 4; w += 32) {
+      const int r = w >> 2, k = w & 3;
+      unsigned long long v;
+      if (k < 3) {
+        v = src[r * 5 + k];
+      } else {
+        const unsigned long long idx = src[r * 5 + 3], ids = src[r * 5 + 4];  // row | col << 32 ; foot | cycle << 8 | kind << 16
+        v = (idx & 0xffffull) | ((idx >> 32 & 0xffffull) << 16) | ((ids & 0xffffffull) << 32);
+      }
+      dst[w] = v;
+    }
+  }
 }
 
 cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st, long long n, int R, long long* offs,
-                           fhp_foothold* out, cudaStream_t stream) {
+                           void* out, bool packed, long long* hostTotal, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  scan_rows_kernel<<<1, 1024, 0, stream>>>(st, n, offs);
-  compact_rows_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(rows, offs, n, R, out);
+  scan_rows_kernel<<<1, 1024, 0, stream>>>(st, n, offs, hostTotal);
+  const unsigned nb = static_cast<unsigned>((n + 7) / 8);
+  if (packed)
+    compact_rows_kernel<true><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
+  else
+    compact_rows_kernel<false><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
   return cudaGetLastError();
 }
 

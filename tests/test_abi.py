@@ -39,6 +39,8 @@ def test_struct_layouts_match_header(tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu %zu\n", sizeof(fhp_map_desc), sizeof(fhp_params), sizeof(fhp_query), sizeof(fhp_foothold),
          sizeof(fhp_query_status));
+  if (sizeof(fhp_foothold_packed) != 32 || offsetof(fhp_foothold_packed, row) != 24 ||
+      offsetof(fhp_foothold_packed, foot_id) != 28 || offsetof(fhp_foothold_packed, kind) != 30) return 1;
   printf("%zu %zu %zu %zu %zu\n", offsetof(fhp_params, h), offsetof(fhp_params, bias), offsetof(fhp_foothold, row),
          offsetof(fhp_foothold, foot_id), offsetof(fhp_query_status, n_rows));
   printf("%zu %zu %zu\n", offsetof(fhp_map_desc, resolution), offsetof(fhp_map_desc, start_row),

@@ -330,6 +330,13 @@ def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
         fhp.plan_compact(p, q, 12, capacity_rows=int(offs[-1]) - 1)
     rows0, offs0, _ = fhp.plan_compact(p, q[:0], 12)
     assert len(rows0) == 0 and offs0.tolist() == [0]
+    # 32-byte packed rows carry the same information
+    pr, poffs, pst = fhp.plan_compact(p, q, 12, packed=True)
+    assert np.array_equal(poffs, offs) and np.array_equal(pst, st) and pr.dtype.itemsize == 32
+    for f in ("x", "y", "z", "foot_id", "gait_cycle_id", "kind"):
+        assert np.array_equal(pr[f], rows[f])
+    assert np.array_equal(pr["row"], (rows["row"] & 0xFFFF).astype(np.uint16))
+    assert np.array_equal(pr["col"], (rows["col"] & 0xFFFF).astype(np.uint16))
 
 
 @pytest.mark.parametrize("foot_radius", [0.031, 0.05, 0.085])
