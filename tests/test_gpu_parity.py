@@ -396,3 +396,24 @@ def test_c4_parameter_sweep_heading_zero(fhp, oracle):
     # different step lengths really produce different plans
     first = got[0][:, 4]["x"].reshape(128, 64)
     assert np.unique(np.round(first[:64, 0] - first[0, 0], 9)).size > 32
+
+
+def test_c5_sized_map(fhp, oracle):
+    """BASELINE config 5's map size: 16000 x 16000 @ 0.01 m (2.56e8 cells per layer, 1 GB each) with a wrapped start
+    index — index arithmetic, class planes (128 MB) and tensor map at the largest size the configs name."""
+    rows = cols = 16000
+    rng = np.random.default_rng(17)
+    t = np.asfortranarray(rng.random((rows, cols), dtype=np.float32) ** 0.15)  # mostly traversable, some blocked
+    t[::97, ::89] = np.nan
+    e = np.zeros((rows, cols), dtype=np.float32, order="F")
+    e[::2, :] = 0.125
+    m = _abi.HostMap(rows, cols, 0.01, pos=(3.0, -2.0), start=(15999, 7777), layers={"traversability": t, "elevation": e})
+    half = rows * 0.01 / 2
+    pts = [[3.0 - half + 0.5, -2.0 + half - 0.5, 0.0], [3.0 + half - 3.0, -2.0 - half + 0.5, 0.1], [3.0, -2.0, 0.0],
+           [3.0 + 70.0, -2.0 + 65.0, 0.0], [3.0 - 79.0, -2.0 - 79.5, 0.0]]
+    q = np.concatenate([_abi.make_queries(pts), synth.uniform_queries(123, (3.0 - 75, 3.0 + 70), (-2.0 - 75, -2.0 + 75), seed=8)])
+    p = _abi.yaml_params()
+    got, exp = _run_both(fhp, oracle, m, p, q, 6)
+    assert compare_plans(got, exp, "C5-sized map") <= XYZ_TOL
+    assert (got[2]["n_rows"] > 4).sum() > 30
+    fhp.set_map(synth.flat_map(64, 64, 0.02))  # release the 2 GB of layers for the tests that follow
