@@ -71,6 +71,12 @@ struct fhp_ctx {
   // of ldg).  The tests run every path; calls the preferred path cannot serve fall back mask -> tma -> ldg.
   int stagePref = kStageMask;
   int geoStage = -1;  // staging path the cached geometry tables were laid out for
+  // experiment knobs, read once at fhp_create: FHP_CHUNK_DIV (host pipeline chunk = wave / div), FHP_QPW_SHIFT (force
+  // log2 queries per warp), FHP_TMA_BOX_BUDGET (bytes of TMA box buffers per warp)
+  int chunkDiv = 3;
+  long long waveQueries[2] = {0, 0};  // plan_wave_queries(G, wantCen) for the cached geometry (0 = not asked yet)
+  int qpwShiftForce = -1;
+  int tmaBoxBudget = 8192;
   // D/C/F mask planes of the traversability layer for one threshold pair (rebuilt lazily after a map update)
   DevBuf dMask;
   bool maskValid = false;
@@ -434,8 +440,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   const int warps = kPlanThreads / 32;
   const int planesEnd = G.spiralWords + warps * 32 * G.stride;
   G.boxWords = 32 * G.nIter;
-  int boxBudget = 8192;  // bytes of box buffers per warp (two rounds in flight)
-  if (const char* e = std::getenv("FHP_TMA_BOX_BUDGET")) boxBudget = std::max(1024, atoi(e));
+  const int boxBudget = ctx->tmaBoxBudget;  // bytes of box buffers per warp (two rounds in flight)
   G.tmaBShift = 0;
   while (G.tmaBShift < 3 && (2 << (G.tmaBShift + 1)) * G.boxWords * 4 <= boxBudget) ++G.tmaBShift;
   G.tmaB = 1 << G.tmaBShift;
@@ -450,6 +455,7 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   ctx->geoSearch = searchRadius;
   ctx->geoTrim = allowTrim;
   ctx->haveGeo = true;
+  ctx->waveQueries[0] = ctx->waveQueries[1] = 0;
   return FHP_OK;
 }
 
@@ -586,6 +592,9 @@ int fhp_create(int device, fhp_ctx** out) {
   std::memset(&ctx->tmapTrav, 0, sizeof(ctx->tmapTrav));
   if (const char* dt = std::getenv("FHP_DISABLE_TMA"))
     if (dt[0] == '1') ctx->stagePref = kStageLdg;
+  if (const char* e = std::getenv("FHP_CHUNK_DIV")) ctx->chunkDiv = std::max(1, atoi(e));
+  if (const char* e = std::getenv("FHP_QPW_SHIFT")) ctx->qpwShiftForce = std::max(0, std::min(3, atoi(e)));
+  if (const char* e = std::getenv("FHP_TMA_BOX_BUDGET")) ctx->tmaBoxBudget = std::max(1024, atoi(e));
   if (const char* st = std::getenv("FHP_STAGING")) {
     if (!std::strcmp(st, "mask")) ctx->stagePref = kStageMask;
     else if (!std::strcmp(st, "tma")) ctx->stagePref = kStageTma;
@@ -857,11 +866,15 @@ const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* name) {
   return nullptr;
 }
 
+static long long wave_queries(fhp_ctx* ctx, bool wantCen) {  // occupancy query cached per geometry
+  long long& w = ctx->waveQueries[wantCen ? 1 : 0];
+  if (w == 0) w = plan_wave_queries(ctx->G, wantCen);
+  return w;
+}
+
 // Chunk size of the host-buffer pipelines (FHP_CHUNK_DIV overrides the divisor for experiments).
 static int64_t chunk_queries(fhp_ctx* ctx, bool wantCen) {
-  int div = 3;
-  if (const char* e = std::getenv("FHP_CHUNK_DIV")) div = std::max(1, atoi(e));
-  return std::max<int64_t>(1024, plan_wave_queries(ctx->G, wantCen) / div);
+  return std::max<int64_t>(1024, wave_queries(ctx, wantCen) / ctx->chunkDiv);
 }
 
 static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_queries, int64_t n_queries,
@@ -877,10 +890,10 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.nq = n_queries;
   A.cycles = gait_cycles;
   {  // queries per warp: the smallest power of two that still fits the batch into one resident wave of warps
-    const long long waveWarps = std::max<long long>(1, plan_wave_queries(ctx->G, d_outC != nullptr) / 8);
+    const long long waveWarps = std::max<long long>(1, wave_queries(ctx, d_outC != nullptr) / 8);
     const long long need = (n_queries + waveWarps - 1) / waveWarps;
     A.qpwShift = need <= 1 ? 0 : (need <= 2 ? 1 : (need <= 4 ? 2 : 3));
-    if (const char* e = std::getenv("FHP_QPW_SHIFT")) A.qpwShift = std::max(0, std::min(3, atoi(e)));
+    if (ctx->qpwShiftForce >= 0) A.qpwShift = ctx->qpwShiftForce;
   }
   A.outN = d_outN;
   A.outC = d_outC;
@@ -1123,7 +1136,10 @@ static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_p
     cudaStream_t cs = (c & 1) ? ctx->stream2 : ctx->stream;
     volatile long long* word = ctx->hTotals + c;
     long long t = 0;
-    for (unsigned spins = 0; (t = *word) == 0; ++spins) {
+    for (unsigned spins = 0; (t = *word) == 0; ++spins) {  // short: the chunk's kernels are already queued
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
       if ((spins & 0x3ff) == 0x3ff) {
         const cudaError_t q = cudaStreamQuery(cs);
         if (q == cudaSuccess) {  // the stream drained: the word must be there now
