@@ -138,8 +138,6 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
   int nrows = 4, succeed = 0;
   bool success = false;
   unsigned err = 0;
-  const double bx = P.biasx[f], by = P.biasy[f];
-  const float thrD = P.thrD, thrC = P.thrC;
 
   for (int g = 0; g < A.cycles; ++g) {
 #if FHP_SYNC_LEVEL >= 1
@@ -154,6 +152,8 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
                    shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
                    ncx, ncy);
     const double nextY = qu.y + adjY;                                 // :2201
+    // (per-leg bias and thresholds are re-read from the parameter table each cycle: L1 hits, fewer live registers)
+    const double bx = P.biasx[f], by = P.biasy[f];
     double dnx = 0.0, dny = 0.0, dnz = 0.0;                           // getDefaultFootholds (FP.cpp:2253-2304)
     if (wantDef) {
       double dcx, dcy;
@@ -187,11 +187,11 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     prevW0 = w0;
     prevW1 = w1;
     if (STAGE == kStageMask)
-      stage_windows_mask(M, G, A.mask, sw, lane, restage, w0, w1, thrD, thrC);
+      stage_windows_mask(M, G, A.mask, sw, lane, restage, w0, w1, P.thrD, P.thrC);
     else if (USE_TMA)
-      stage_windows_tma(M, G, &A.tmap, T, sw, lane, restage, w0, w1, thrD, thrC);
+      stage_windows_tma(M, G, &A.tmap, T, sw, lane, restage, w0, w1, P.thrD, P.thrC);
     else
-      stage_windows(M, G, sw, lane, restage, w0, w1, thrD, thrC);
+      stage_windows(M, G, sw, lane, restage, w0, w1, P.thrD, P.thrC);
 
 #if FHP_SYNC_LEVEL >= 2
     __syncthreads();
