@@ -5,9 +5,10 @@
  * per-gait-cycle, per-leg foothold search behind the `plan_global_footholds` service
  * (foothold_planner/src/FootholdPlanner.cpp, "FP.cpp" below).  ROS and grid_map stay host-side; a ROS node
  * keeps its `foothold_planner::FootholdPlanner` class and calls these entry points from
- *   - FootholdPlanner::gridmapCallback   (FP.cpp:504-536)  -> fhp_set_map
- *   - FootholdPlanner::globalFootholdPlan (FP.cpp:539-1602) -> fhp_plan (n_queries = 1)
- * (binding shown in INTEGRATION.md).  Batch callers use n_queries >> 1.
+ *   - FootholdPlanner::gridmapCallback   (FP.cpp:504-536)  -> fhp_set_map_msg (the message itself) or fhp_set_map
+ *   - FootholdPlanner::globalFootholdPlan (FP.cpp:539-1602) -> fhp_plan / fhp_plan_ex (n_queries = 1)
+ * (binding shown in INTEGRATION.md).  Batch callers use n_queries >> 1, fhp_plan_compact[_packed] for a
+ * service-shaped variable-length response, fhp_plan_device for device-resident buffers.
  *
  * Conventions: plain pointers and sizes, no exceptions cross the boundary, every function returns an int
  * status (FHP_OK == 0); fhp_last_error(ctx) returns a human-readable message for the last failure.

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <algorithm>
@@ -157,24 +158,12 @@ int set_geometry(fhp_ctx* ctx, const fhp_map_desc* d) {
 constexpr size_t kSmallBytes = 256u << 10;  // fhp_plan* calls whose buffers fit here take the zero-copy latency path
 constexpr size_t kPinChunk = 8u << 20;
 constexpr size_t kDirectBytes = 1u << 20;
-constexpr int kCopyThreads = 4;
+constexpr int kCopyThreads = 6;
 
-void parallel_memcpy(void* dst, const void* src, size_t n) {
-  if (n < (1u << 20)) {
-    std::memcpy(dst, src, n);
-    return;
-  }
-  const size_t per = (n / kCopyThreads + 63) & ~static_cast<size_t>(63);
-  std::thread th[kCopyThreads - 1];
-  int nt = 0;
-  for (int t = 1; t < kCopyThreads; ++t) {
-    const size_t lo = per * t;
-    if (lo >= n) break;
-    const size_t len = std::min(per, n - lo);
-    th[nt++] = std::thread([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, len); });
-  }
-  std::memcpy(dst, src, std::min(per, n));
-  for (int t = 0; t < nt; ++t) th[t].join();
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
 }
 
 int upload_layer(fhp_ctx* ctx, float* dst, const void* src, size_t bytes, cudaStream_t s) {
@@ -191,16 +180,44 @@ int upload_layer(fhp_ctx* ctx, float* dst, const void* src, size_t bytes, cudaSt
       CU(cudaHostAlloc(&ctx->pin[b], kPinChunk, cudaHostAllocDefault));
       CU(cudaEventCreateWithFlags(&ctx->pinEv[b], cudaEventDisableTiming));
     }
-  int b = 0;
-  for (size_t off = 0; off < bytes; off += kPinChunk, b ^= 1) {
-    const size_t n = std::min(kPinChunk, bytes - off);
-    if (ctx->pinUsed[b]) CU(cudaEventSynchronize(ctx->pinEv[b]));  // the DMA that last read this chunk is done
-    parallel_memcpy(ctx->pin[b], static_cast<const char*>(src) + off, n);
-    CU(cudaMemcpyAsync(reinterpret_cast<char*>(dst) + off, ctx->pin[b], n, cudaMemcpyHostToDevice, s));
-    CU(cudaEventRecord(ctx->pinEv[b], s));
-    ctx->pinUsed[b] = true;
+  // Helper threads live for the whole layer (spawning them per chunk costs as much as the copy of a chunk): chunk c is
+  // released to them through `go`, each copies its slice into the pinned buffer and bumps `done`.
+  const int nChunks = static_cast<int>((bytes + kPinChunk - 1) / kPinChunk);
+  const int nThreads = std::max(1, std::min<int>(kCopyThreads, static_cast<int>(std::thread::hardware_concurrency()) / 2));
+  std::atomic<int> go{-1}, done{0};
+  auto slice = [&](int c, int t) {
+    const size_t off = static_cast<size_t>(c) * kPinChunk, n = std::min(kPinChunk, bytes - off);
+    const size_t per = (n / nThreads + 63) & ~static_cast<size_t>(63);
+    const size_t lo = std::min(n, per * t), hi = (t == nThreads - 1) ? n : std::min(n, per * (t + 1));
+    if (hi > lo) std::memcpy(static_cast<char*>(ctx->pin[c & 1]) + lo, static_cast<const char*>(src) + off + lo, hi - lo);
+  };
+  std::vector<std::thread> helpers;
+  for (int t = 1; t < nThreads; ++t)
+    helpers.emplace_back([&, t] {
+      for (int c = 0; c < nChunks; ++c) {
+        while (go.load(std::memory_order_acquire) < c) cpu_relax();
+        slice(c, t);
+        done.fetch_add(1, std::memory_order_release);
+      }
+    });
+  int rc = FHP_OK;
+  for (int c = 0; c < nChunks; ++c) {
+    const int b = c & 1;
+    const size_t off = static_cast<size_t>(c) * kPinChunk, n = std::min(kPinChunk, bytes - off);
+    cudaError_t e = cudaSuccess;
+    if (ctx->pinUsed[b]) e = cudaEventSynchronize(ctx->pinEv[b]);  // the DMA that last read this buffer is done
+    go.store(c, std::memory_order_release);  // (released even after an error so that the helpers run out)
+    slice(c, 0);
+    while (done.load(std::memory_order_acquire) < (c + 1) * (nThreads - 1)) cpu_relax();
+    if (e == cudaSuccess && rc == FHP_OK) {
+      e = cudaMemcpyAsync(reinterpret_cast<char*>(dst) + off, ctx->pin[b], n, cudaMemcpyHostToDevice, s);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->pinEv[b], s);
+      ctx->pinUsed[b] = true;
+    }
+    if (e != cudaSuccess && rc == FHP_OK) rc = fail(ctx, FHP_ERR_CUDA, std::string("map upload: ") + cudaGetErrorString(e));
   }
-  return FHP_OK;
+  for (std::thread& t : helpers) t.join();
+  return rc;
 }
 
 int bind_layers(fhp_ctx* ctx);
