@@ -257,6 +257,25 @@ int fhp_check_centroid(fhp_ctx* ctx, const fhp_params* params, const double* poi
                        int8_t* case_out);
 int fhp_mean_height(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, int64_t n, float* z_out);
 int fhp_check_default(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, int64_t n, uint8_t* valid_out);
+/* Host-side geometry members (pure functions of the parameters; no device involved, same expressions as the kernel).
+ * fhp_initial_stance: initialize()'s stance RF,RH,LH,LF (FP.cpp:350-378) and setFirstGait (FP.cpp:2679-2699);
+ * 4 x (x,y,z) each.
+ * fhp_search_geometry: for the four current feet cur_xyz (RF,RH,LH,LF): getPolygonCenter (FP.cpp:2421-2463) ->
+ * center_xyz[3]; getFootholdSearchGridMap (FP.cpp:2166-2250) with getDefaultFootholdNext (:2411-2418) -> next_xy[4][2];
+ * getSearchPolygon (:2496-2517) -> polygon_xy[4][4][2] in the reference's vertex order.  adjusted_y = ajustedPose_[1]
+ * (0 at the first cycle, -0.007 per cycle after). */
+int fhp_initial_stance(const fhp_params* params, const fhp_query* query, double* initial_xyz, double* first_gait_xyz);
+int fhp_search_geometry(const fhp_params* params, const fhp_query* query, double adjusted_y, const double* cur_xyz,
+                        double* center_xyz, double* next_xy, double* polygon_xy);
+/* checkCandidateFoothold (FP.cpp:2085-2114): the SpiralIterator search alone (no default test, no height).  out: xy
+ * and cell of the first valid cell in spiral order when valid_out is 1, zeros / (-1,-1) otherwise. */
+int fhp_check_candidate(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, const double* rect_centres_xy,
+                        int64_t n, fhp_foothold* out, uint8_t* valid_out);
+/* checkCirclePolygonFoothold (FP.cpp:2117-2163) at arbitrary foot centres: 1 iff the foot disc visits at least one
+ * cell and every finite cell of it is >= candidateFootholdThreshold and inside the search rectangle around
+ * rect_centres_xy (getSearchPolygon, FP.cpp:2496-2517). */
+int fhp_check_circle_polygon(fhp_ctx* ctx, const fhp_params* params, const double* foot_centres_xy,
+                             const double* rect_centres_xy, int64_t n, uint8_t* valid_out);
 
 /* Kernel launch counter (for bench.py's "gpu_launches"): number of libfhp kernels launched on this ctx. */
 int64_t fhp_kernel_launches(const fhp_ctx* ctx);

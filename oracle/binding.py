@@ -116,6 +116,37 @@ def check_foothold(hmap, params, centres, rect_centres):
     return out, valid
 
 
+def check_candidate(hmap, params, centres, rect_centres):
+    d, ptrs, keep = hmap.desc()
+    c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+    r = np.ascontiguousarray(rect_centres, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros(len(c), dtype=_abi.FOOTHOLD_DTYPE)
+    valid = np.zeros(len(c), dtype=np.uint8)
+    rc = lib().oracle_check_candidate(C.byref(d), ptrs, C.byref(params), _p(c), _p(r), C.c_int64(len(c)), _p(out),
+                                      _p(valid))
+    assert rc == 0, rc
+    return out, valid
+
+
+def check_circle_polygon(hmap, params, foot_centres, rect_centres):
+    d, ptrs, keep = hmap.desc()
+    c = np.ascontiguousarray(foot_centres, dtype=np.float64).reshape(-1, 2)
+    r = np.ascontiguousarray(rect_centres, dtype=np.float64).reshape(-1, 2)
+    valid = np.zeros(len(c), dtype=np.uint8)
+    rc = lib().oracle_check_circle_polygon(C.byref(d), ptrs, C.byref(params), _p(c), _p(r), C.c_int64(len(c)), _p(valid))
+    assert rc == 0, rc
+    return valid
+
+
+def search_geometry(params, query_xyz, adjusted_y, cur_xyz):
+    q = _abi.make_queries([query_xyz])
+    cur = np.ascontiguousarray(cur_xyz, dtype=np.float64).reshape(4, 3)
+    c, n, p = np.zeros(2), np.zeros((4, 2)), np.zeros((4, 4, 2))
+    rc = lib().oracle_search_geometry(C.byref(params), _p(q), C.c_double(adjusted_y), _p(cur), _p(c), _p(n), _p(p))
+    assert rc == 0, rc
+    return c, n, p
+
+
 def check_centroid(hmap, params, points):
     d, ptrs, keep = hmap.desc()
     c = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)

@@ -264,6 +264,78 @@ int oracle_check_default(const fhp_map_desc* desc, const float* const* layers, c
   return FHP_OK;
 }
 
+// checkCandidateFoothold (FP.cpp:2085-2114): the spiral search alone.  out = chosen cell centre (xy; z = 0) when valid.
+int oracle_check_candidate(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params,
+                           const double* centres_xy, const double* rect_centres_xy, int64_t n, fhp_foothold* out,
+                           uint8_t* valid_out) {
+  gm::GridMap map = make_map(desc, layers);
+  if (!map.exists("traversability")) return FHP_ERR_MISSING_LAYER;
+  fhp_query q0{0, 0, 0, 0, 0};
+  ref::Planner pl = make_planner(*params, q0);
+  for (int64_t i = 0; i < n; ++i) {
+    gm::Vec2 c{centres_xy[2 * i], centres_xy[2 * i + 1]};
+    ref::Point rc;
+    rc.x = rect_centres_xy[2 * i];
+    rc.y = rect_centres_xy[2 * i + 1];
+    gm::Polygon poly = ref::Planner::getSearchPolygon(rc, pl.p.searchRadius);
+    ref::Foothold fh;
+    fh.kind = ref::KIND_CANDIDATE;
+    const bool ok = pl.checkCandidateFoothold(map, c, pl.p.footRadius, pl.p.searchRadius, poly, fh.point);
+    if (ok) ref::Planner::fillIndex(map, fh); else fh.row = fh.col = -1;
+    to_row(fh, out + i);
+    valid_out[i] = ok ? 1 : 0;
+  }
+  return FHP_OK;
+}
+
+// checkCirclePolygonFoothold (FP.cpp:2117-2163) at arbitrary foot centres against the rectangle around rect centres.
+int oracle_check_circle_polygon(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params,
+                                const double* foot_centres_xy, const double* rect_centres_xy, int64_t n,
+                                uint8_t* valid_out) {
+  gm::GridMap map = make_map(desc, layers);
+  if (!map.exists("traversability")) return FHP_ERR_MISSING_LAYER;
+  fhp_query q0{0, 0, 0, 0, 0};
+  ref::Planner pl = make_planner(*params, q0);
+  for (int64_t i = 0; i < n; ++i) {
+    ref::Point rc;
+    rc.x = rect_centres_xy[2 * i];
+    rc.y = rect_centres_xy[2 * i + 1];
+    gm::Polygon poly = ref::Planner::getSearchPolygon(rc, pl.p.searchRadius);
+    valid_out[i] = pl.checkCirclePolygonFoothold(map, gm::Vec2{foot_centres_xy[2 * i], foot_centres_xy[2 * i + 1]},
+                                                 pl.p.footRadius, poly) ? 1 : 0;
+  }
+  return FHP_OK;
+}
+
+// getPolygonCenter (FP.cpp:2421-2463), getDefaultFootholdNext via getFootholdSearchGridMap (:2166-2250) and
+// getSearchPolygon (:2496-2517) for one set of four current feet: out_center_xy[2], out_next_xy[4][2],
+// out_poly_xy[4][4][2] (vertex order of the reference).
+int oracle_search_geometry(const fhp_params* params, const fhp_query* q, double adjusted_y, const double* cur_xyz,
+                           double* out_center_xy, double* out_next_xy, double* out_poly_xy) {
+  ref::Planner pl = make_planner(*params, *q);
+  pl.ajustedPoseY = adjusted_y;
+  ref::Point cur[4], next[4];
+  for (int f = 0; f < 4; ++f) {
+    cur[f].x = cur_xyz[3 * f];
+    cur[f].y = cur_xyz[3 * f + 1];
+    cur[f].z = cur_xyz[3 * f + 2];
+  }
+  ref::Point c = pl.getPolygonCenter(cur[0], cur[1], cur[2], cur[3]);
+  out_center_xy[0] = c.x;
+  out_center_xy[1] = c.y;
+  gm::Polygon poly[4];
+  pl.getFootholdSearchGridMap(cur, next, poly);
+  for (int f = 0; f < 4; ++f) {
+    out_next_xy[2 * f] = next[f].x;
+    out_next_xy[2 * f + 1] = next[f].y;
+    for (int v = 0; v < 4; ++v) {
+      out_poly_xy[(f * 4 + v) * 2] = poly[f].vertices[v].x;
+      out_poly_xy[(f * 4 + v) * 2 + 1] = poly[f].vertices[v].y;
+    }
+  }
+  return FHP_OK;
+}
+
 // ---- grid_map_core probes (unit tests of the restatement itself) -------------------------------------------
 // Buffer indices visited by SpiralIterator(map, centre, radius), in order.  Returns the count (<= max_out).
 int64_t oracle_spiral_cells(const fhp_map_desc* desc, double cx, double cy, double radius, int32_t wrap_correct,

@@ -13,6 +13,10 @@
 //   checkDefaultFoothold(map, center, r)            checkDefaultFoothold(center)             FP.cpp:2039-2082
 //   checkFootholdUseCentroidMethod(map, p, out,..)  checkFootholdUseCentroidMethod(p, out)   FP.cpp:1605-1997
 //   getFootholdMeanHeight(map, center, r, h)        getFootholdMeanHeight(center)            FP.cpp:2520-2554
+//   checkCandidateFoothold(map, c, r, R, poly, out) checkCandidateFoothold(c, polyCenter, out)  FP.cpp:2085-2114
+//   checkCirclePolygonFoothold(map, c, r, poly)     checkCirclePolygonFoothold(c, polyCenter)   FP.cpp:2117-2163
+//   setFirstGait / getPolygonCenter / getDefaultFootholdNext / getSearchPolygon / getFootholdSearchGridMap
+//                                                   same names, host-side (fhp_initial_stance, fhp_search_geometry)
 // The map arguments disappear because the map is device-resident after gridmapCallback (the reference passes
 // copies of the same member map); radii/thresholds come from the rosparams as in the reference.
 #pragma once
@@ -286,6 +290,82 @@ class FootholdPlannerGpu {
     float z = 0;
     check(fhp_mean_height(ctx_, &params, c, 1, &z), "fhp_mean_height");
     return z;
+  }
+  // FP.cpp:2085-2114 — the spiral search alone; resultFoothold.xy is set on a hit only
+  bool checkCandidateFoothold(double cx, double cy, double poly_cx, double poly_cy, Point& footholdResult) {
+    const double c[2] = {cx, cy}, rc[2] = {poly_cx, poly_cy};
+    fhp_foothold out;
+    uint8_t ok = 0;
+    check(fhp_check_candidate(ctx_, &params, c, rc, 1, &out, &ok), "fhp_check_candidate");
+    if (ok) {
+      footholdResult.x = out.x;
+      footholdResult.y = out.y;
+    }
+    return ok != 0;
+  }
+  // FP.cpp:2117-2163
+  bool checkCirclePolygonFoothold(double cx, double cy, double poly_cx, double poly_cy) {
+    const double c[2] = {cx, cy}, rc[2] = {poly_cx, poly_cy};
+    uint8_t ok = 0;
+    check(fhp_check_circle_polygon(ctx_, &params, c, rc, 1, &ok), "fhp_check_circle_polygon");
+    return ok != 0;
+  }
+  // FP.cpp:2679-2699 on the stance of initialize() (FP.cpp:350-378): currentFootholds[f] = initial[f] - (stepLength/2, 0, 0)
+  bool setFirstGait(Point initialFootholds[4], Point currentFootholds[4]) {
+    fhp_query q;
+    q.x = initialPose_[0];
+    q.y = initialPose_[1];
+    q.z = initialPose_[2];
+    q.param_id = 0;
+    q.reserved = 0;
+    double a[12], b[12];
+    if (fhp_initial_stance(&params, &q, a, b) != FHP_OK) return false;
+    for (int f = 0; f < 4; ++f) {
+      initialFootholds[f].x = a[3 * f];
+      initialFootholds[f].y = a[3 * f + 1];
+      initialFootholds[f].z = a[3 * f + 2];
+      currentFootholds[f].x = b[3 * f];
+      currentFootholds[f].y = b[3 * f + 1];
+      currentFootholds[f].z = b[3 * f + 2];
+    }
+    return true;
+  }
+  // FP.cpp:2166-2250: next default footholds and search rectangles (4 vertices each, reference order) of the four
+  // current feet RF,RH,LH,LF; ajustedPoseY = ajustedPose_[1] of the cycle.  polygonCenter = getPolygonCenter (:2421-2463).
+  void getFootholdSearchGridMap(const Point currentFootholds[4], double ajustedPoseY, Point nextFootholds[4],
+                                Point searchPolygons[4][4], Point& polygonCenter) {
+    fhp_query q;
+    q.x = initialPose_[0];
+    q.y = initialPose_[1];
+    q.z = initialPose_[2];
+    q.param_id = 0;
+    q.reserved = 0;
+    double cur[12], c[3], nxt[8], poly[32];
+    for (int f = 0; f < 4; ++f) {
+      cur[3 * f] = currentFootholds[f].x;
+      cur[3 * f + 1] = currentFootholds[f].y;
+      cur[3 * f + 2] = currentFootholds[f].z;
+    }
+    check(fhp_search_geometry(&params, &q, ajustedPoseY, cur, c, nxt, poly), "fhp_search_geometry");
+    polygonCenter.x = c[0];
+    polygonCenter.y = c[1];
+    polygonCenter.z = c[2];
+    for (int f = 0; f < 4; ++f) {
+      nextFootholds[f].x = nxt[2 * f];
+      nextFootholds[f].y = nxt[2 * f + 1];
+      nextFootholds[f].z = 0.0;  // getDefaultFootholdNext leaves z at 0 (FP.cpp:2411-2418)
+      for (int v = 0; v < 4; ++v) {
+        searchPolygons[f][v].x = poly[8 * f + 2 * v];
+        searchPolygons[f][v].y = poly[8 * f + 2 * v + 1];
+        searchPolygons[f][v].z = 0.0;
+      }
+    }
+  }
+  Point getPolygonCenter(const Point& RF, const Point& RH, const Point& LH, const Point& LF) {
+    const Point cur[4] = {RF, RH, LH, LF};
+    Point next[4], poly[4][4], c;
+    getFootholdSearchGridMap(cur, 0.0, next, poly, c);
+    return c;
   }
   fhp_ctx* ctx() { return ctx_; }
 

@@ -1318,6 +1318,71 @@ int fhp_check_default(fhp_ctx* ctx, const fhp_params* params, const double* cent
   return run_task(ctx, 3, params, centres_xy, nullptr, n, nullptr, valid_out, nullptr, nullptr);
 }
 
+// Host-side geometry of the path (pure functions of the parameters, like the message assembly): the same expressions
+// the kernel evaluates, for callers of the reference's public geometry members.
+int fhp_initial_stance(const fhp_params* params, const fhp_query* query, double* initial_xyz, double* first_gait_xyz) {
+  if (!params || !query || !initial_xyz || !first_gait_xyz) return FHP_ERR_INVALID_ARG;
+  ParDev d;
+  derive_params(*params, d);
+  for (int f = 0; f < 4; ++f) {  // initialize() (FP.cpp:350-378), setFirstGait (FP.cpp:2679-2699)
+    initial_xyz[3 * f] = d.stancex[f] + query->x;
+    initial_xyz[3 * f + 1] = d.stancey[f] + query->y;
+    initial_xyz[3 * f + 2] = 0.0 + query->z;
+    first_gait_xyz[3 * f] = initial_xyz[3 * f] - d.halfStep;
+    first_gait_xyz[3 * f + 1] = initial_xyz[3 * f + 1];
+    first_gait_xyz[3 * f + 2] = initial_xyz[3 * f + 2];
+  }
+  return FHP_OK;
+}
+
+int fhp_search_geometry(const fhp_params* params, const fhp_query* query, double adjusted_y, const double* cur_xyz,
+                        double* center_xyz, double* next_xy, double* polygon_xy) {
+  if (!params || !query || !cur_xyz || !center_xyz || !next_xy || !polygon_xy) return FHP_ERR_INVALID_ARG;
+  ParDev d;
+  derive_params(*params, d);
+  // getPolygonCenter (FP.cpp:2421-2463): area-weighted centroid of the quad RF->RH->LH->LF by triangle fan
+  const double x1 = cur_xyz[0], y1 = cur_xyz[1];
+  double x2 = cur_xyz[3], y2 = cur_xyz[4];
+  double sum_x = 0, sum_y = 0, sum_s = 0;
+  for (int i = 2; i <= 3; ++i) {
+    const double x3 = cur_xyz[3 * i], y3 = cur_xyz[3 * i + 1];
+    const double s = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) / 2.0;
+    sum_x += (x1 + x2 + x3) * s;
+    sum_y += (y1 + y2 + y3) * s;
+    sum_s += s;
+    x2 = x3;
+    y2 = y3;
+  }
+  center_xyz[0] = sum_x / sum_s / 3.0;
+  center_xyz[1] = sum_y / sum_s / 3.0;
+  center_xyz[2] = (cur_xyz[2] + cur_xyz[5] + cur_xyz[8] + cur_xyz[11]) / 4.0;
+  // getFootholdSearchGridMap (FP.cpp:2166-2250): next centre, getDefaultFootholdNext (:2411-2418), getSearchPolygon
+  const double ncx = center_xyz[0] + d.stepLength;  // :2199
+  const double ncy = query->y + adjusted_y;         // :2201
+  for (int f = 0; f < 4; ++f) {
+    const double nx = ncx + d.biasx[f], ny = ncy + d.biasy[f];
+    next_xy[2 * f] = nx;
+    next_xy[2 * f + 1] = ny;
+    double* v = polygon_xy + 8 * f;  // :2496-2517, vertex order leftup, rightup, rightdown, leftdown
+    v[0] = nx + d.R;  v[1] = ny + 0.5 * d.R;
+    v[2] = nx + d.R;  v[3] = ny - 0.5 * d.R;
+    v[4] = nx - d.R;  v[5] = ny - 0.5 * d.R;
+    v[6] = nx - d.R;  v[7] = ny + 0.5 * d.R;
+  }
+  return FHP_OK;
+}
+
+int fhp_check_candidate(fhp_ctx* ctx, const fhp_params* params, const double* centres_xy, const double* rect_centres_xy,
+                        int64_t n, fhp_foothold* out, uint8_t* valid_out) {
+  if (n > 0 && (!rect_centres_xy || !out || !valid_out)) return fail(ctx, FHP_ERR_INVALID_ARG, "null output");
+  return run_task(ctx, 4, params, centres_xy, rect_centres_xy, n, out, valid_out, nullptr, nullptr);
+}
+int fhp_check_circle_polygon(fhp_ctx* ctx, const fhp_params* params, const double* foot_centres_xy,
+                             const double* rect_centres_xy, int64_t n, uint8_t* valid_out) {
+  if (n > 0 && (!rect_centres_xy || !valid_out)) return fail(ctx, FHP_ERR_INVALID_ARG, "null output");
+  return run_task(ctx, 5, params, foot_centres_xy, rect_centres_xy, n, nullptr, valid_out, nullptr, nullptr);
+}
+
 int64_t fhp_kernel_launches(const fhp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---- NCCL map replication (symbols resolved at run time from the NCCL already in the process) ------------------

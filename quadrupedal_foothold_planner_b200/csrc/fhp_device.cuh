@@ -925,6 +925,29 @@ __device__ __forceinline__ bool candidate_on_planes(const GeoDev& G, const Plane
   return good;
 }
 
+// checkCirclePolygonFoothold (FP.cpp:2117-2163) at an ARBITRARY foot centre, straight from global memory (the public
+// member; the plan's own candidates sit on cell centres and use the planes): walk CircleIterator's window, every finite
+// member cell must be >= candidateFootholdThreshold and inside the box; a disc without member cells is invalid.
+__device__ __noinline__ bool circle_polygon_direct(const MapDev& M, const ParDev& P, double cx, double cy, double xlo,
+                                                   double xhi, double ylo, double yhi) {
+  const DiscWin dw = disc_window_generic(M, cx, cy, P.r);
+  bool validation = false;  // FP.cpp:2122: stays false when the iterator visits nothing
+  for (int u0 = dw.tl0; u0 <= dw.br0; ++u0) {
+    const double X = pos_axis(M.fcx, M.res, u0), dx = X - cx;
+    const double dx2 = dx * dx;
+    for (int u1 = dw.tl1; u1 <= dw.br1; ++u1) {
+      const double Y = pos_axis(M.fcy, M.res, u1), dy = Y - cy;
+      if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
+      validation = true;  // :2159 — every visited cell, valid or not, ends its iteration with validation = true
+      const float v = load_cell(M, M.trav, u0, u1);
+      if (!(fabsf(v) < __int_as_float(0x7f800000))) continue;  // :2132 invalid cells are not tested
+      const bool inside = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
+      if (v < P.thrC || !inside) return false;  // :2138-2143 (break with validation = false)
+    }
+  }
+  return validation;
+}
+
 // One candidate evaluated straight from global memory (faithful-mode candidates that wrap to the far side of the
 // circular buffer): checkCirclePolygonFoothold (FP.cpp:2117-2163).
 __device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, float thrC, int q0, int q1, double xlo,

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
 }
 
 // ---- fine-grained primitives: one lane per task -------------------------------------------------------------------
-// mode 0: checkFoothold, 1: checkFootholdUseCentroidMethod, 2: getFootholdMeanHeight, 3: checkDefaultFoothold
+// mode 0: checkFoothold, 1: checkFootholdUseCentroidMethod, 2: getFootholdMeanHeight, 3: checkDefaultFoothold,
+//      4: checkCandidateFoothold (the spiral search alone), 5: checkCirclePolygonFoothold
 template <int MODE>
 __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constant__ TaskArgs A,
                                                             const __grid_constant__ GeoDev G) {
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   if (active) {
     px = A.centres[2 * i];
     py = A.centres[2 * i + 1];
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 4 || MODE == 5) {
       rx = A.rects[2 * i];
       ry = A.rects[2 * i + 1];
     }
@@ -295,16 +296,23 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     if (active) A.z[i] = mean_height(M, G, P, px, py);
     return;
   }
+  if (MODE == 5) {
+    if (active) {
+      const Box b = search_box(P, rx, ry);
+      A.valid[i] = circle_polygon_direct(M, P, px, py, b.xlo, b.xhi, b.ylo, b.yhi) ? 1 : 0;
+    }
+    return;
+  }
   const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
   const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
   Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
-  if (MODE == 0 || MODE == 3) {
+  if (MODE == 0 || MODE == 3 || MODE == 4) {
     DiscWin dw = {0, 0, -1, -1, 0ull, 0};
     if (active) dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
     NominalOut no;
-    const bool okDef = active && default_eval(M, G, P, pl, w0, w1, px, py, dw, err);
-    if (MODE == 0)
+    const bool okDef = (MODE != 4) && active && default_eval(M, G, P, pl, w0, w1, px, py, dw, err);
+    if (MODE == 0 || MODE == 4)
       no = nominal_eval<false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     else
       no = nominal_eval<true, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
@@ -313,6 +321,12 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
         double z = 0.0;
         if (no.ok) z = static_cast<double>(mean_height(M, P, px, py, dw));
         write_row(A.out + i, no.x, no.y, z, no.row, no.col, 0, 0, no.kind);
+      }
+      if (MODE == 4) {  // checkCandidateFoothold sets only the xy of a hit (FP.cpp:2105-2107)
+        if (no.ok)
+          write_row(A.out + i, no.x, no.y, 0.0, no.row, no.col, 0, 0, FHP_KIND_CANDIDATE);
+        else
+          write_row(A.out + i, 0.0, 0.0, 0.0, -1, -1, 0, 0, FHP_KIND_CANDIDATE);
       }
       A.valid[i] = no.ok ? 1 : 0;
     }
@@ -541,7 +555,9 @@ cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream
       case 0: e = cudaFuncSetAttribute(task_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
       case 1: e = cudaFuncSetAttribute(task_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
       case 2: e = cudaFuncSetAttribute(task_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
-      default: e = cudaFuncSetAttribute(task_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+      case 3: e = cudaFuncSetAttribute(task_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+      case 4: e = cudaFuncSetAttribute(task_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
+      default: e = cudaFuncSetAttribute(task_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)); break;
     }
     if (e != cudaSuccess) return e;
   }
@@ -549,7 +565,9 @@ cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream
     case 0: task_kernel<0><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
     case 1: task_kernel<1><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
     case 2: task_kernel<2><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
-    default: task_kernel<3><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+    case 3: task_kernel<3><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+    case 4: task_kernel<4><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
+    default: task_kernel<5><<<nb, kPlanThreads, shm, stream>>>(A, G); break;
   }
   return cudaGetLastError();
 }

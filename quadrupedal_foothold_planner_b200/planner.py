@@ -75,6 +75,10 @@ def load_lib():
     L.fhp_check_centroid.argtypes = [vp, vp, vp, i64, vp, vp]
     L.fhp_mean_height.argtypes = [vp, vp, vp, i64, vp]
     L.fhp_check_default.argtypes = [vp, vp, vp, i64, vp]
+    L.fhp_check_candidate.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.fhp_check_circle_polygon.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.fhp_initial_stance.argtypes = [vp, vp, vp, vp]
+    L.fhp_search_geometry.argtypes = [vp, vp, C.c_double, vp, vp, vp, vp]
     L.fhp_kernel_launches.argtypes = [vp]
     L.fhp_kernel_launches.restype = i64
     L.fhp_broadcast_map.argtypes = [vp, C.POINTER(MapDesc), vp, C.c_int, C.c_int]
@@ -272,11 +276,54 @@ class Fhp:
         self._check(self.L.fhp_mean_height(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), len(c), _ptr(z)))
         return z
 
+    def check_candidate(self, params: Params, centres, rect_centres):
+        """checkCandidateFoothold (FP.cpp:2085-2114): the spiral search alone -> (rows, valid)."""
+        c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+        r = np.ascontiguousarray(rect_centres, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros(len(c), dtype=FOOTHOLD_DTYPE)
+        valid = np.zeros(len(c), dtype=np.uint8)
+        self._check(self.L.fhp_check_candidate(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), _ptr(r), len(c),
+                                               _ptr(out), _ptr(valid)))
+        return out, valid
+
+    def check_circle_polygon(self, params: Params, foot_centres, rect_centres):
+        """checkCirclePolygonFoothold (FP.cpp:2117-2163) at arbitrary foot centres -> valid."""
+        c = np.ascontiguousarray(foot_centres, dtype=np.float64).reshape(-1, 2)
+        r = np.ascontiguousarray(rect_centres, dtype=np.float64).reshape(-1, 2)
+        valid = np.zeros(len(c), dtype=np.uint8)
+        self._check(self.L.fhp_check_circle_polygon(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), _ptr(r),
+                                                    len(c), _ptr(valid)))
+        return valid
+
     def check_default(self, params: Params, centres):
         c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
         v = np.zeros(len(c), dtype=np.uint8)
         self._check(self.L.fhp_check_default(self.h, C.cast(C.pointer(params), C.c_void_p), _ptr(c), len(c), _ptr(v)))
         return v
+
+
+def initial_stance(params: Params, query_xyz=(0.0, 0.0, 0.0)):
+    """fhp_initial_stance -> (initial [4,3], first_gait [4,3]); no device needed."""
+    L = load_lib()
+    q = make_queries([query_xyz])
+    a, b = np.zeros((4, 3)), np.zeros((4, 3))
+    rc = L.fhp_initial_stance(C.cast(C.pointer(params), C.c_void_p), _ptr(q), _ptr(a), _ptr(b))
+    if rc != 0:
+        raise FhpError(rc, "fhp_initial_stance")
+    return a, b
+
+
+def search_geometry(params: Params, query_xyz, adjusted_y: float, cur_xyz):
+    """fhp_search_geometry -> (center [3], next [4,2], polygons [4,4,2]); no device needed."""
+    L = load_lib()
+    q = make_queries([query_xyz])
+    cur = np.ascontiguousarray(cur_xyz, dtype=np.float64).reshape(4, 3)
+    c, n, p = np.zeros(3), np.zeros((4, 2)), np.zeros((4, 4, 2))
+    rc = L.fhp_search_geometry(C.cast(C.pointer(params), C.c_void_p), _ptr(q), float(adjusted_y), _ptr(cur), _ptr(c),
+                               _ptr(n), _ptr(p))
+    if rc != 0:
+        raise FhpError(rc, "fhp_search_geometry")
+    return c, n, p
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -417,3 +417,35 @@ def test_c5_sized_map(fhp, oracle):
     assert compare_plans(got, exp, "C5-sized map") <= XYZ_TOL
     assert (got[2]["n_rows"] > 4).sum() > 30
     fhp.set_map(synth.flat_map(64, 64, 0.02))  # release the 2 GB of layers for the tests that follow
+
+
+@pytest.mark.parametrize("res", [0.02, 0.01])
+def test_candidate_and_circle_polygon_members(fhp, oracle, res):
+    """The two remaining public search members: checkCandidateFoothold (spiral alone) and
+    checkCirclePolygonFoothold at arbitrary foot centres, including border, NaN-only and out-of-map discs."""
+    n = 400 if res == 0.02 else 700
+    m = synth.rough_map(n, n, res, seed=97, start=(n // 3, n - 7))
+    t = m.layers["traversability"].copy()
+    t[40:60, 40:70] = np.nan  # a NaN patch: discs that visit only invalid cells are VALID (FP.cpp:2159)
+    m.set_layer("traversability", t)
+    fhp.set_map(m)
+    p = _abi.yaml_params()
+    half = n * res / 2
+    rng = np.random.default_rng(11)
+    c = rng.uniform(-half - 0.1, half + 0.1, size=(3000, 2))
+    c[:200] = m.pos + np.stack([half - res * rng.uniform(40, 60, 200), half - res * rng.uniform(40, 70, 200)], axis=1)
+    r = c + rng.normal(0, 0.04, size=c.shape)
+    got, gv = fhp.check_candidate(p, c, r)
+    exp, ev = oracle.check_candidate(m, p, c, r)
+    assert np.array_equal(gv, ev) and gv.sum() > 100 and (gv == 0).sum() > 20
+    ok = gv == 1
+    for f in ("row", "col"):
+        assert np.array_equal(got[f][ok], exp[f][ok])
+    for f in ("x", "y"):
+        assert np.max(np.abs(got[f][ok] - exp[f][ok])) <= XYZ_TOL
+    gp = fhp.check_circle_polygon(p, c, r)
+    ep = oracle.check_circle_polygon(m, p, c, r)
+    assert np.array_equal(gp, ep) and gp.sum() > 50 and (gp == 0).sum() > 20
+    # cell-centred candidates: the member agrees with what the spiral search accepted
+    cc = np.stack([got["x"][ok], got["y"][ok]], axis=1)
+    assert np.all(fhp.check_circle_polygon(p, cc, r[ok]) == 1)

@@ -56,3 +56,24 @@ def test_shard_bounds_partition():
         spans = [dist.shard_bounds(n, w, r) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(lo <= hi for lo, hi in spans)
+
+
+def test_host_geometry_members_match_the_oracle(oracle):
+    """fhp_initial_stance / fhp_search_geometry (initialize + setFirstGait, getPolygonCenter, getFootholdSearchGridMap,
+    getDefaultFootholdNext, getSearchPolygon) are host-side pure functions of libfhp: bit-identical to the oracle."""
+    import numpy as np
+    from quadrupedal_foothold_planner_b200 import _abi, planner
+    rng = np.random.default_rng(3)
+    for p in (_abi.yaml_params(), _abi.yaml_params(rf_first=1, step_length=0.23, skew=0.055),
+              _abi.yaml_params(gait=_abi.FHP_GAIT_WALK, search_radius=0.13)):
+        pose = (float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)), float(rng.uniform(-1, 1)))
+        init, first = planner.initial_stance(p, pose)
+        o_init, o_bias, o_first = oracle.initial_geometry(p, pose)
+        assert np.array_equal(init[:, :2], o_init) and np.array_equal(first[:, :2], o_first)
+        assert np.all(init[:, 2] == pose[2]) and np.all(first[:, 2] == pose[2])
+        for adj in (0.0, -0.007, -0.049):
+            cur = first + rng.normal(0, 0.03, size=(4, 3))
+            c, nxt, poly = planner.search_geometry(p, pose, adj, cur)
+            oc, onxt, opoly = oracle.search_geometry(p, pose, adj, cur)
+            assert np.array_equal(c[:2], oc) and np.array_equal(nxt, onxt) and np.array_equal(poly, opoly)
+            assert c[2] == (cur[0, 2] + cur[1, 2] + cur[2, 2] + cur[3, 2]) / 4.0
