@@ -72,5 +72,14 @@ int main(int argc, char** argv) {
     const foothold_planner::Foothold& h = resp.footholds.footholds[i];
     printf("%.17g %.17g %.17g %d %d\n", h.point.x, h.point.y, h.point.z, h.foot_id, h.gait_cycle_id);
   }
+  // the fine-grained public members, once each (values checked by the test against the oracle)
+  foothold_planner::Point init[4], cur[4], next[4], poly[4][4], centre, cand;
+  if (!planner.setFirstGait(init, cur)) return 7;
+  planner.getFootholdSearchGridMap(cur, -0.007, next, poly, centre);
+  const bool candOk = planner.checkCandidateFoothold(next[0].x, next[0].y, next[0].x + 0.01, next[0].y - 0.02, cand);
+  const bool cpOk = planner.checkCirclePolygonFoothold(next[1].x, next[1].y, next[1].x, next[1].y);
+  printf("members %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %d %.17g %.17g %d\n", cur[0].x, cur[3].y, centre.x, centre.y,
+         next[2].x, next[2].y, poly[3][0].x, poly[3][2].y, candOk ? 1 : 0, candOk ? cand.x : 0.0, candOk ? cand.y : 0.0,
+         cpOk ? 1 : 0);
   return 0;
 }

@@ -39,7 +39,18 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle):
         nom, _, st = oracle.plan(m, _abi.yaml_params(), _abi.make_queries([pose]), 9)
         s, gc, gs, n = (int(v) for v in out[0].split())
         assert (s, gc, gs, n) == (st[0]["success"], 9, st[0]["gait_cycles_succeed"], st[0]["n_rows"])
-        for line, row in zip(out[1:], nom[0][:n]):
+        mem = out[1 + n].split()
+        assert mem[0] == "members"
+        p0 = _abi.yaml_params()
+        o_init, _, o_first = oracle.initial_geometry(p0, pose)
+        cur = np.concatenate([o_first, np.full((4, 1), pose[2])], axis=1)
+        oc, onxt, opoly = oracle.search_geometry(p0, pose, -0.007, cur)
+        vals = [float(v) for v in mem[1:9]]
+        assert vals == [o_first[0, 0], o_first[3, 1], oc[0], oc[1], onxt[2, 0], onxt[2, 1], opoly[3, 0, 0], opoly[3, 2, 1]]
+        ec, ev = oracle.check_candidate(m, p0, [onxt[0]], [onxt[0] + np.array([0.01, -0.02])])
+        assert int(mem[9]) == ev[0] and (ev[0] == 0 or (float(mem[10]), float(mem[11])) == (ec[0]["x"], ec[0]["y"]))
+        assert int(mem[12]) == oracle.check_circle_polygon(m, p0, [onxt[1]], [onxt[1]])[0]
+        for line, row in zip(out[1:1 + n], nom[0][:n]):
             x, y, z, foot, cyc = line.split()
             assert abs(float(x) - row["x"]) <= 1e-5 and abs(float(y) - row["y"]) <= 1e-5 and abs(float(z) - row["z"]) <= 1e-5
             assert (int(foot), int(cyc)) == (row["foot_id"], row["gait_cycle_id"])
