@@ -439,3 +439,24 @@ class FootholdPlanner:
     # FP.cpp:2520-2554
     def getFootholdMeanHeight(self, center) -> float:
         return float(self.fhp.mean_height(self.params, [center])[0])
+
+    # FP.cpp:2085-2114 -> (valid, (x, y) of the first valid cell in spiral order or None)
+    def checkCandidateFoothold(self, center, polygon_center):
+        out, valid = self.fhp.check_candidate(self.params, [center], [polygon_center])
+        return bool(valid[0]), ((float(out[0]["x"]), float(out[0]["y"])) if valid[0] else None)
+
+    # FP.cpp:2117-2163
+    def checkCirclePolygonFoothold(self, center, polygon_center) -> bool:
+        return bool(self.fhp.check_circle_polygon(self.params, [center], [polygon_center])[0])
+
+    # FP.cpp:350-378 + :2679-2699 -> (initialFootholds [4,3], currentFootholds [4,3]), RF,RH,LH,LF
+    def setFirstGait(self):
+        return initial_stance(self.params, self.initialPose_)
+
+    # FP.cpp:2166-2250 -> (polygonCenter [3], nextFootholds [4,2], searchPolygons [4,4,2])
+    def getFootholdSearchGridMap(self, currentFootholds, ajustedPoseY: float = 0.0):
+        return search_geometry(self.params, self.initialPose_, ajustedPoseY, currentFootholds)
+
+    # FP.cpp:2421-2463
+    def getPolygonCenter(self, RF, RH, LH, LF):
+        return search_geometry(self.params, self.initialPose_, 0.0, [RF, RH, LH, LF])[0]
