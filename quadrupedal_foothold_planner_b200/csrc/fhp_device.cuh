@@ -465,36 +465,25 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
     const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
     for (int k = 0; k < G.nIter; ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
   }
-  if (fastMask) {
-    const int org = (bb0 >> 5) * M.cols;          // entry index of (row word, column 0); < 2^27
-    const int b1s = bb1 | ((bb0 & 31) << 26);     // first buffer column | row shift (cols < 2^26)
-    const int c = lane & 7, grp = lane >> 3;      // 8 lanes per window, 4 windows per pass
-    for (int pass = 0; pass < 8; ++pass) {
-      if (((fastMask >> (pass * 4)) & 0xfu) == 0u) continue;  // warp-uniform
-      const int j = pass * 4 + grp;
-      const int jorg = __shfl_sync(kFull, org, j), jbs = __shfl_sync(kFull, b1s, j);
-      const bool jf = (fastMask >> j) & 1u;
-      const int s = static_cast<unsigned>(jbs) >> 26;
-      const int jb1 = jbs & 0x3ffffff;
-      const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
-      for (int ca = c; ca < G.WIN; ca += 16) {  // two columns per lane and iteration: two independent loads in flight
-        const int cb = ca + 8;
-        const bool fa = jf, fb = jf && cb < G.WIN;
-        int colA = jb1 + ca, colB = jb1 + cb;
-        if (colA >= M.cols) colA -= M.cols;
-        if (colB >= M.cols) colB -= M.cols;
-        // (lanes without a column load entry 0: valid memory, result unused — cheaper than predicated zero-fills)
-        const uint4 ea = __ldg(mask + (fa ? jorg + colA : 0));
-        const uint4 eb = __ldg(mask + (fb ? jorg + colB : 0));
-        if (fa) {
-          const uint32_t e0 = __funnelshift_r(ea.x, ea.y, s), e1 = __funnelshift_r(ea.z, ea.w, s);
-          sts_v4(dst + static_cast<uint32_t>(ca) * 16u, e1, e0 & e1, e0 | e1, 0u);
-        }
-        if (fb) {
-          const uint32_t e0 = __funnelshift_r(eb.x, eb.y, s), e1 = __funnelshift_r(eb.z, eb.w, s);
-          sts_v4(dst + static_cast<uint32_t>(cb) * 16u, e1, e0 & e1, e0 | e1, 0u);
-        }
+  if (fast) {  // every lane stages ITS OWN window: WIN independent 16-byte loads, no cross-lane traffic
+    const uint4* src = mask + (bb0 >> 5) * M.cols;
+    const int s = bb0 & 31;
+    const uint32_t dst = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
+    int col = bb1;
+    for (int c = 0; c < G.WIN; c += 4) {
+      uint4 e[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        e[i] = __ldg(src + col);  // (columns past WIN-1 read the next entries of the row word: valid memory, unused)
+        col += 1;
+        if (col >= M.cols) col -= M.cols;
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c + i < G.WIN) {
+          const uint32_t e0 = __funnelshift_r(e[i].x, e[i].y, s), e1 = __funnelshift_r(e[i].z, e[i].w, s);
+          sts_v4(dst + static_cast<uint32_t>(c + i) * 16u, e1, e0 & e1, e0 | e1, 0u);
+        }
     }
   }
   if (slowMask) stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
