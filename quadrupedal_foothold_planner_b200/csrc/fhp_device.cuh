@@ -875,12 +875,19 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
 // over a = 0..n-1: first_below returns the first a where it holds (n if none), found from a reciprocal estimate and
 // verified with the exact predicate on both sides (any estimate gives the right answer; a good one costs two tests).
 __device__ __forceinline__ int first_below(double fc, double res, double rinv, int org, int n, double bound) {
-  double t = (fc - bound) * rinv - static_cast<double>(org);  // pos(org+a) < bound  <=>  a > t (up to rounding)
-  t = fmin(fmax(t, -1.0), static_cast<double>(n));             // NaN -> -1
-  int a = static_cast<int>(t) + 1;
+  // pos(org+a) < bound  <=>  a > t with t = (fc - bound)/res - org.  The estimate below and the exact pos() each
+  // carry errors of ~1e-12 cells (|indices| < 2^30 is far from reached: maps have < 2^16 cells per axis), so when
+  // t is farther than 1e-6 from an integer both orderings agree and the first integer above t IS the answer; only in
+  // that band (and for NaN bounds) the exact predicate decides, walking from the estimate.
+  double t = (fc - bound) * rinv - static_cast<double>(org);
+  const bool certain = fabs(t - rint(t)) > 1e-6 && fabs(t) < 1.0e6;
+  t = fmin(fmax(t, -1.0), static_cast<double>(n));  // NaN -> -1
+  int a = static_cast<int>(floor(t)) + 1;
   a = max(0, min(a, n));
-  while (a > 0 && pos_axis(fc, res, org + a - 1) < bound) --a;
-  while (a < n && !(pos_axis(fc, res, org + a) < bound)) ++a;
+  if (!certain) {
+    while (a > 0 && pos_axis(fc, res, org + a - 1) < bound) --a;
+    while (a < n && !(pos_axis(fc, res, org + a) < bound)) ++a;
+  }
   return a;
 }
 __device__ __forceinline__ uint32_t bits_between(int lo, int hi) {  // bits lo..hi-1 (0 <= lo, hi <= 32)
