@@ -449,3 +449,42 @@ def test_candidate_and_circle_polygon_members(fhp, oracle, res):
     # cell-centred candidates: the member agrees with what the spiral search accepted
     cc = np.stack([got["x"][ok], got["y"][ok]], axis=1)
     assert np.all(fhp.check_circle_polygon(p, cc, r[ok]) == 1)
+
+
+def test_search_rectangle_edges_on_cell_centres(fhp, oracle):
+    """Rectangle edges that coincide EXACTLY with cell-centre coordinates (the half-open box: low edge inside, high
+    edge outside) — the guard band of the interval estimate must hand these to the exact predicate."""
+    m = synth.rough_map(400, 400, 0.02, seed=101, start=(0, 0))
+    t = np.clip(m.layers["traversability"] + 0.3, 0, 1).astype(np.float32)  # many candidates accepted
+    t[::3, ::2] = 0.75                                                       # default test fails often -> spiral runs
+    m.set_layer("traversability", t)
+    fhp.set_map(m)
+    p = _abi.yaml_params()
+    R = float(np.float32(0.1))
+    half = 400 * 0.02 / 2
+    fc = m.pos[0] + (half - 0.5 * 0.02)  # mapPosition + (0.5*length - 0.5*res)
+    rects, centres = [], []
+    for u in range(60, 340):
+        X = fc + 0.02 * float(-u)
+        for edge in (+R, -R, +0.5 * R, -0.5 * R):
+            r = X - edge
+            if r + edge == X:  # the edge lands exactly on the cell-centre coordinate
+                for v in (100, 201, 333):
+                    Y = fc + 0.02 * float(-v)
+                    if abs(edge) == R:
+                        rects.append((r, Y + 0.003))
+                        centres.append((r + 0.013, Y - 0.004))
+                    else:
+                        rects.append((Y + 0.003, r))
+                        centres.append((Y - 0.004, r + 0.007))
+    rects, centres = np.array(rects), np.array(centres)
+    assert len(rects) > 300
+    got, gv = fhp.check_candidate(p, centres, rects)
+    exp, ev = oracle.check_candidate(m, p, centres, rects)
+    assert np.array_equal(gv, ev) and gv.sum() > 100
+    ok = gv == 1
+    assert np.array_equal(got["row"][ok], exp["row"][ok]) and np.array_equal(got["col"][ok], exp["col"][ok])
+    assert np.array_equal(fhp.check_circle_polygon(p, centres, rects), oracle.check_circle_polygon(m, p, centres, rects))
+    g2, v2 = fhp.check_foothold(p, centres, rects)
+    e2, w2 = oracle.check_foothold(m, p, centres, rects)
+    assert np.array_equal(v2, w2) and np.array_equal(g2["row"], e2["row"]) and np.array_equal(g2["kind"], e2["kind"])
