@@ -121,6 +121,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -1153,19 +1158,20 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
       // entry for the cooperative scan) and, for a single-cell foot stencil, settles the two most common outcomes
       // itself: no acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
       const int sh = (uc0 - w0) - G.HW;
-      uint32_t anyOk = 0;
+      uint32_t anyOk = 0, okCentre = 0;
       for (int b = 0; b < G.WIN; ++b) {
-        const uint32_t F = pl.col(PL_F, b), C = pl.col(PL_C, b);
+        const uint4 e = lds_v4(mine + static_cast<uint32_t>(b) * 16u);  // {D, C, F, pad} of column b (pack = 1 layout)
         const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
-        const uint32_t bad = F & (C | ~box);
+        const uint32_t bad = e.z & (e.y | ~box);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(b * 4 + 3) * 4u), "r"(bad) : "memory");
         const uint32_t okb = ((colsIn >> b) & 1u) ? ((G.candRows[b] << sh) & ~bad & rowsIn) : 0u;
         anyOk |= okb;
-        if (b == G.HW && G.lastTwoStart > 0 && ((okb >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
-          found = true;
-          fq0 = uc0;
-          fq1 = uc1;
-        }
+        if (b == G.HW) okCentre = okb;
+      }
+      if (G.lastTwoStart > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
+        found = true;
+        fq0 = uc0;
+        fq1 = uc1;
       }
       if (G.nSten == 1 && (found || anyOk == 0u)) pend = false;
       if (G.nSten > 1) found = false;  // the shortcuts need the dilated masks
