@@ -374,6 +374,7 @@ def test_device_resident_plan_equals_host_plan(fhp, nq):
     d_cen = torch.zeros(nq * R * 40, dtype=torch.uint8, device="cuda")
     d_st = torch.zeros(nq * 8, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.Stream()
+    torch.cuda.synchronize()  # the uploads / fills above ran on torch's default stream; `stream` does not wait for it
     parr, npar = fhp._params_array(p)
     fhp.plan_device(parr, npar, d_q, nq, 10, d_nom, d_cen, d_st, stream=stream.cuda_stream)
     stream.synchronize()
