@@ -163,6 +163,10 @@ enum { PL_D = 0, PL_C = 1, PL_F = 2 };
 // Bits of rows/columns beyond WIN then hold real neighbouring cells, which no consumer ever reads.
 // Windows touching the map border or the seam take the generic per-cell path.
 constexpr int kStageChunk = 8;
+#ifndef FHP_STAGE_BATCH
+#define FHP_STAGE_BATCH 4
+#endif
+constexpr int kStageBatch = FHP_STAGE_BATCH;  // class-plane entries a lane has in flight while staging its window
 
 __device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint32_t dst, int lane, int k0, const float (&v)[kStageChunk],
                                                     float tD, float tC) {
@@ -475,16 +479,16 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
     const int s = bb0 & 31;
     const uint32_t dst = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
     int col = bb1;
-    for (int c = 0; c < G.WIN; c += 4) {
-      uint4 e[4];
+    for (int c = 0; c < G.WIN; c += kStageBatch) {
+      uint4 e[kStageBatch];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < kStageBatch; ++i) {
         e[i] = __ldg(src + col);  // (columns past WIN-1 read the next entries of the row word: valid memory, unused)
         col += 1;
         if (col >= M.cols) col -= M.cols;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kStageBatch; ++i)
         if (c + i < G.WIN) {
           const uint32_t e0 = __funnelshift_r(e[i].x, e[i].y, s), e1 = __funnelshift_r(e[i].z, e[i].w, s);
           sts_v4(dst + static_cast<uint32_t>(c + i) * 16u, e1, e0 & e1, e0 | e1, 0u);
