@@ -489,3 +489,18 @@ def test_search_rectangle_edges_on_cell_centres(fhp, oracle):
     g2, v2 = fhp.check_foothold(p, centres, rects)
     e2, w2 = oracle.check_foothold(m, p, centres, rects)
     assert np.array_equal(v2, w2) and np.array_equal(g2["row"], e2["row"]) and np.array_equal(g2["kind"], e2["kind"])
+
+
+@pytest.mark.parametrize("shape", [(8, 9, 0.02), (16, 24, 0.02), (33, 31, 0.02), (40, 64, 0.01), (5, 200, 0.02), (200, 7, 0.02)])
+def test_maps_smaller_than_a_window(fhp, oracle, shape):
+    """Maps narrower than the staged window / a 32-row word, with a wrapped start index and poses in and around them."""
+    r, c, res = shape
+    rng = np.random.default_rng(r * c)
+    t = rng.random((r, c), dtype=np.float32) ** 0.2
+    t[rng.random((r, c)) < 0.05] = np.nan
+    e = rng.random((r, c), dtype=np.float32)
+    m = _abi.HostMap(r, c, res, pos=(0.3, -0.2), start=(r // 2, c - 1), layers={"traversability": t, "elevation": e})
+    hx, hy = r * res / 2, c * res / 2
+    q = synth.uniform_queries(64, (0.3 - hx - 0.3, 0.3 + hx + 0.1), (-0.2 - hy - 0.2, -0.2 + hy + 0.2), seed=r + c)
+    got, exp = _run_both(fhp, oracle, m, _abi.yaml_params(), q, 5)
+    assert compare_plans(got, exp, f"tiny map {shape}") <= XYZ_TOL
