@@ -91,6 +91,10 @@ def make_workload(name: str, rank: int, with_map: bool = True):
             cycles = 16
         return m, q, cycles, [_abi.yaml_params()], ("C3: trot, 65536 queries x 16 cycles per GPU, 4000x4000 @0.02 m "
                                                     "rough map, start index (1234,2777)")
+    if name == "c5":
+        m, q, cycles = synth.config_c5(seed_q=7 + 1000 * rank, with_map=with_map)
+        return m, q, cycles, [_abi.yaml_params()], ("C5: trot, 262144 queries x 32 cycles per GPU, 16000x16000 @0.01 m "
+                                                    "rough map, 3 layers (3.07 GB), start index (4321,12345)")
     if name == "c2":
         m, q, cycles = synth.config_c2()
         return m, q, cycles, [_abi.yaml_params(gait=_abi.FHP_GAIT_WALK)], \
@@ -262,7 +266,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1", "c5"])
     ap.add_argument("--ref-sample", type=int, default=16384, help="queries per step of the CPU arm")
     ap.add_argument("--cpu-sample", type=int, default=65536, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,10 +299,11 @@ def main():
 
     # ---- workload: rank 0 builds the map, NCCL replicates it; every rank owns its own query shard
     t_gen = time.perf_counter()
-    hmap, queries, cycles, params, desc = make_workload(args.workload, rank, with_map=(rank == 0 or args.workload != "c3"))
+    hmap, queries, cycles, params, desc = make_workload(args.workload, rank,
+                                                        with_map=(rank == 0 or args.workload not in ("c3", "c5")))
     t_gen = time.perf_counter() - t_gen
     fhp = Fhp(local_rank)
-    names = ["traversability", "elevation"]
+    names = ["traversability", "elevation"] + (["slope"] if args.workload == "c5" else [])
     bcast_ms = None
     if world > 1:
         layers, bcast_ms = fdist.replicate_map(hmap if rank == 0 else None, hmap, names, local_rank)
@@ -421,8 +426,9 @@ def main():
             "config": {"workload": desc, "queries_per_gpu": nq, "gait_cycles": cycles,
                        "footholds_per_step_per_gpu": footholds_per_step,
                        "l2": "no explicit flush: every step streams %d MB of response rows through the 126 MB L2 "
-                             "between its reads of the map (8 MB class planes + 64 MB elevation layer)"
-                             % (nq * R * 40 // 2 ** 20),
+                             "between its reads of the map (%d MB class planes + %d MB elevation layer)"
+                             % (nq * R * 40 // 2 ** 20, hmap.rows * hmap.cols // 2 // 2 ** 20,
+                                hmap.rows * hmap.cols * 4 // 2 ** 20),
                        "staging": os.environ.get("FHP_STAGING", "mask"),
                        "map_generation_s": round(t_gen, 2), "map_broadcast_ms": bcast_ms,
                        "map_broadcast_GBps": (None if not bcast_ms else round(

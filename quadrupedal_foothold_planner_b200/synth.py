@@ -171,6 +171,19 @@ def config_c3(n_queries=65536, rows=4000, cols=4000, seed_map=3, seed_q=4, start
     return m, q, 16
 
 
+def config_c5(n_queries=262144, rows=16000, cols=16000, seed_map=6, seed_q=7, start=(4321, 12345), with_map=True):
+    """trot, 262,144 queries x 32 cycles on a 16000x16000 @ 0.01 m rough map with three layers (traversability,
+    elevation, slope = |grad elevation|; 3 x 1.02 GB).  with_map=False returns the geometry only."""
+    if with_map:
+        m = rough_map(rows, cols, 0.01, seed=seed_map, start=start, with_slope=True)
+    else:
+        m = HostMap(rows, cols, 0.01, (0.0, 0.0), start)
+    half = rows * 0.01 / 2
+    # 32 cycles advance 5.8 m; keep every window >= 0.5 m inside the map
+    q = uniform_queries(n_queries, (-half + 1.0, half - 7.5), (-half + 1.0, half - 1.0), seed=seed_q)
+    return m, q, 32
+
+
 def config_c4(n_poses=64, n_steps=64, rows=1500, cols=1500, seed_map=5, seed_q=6):
     """The heading-0 slice of BASELINE config 4: {trot, walk} x n_steps step lengths in [0.10, 0.26] (skew =
     stepLength/4, yaml:44) x n_poses start poses, 8 cycles, on a C3-style rough map with start index (0,0).
