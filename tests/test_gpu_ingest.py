@@ -100,3 +100,37 @@ def test_rejected_messages_keep_the_previous_map(fhp):
     with pytest.raises(FhpError) as e:
         fhp.set_map_wire(serialize_gridmap(lone))
     assert e.value.code == _abi.FHP_ERR_MISSING_LAYER
+
+
+def test_wire_parser_survives_mutations(fhp):
+    """Random truncations, byte flips and length-field corruptions of a valid message: every call returns (accepted
+    or rejected with INVALID_ARG / MISSING_LAYER) — no crash, no out-of-bounds read — and the planner stays usable."""
+    m = synth.rough_map(48, 40, 0.02, seed=5, start=(3, 7))
+    wire = bytearray(serialize_gridmap(m, frame_id="odom", basic_layers=["elevation"]))
+    rng = np.random.default_rng(2)
+    header_end = 12 + 4 + 4 + 80 + 200  # header, geometry, names and the first array's layout live in these bytes
+    outcomes = {"ok": 0, "rejected": 0}
+    for trial in range(400):
+        b = bytearray(wire)
+        kind = trial % 4
+        if kind == 0:
+            b = b[: int(rng.integers(0, len(b)))]
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, header_end))] = int(rng.integers(0, 256))
+        elif kind == 2:
+            off = int(rng.integers(0, header_end - 4))
+            b[off:off + 4] = struct.pack("<I", int(rng.choice([0, 1, 0x7FFFFFFF, 0xFFFFFFFF, len(b), len(b) * 4])))
+        else:
+            b += bytes(int(rng.integers(1, 9)))
+        try:
+            fhp.set_map_wire(bytes(b))
+            outcomes["ok"] += 1
+        except FhpError as e:
+            assert e.code in (_abi.FHP_ERR_INVALID_ARG, _abi.FHP_ERR_MISSING_LAYER), e
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 250
+    fhp.set_map_wire(bytes(wire))
+    q = synth.uniform_queries(16, (-0.2, 0.0), (-0.2, 0.2), seed=1)
+    st = fhp.plan(_abi.yaml_params(), q, 2)[2]
+    assert np.all(st["reserved"] == 0)
