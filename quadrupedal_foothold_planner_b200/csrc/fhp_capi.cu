@@ -609,9 +609,9 @@ int fhp_create(int device, fhp_ctx** out) {
   std::memset(&ctx->tmapTrav, 0, sizeof(ctx->tmapTrav));
   if (const char* dt = std::getenv("FHP_DISABLE_TMA"))
     if (dt[0] == '1') ctx->stagePref = kStageLdg;
-  if (const char* e = std::getenv("FHP_CHUNK_DIV")) ctx->chunkDiv = std::max(1, atoi(e));
-  if (const char* e = std::getenv("FHP_QPW_SHIFT")) ctx->qpwShiftForce = std::max(0, std::min(3, atoi(e)));
-  if (const char* e = std::getenv("FHP_TMA_BOX_BUDGET")) ctx->tmaBoxBudget = std::max(1024, atoi(e));
+  if (const char* v = std::getenv("FHP_CHUNK_DIV")) ctx->chunkDiv = std::max(1, atoi(v));
+  if (const char* v = std::getenv("FHP_QPW_SHIFT")) ctx->qpwShiftForce = std::max(0, std::min(3, atoi(v)));
+  if (const char* v = std::getenv("FHP_TMA_BOX_BUDGET")) ctx->tmaBoxBudget = std::max(1024, atoi(v));
   if (const char* st = std::getenv("FHP_STAGING")) {
     if (!std::strcmp(st, "mask")) ctx->stagePref = kStageMask;
     else if (!std::strcmp(st, "tma")) ctx->stagePref = kStageTma;
