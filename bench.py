@@ -91,6 +91,10 @@ def make_workload(name: str, rank: int, with_map: bool = True):
             cycles = 16
         return m, q, cycles, [_abi.yaml_params()], ("C3: trot, 65536 queries x 16 cycles per GPU, 4000x4000 @0.02 m "
                                                     "rough map, start index (1234,2777)")
+    if name == "c4":  # heading-0 slice of BASELINE config 4: 128 parameter sets x 4096 poses, every rank its own poses
+        m, params, q, cycles = synth.config_c4(n_poses=4096, rows=4000, cols=4000, seed_q=6 + 1000 * rank)
+        return m, q, cycles, params, ("C4 (heading 0): {trot,walk} x 64 step lengths x 4096 poses = 524288 queries x 8 "
+                                      "cycles per GPU, 128 parameter sets, 4000x4000 @0.02 m rough map")
     if name == "c5":
         m, q, cycles = synth.config_c5(seed_q=7 + 1000 * rank, with_map=with_map)
         return m, q, cycles, [_abi.yaml_params()], ("C5: trot, 262144 queries x 32 cycles per GPU, 16000x16000 @0.01 m "
@@ -266,7 +270,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1", "c4", "c5"])
     ap.add_argument("--ref-sample", type=int, default=16384, help="queries per step of the CPU arm")
     ap.add_argument("--cpu-sample", type=int, default=65536, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
