@@ -83,6 +83,10 @@ typedef struct fhp_params {
   double h;                 /* h_ = 0.01, FP.cpp:336      */
   double drift_per_cycle;   /* -0.007, FP.cpp:1578        */
   double bias[4][2];        /* RF,RH,LH,LF (x,y); read only when gait == FHP_GAIT_CUSTOM */
+  double heading;           /* extension: body heading in the map frame, radians; 0 = the reference (which always advances
+                               along +x, FP.cpp:2199-2202).  Rotates the stance, the step vector, the bias table and the
+                               search rectangle; the lateral pin initialPose.y + adjusted_y (FP.cpp:2201) becomes a pin
+                               along the rotated normal.  Exact definition: DESIGN.md §8 */
 } fhp_params;
 
 /* One independent plan request: the robot's initial stance centre (rosparam initial_position/{x,y,z},

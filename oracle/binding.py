@@ -76,6 +76,18 @@ def plan_ex(hmap, params, queries, gait_cycles):
     return nom, cen, dfl, kpi, st
 
 
+def plan_latency(hmap, params, query, gait_cycles, repeats=200, leg_threads=False):
+    """-> (ms per call [repeats], status) of ONE plan on the CPU; leg_threads: the reference's 4 std::threads per cycle."""
+    d, ptrs, keep = hmap.desc()
+    q = np.ascontiguousarray(query).reshape(1)
+    ms = np.zeros(repeats, dtype=np.float64)
+    st = np.zeros(1, dtype=_abi.STATUS_DTYPE)
+    rc = lib().oracle_plan_latency(C.byref(d), ptrs, C.byref(params), _p(q), C.c_int32(gait_cycles), C.c_int32(repeats),
+                                   C.c_int32(1 if leg_threads else 0), _p(ms), _p(st))
+    assert rc == 0, rc
+    return ms, st[0]
+
+
 def touch_bytes(hmap, params, queries, gait_cycles, with_centroid_height=True):
     params = list(params) if isinstance(params, (list, tuple)) else [params]
     parr = (_abi.Params * len(params))(*params)

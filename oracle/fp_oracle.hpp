@@ -19,6 +19,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gm_core.hpp"
@@ -48,6 +49,18 @@ struct Params {
   bool useCustomBias = false;
   double customBias[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   int spiralMode = SPIRAL_WRAP_CORRECT;
+  // extension (not in the reference, which always advances along +x, FP.cpp:2199-2202): heading of the body in the
+  // map frame (radians).  heading == 0 runs the restated reference code unchanged; any other value (or
+  // forceHeadingPath, which the tests use to prove the general expressions reduce BIT-EXACTLY to the reference at
+  // theta = 0) runs the rotated expressions marked "heading" below.  Definition:
+  //   u = (cos, sin) forward, n = (-sin, cos) lateral;  rot(v) = (v.x*cos - v.y*sin, v.x*sin + v.y*cos)
+  //   stance, bias table and the four rectangle vertex offsets are rot() of the reference's values;
+  //   setFirstGait: cur = init - (stepLength/2) u;
+  //   next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n   — the forward coordinate comes from the stance
+  //   centroid c, the lateral one is pinned to the initial pose p0 plus the drift, exactly as FP.cpp:2199-2201 does
+  //   for u = +x;  the centroid method keeps its axis-aligned getSubmap window (grid_map cuts no rotated submaps).
+  double heading = 0.0;
+  bool forceHeadingPath = false;
 };
 
 struct Foothold {  // foothold_planner_msgs/Foothold + diagnostics
@@ -79,12 +92,19 @@ class Planner {
   Point initial[4];  // RF, RH, LH, LF initial stance
   Point bias[4];     // RF, RH, LH, LF default bias (trapezoid vertices relative to the stance centroid)
   double ajustedPoseY = 0;
+  // heading extension: derived in initialize()
+  bool useHeading = false;
+  double ch = 1.0, sh = 0.0;   // cos / sin of the heading
+  gm::Vec2 rectOff[4];         // rot() of the rectangle's vertex offsets, vertex order of getSearchPolygon
   // instrumentation: when countTouched is set, globalFootholdPlan accumulates the number of UNIQUE
   // map cells (any layer) read per (cycle, leg) foothold = centroid task + nominal task of that leg.
   bool countTouched = false;
   // response-only variant: skip the centroid chain's height lookups (their z never reaches the
   // plan_global_footholds response, FP.cpp:1588) — used only to count the algorithmic bytes of that variant.
   bool centroidHeight = true;
+  // timing variant: run the four nominal-chain leg searches of a cycle on four std::threads and
+  // join them, as the reference does (FP.cpp:863-909).  Same results; never combined with countTouched.
+  bool legThreads = false;
   int64_t touchedCells = 0;
   int64_t spiralTaken = 0;  // footholds whose default-disc test failed (spiral search executed)
   // instrumentation for kernel design (scratch statistics, never part of a result): when set, rankHist[k] counts
@@ -123,14 +143,62 @@ class Planner {
         bias[f].x = p.customBias[f][0];
         bias[f].y = p.customBias[f][1];
       }
+    // ---- heading extension: rotate stance, bias table and rectangle vertex offsets
+    useHeading = (p.heading != 0.0) || p.forceHeadingPath;
+    ch = std::cos(p.heading);
+    sh = std::sin(p.heading);
+    if (useHeading) {
+      const double ox[4] = {lengthBase * 0.5, -lengthBase * 0.5, -lengthBase * 0.5, lengthBase * 0.5};
+      const double oy[4] = {-widthBase * 0.5, -widthBase * 0.5, widthBase * 0.5, widthBase * 0.5};
+      for (int f = 0; f < 4; ++f) {
+        initial[f].x = (ox[f] * ch - oy[f] * sh) + initialPose[0];
+        initial[f].y = (ox[f] * sh + oy[f] * ch) + initialPose[1];
+        initial[f].z = 0.0 + initialPose[2];
+        const double bx = bias[f].x, by = bias[f].y;
+        bias[f].x = bx * ch - by * sh;
+        bias[f].y = bx * sh + by * ch;
+      }
+      const double R = p.searchRadius, hR = 0.5 * p.searchRadius;  // float promoted (FP.cpp:2502-2511)
+      const double vx[4] = {R, R, -R, -R}, vy[4] = {hR, -hR, -hR, hR};
+      for (int k = 0; k < 4; ++k) {
+        rectOff[k].x = vx[k] * ch - vy[k] * sh;
+        rectOff[k].y = vx[k] * sh + vy[k] * ch;
+      }
+    }
   }
 
   // FP.cpp:2679-2699
   void setFirstGait(const Point init[4], Point cur[4]) const {
     for (int f = 0; f < 4; ++f) {
       cur[f] = init[f];
+      if (useHeading) {  // heading: half a step back along u
+        const double hs = p.stepLength / 2;
+        cur[f].x = init[f].x - hs * ch;
+        cur[f].y = init[f].y - hs * sh;
+        continue;
+      }
       cur[f].x = init[f].x - p.stepLength / 2;  // float/int -> float, promoted
     }
+  }
+
+  // heading: the next stance centre from the current stance centroid (see Params::heading)
+  Point headingNextCenter(const Point& polygonCenter) const {
+    Point n;
+    const double fwd = (polygonCenter.x * ch + polygonCenter.y * sh) + p.stepLength;
+    const double lat = (initialPose[1] * ch - initialPose[0] * sh) + ajustedPoseY;
+    n.x = fwd * ch - lat * sh;
+    n.y = fwd * sh + lat * ch;
+    n.z = polygonCenter.z;
+    return n;
+  }
+  // heading: getSearchPolygon with rotated vertex offsets (same vertex order)
+  gm::Polygon headingSearchPolygon(const Point& center) const {
+    gm::Polygon poly;
+    for (int k = 0; k < 4; ++k) poly.addVertex(gm::Vec2{center.x + rectOff[k].x, center.y + rectOff[k].y});
+    return poly;
+  }
+  gm::Polygon searchPolygon(const Point& center) const {
+    return useHeading ? headingSearchPolygon(center) : getSearchPolygon(center, p.searchRadius);
   }
 
   // FP.cpp:2421-2463
@@ -189,8 +257,9 @@ class Planner {
     polygonCenterNext.x = polygonCenter.x + p.stepLength;         // :2199
     polygonCenterNext.y = initialPose[1] + ajustedPoseY;          // :2201
     polygonCenterNext.z = polygonCenter.z;
+    if (useHeading) polygonCenterNext = headingNextCenter(polygonCenter);
     for (int f = 0; f < 4; ++f) next[f] = getDefaultFootholdNext(polygonCenterNext, bias[f]);  // :2207-2213
-    for (int f = 0; f < 4; ++f) poly[f] = getSearchPolygon(next[f], p.searchRadius);           // :2235-2244
+    for (int f = 0; f < 4; ++f) poly[f] = searchPolygon(next[f]);                              // :2235-2244
   }
 
   // FP.cpp:2520-2554
@@ -408,6 +477,7 @@ class Planner {
     polygonCenterNext.x = polygonCenter.x + p.stepLength;   // :2270
     polygonCenterNext.y = initialPose[1] + ajustedPoseY;    // :2272
     polygonCenterNext.z = polygonCenter.z;
+    if (useHeading) polygonCenterNext = headingNextCenter(polygonCenter);
     for (int f = 0; f < 4; ++f) {
       next[f] = getDefaultFootholdNext(polygonCenterNext, bias[f]);
       next[f].z = getFootholdMeanHeight(gridmap, gm::Vec2{next[f].x, next[f].y}, p.footRadius, p.h);  // :2289-2301
@@ -489,6 +559,15 @@ class Planner {
       Point nomRes[4];
       bool ok[4];
       uint8_t kind[4];
+      if (legThreads && !countTouched) {  // :863-909: one std::thread per leg, joined before the AND
+        std::thread th[4];
+        for (int f = 0; f < 4; ++f)
+          th[f] = std::thread([&, f]() {
+            gm::Vec2 center{cenNext[f].x, cenNext[f].y};
+            checkFoothold(gridmap, center, p.footRadius, p.searchRadius, nomPoly[f], nomRes[f], ok[f], &kind[f]);
+          });
+        for (int f = 0; f < 4; ++f) th[f].join();
+      } else
       for (int f = 0; f < 4; ++f) {
         gm::Vec2 center{cenNext[f].x, cenNext[f].y};  // centre from the CENTROID chain (:861-862)
         if (countTouched) gridmap.touch = &legLog[f];

@@ -12,6 +12,9 @@
 
 namespace {
 
+// test hook: run the heading expressions even for heading == 0 (they must reduce bit-exactly to the reference there)
+std::atomic<int> g_force_heading{0};
+
 gm::GridMap make_map(const fhp_map_desc* d, const float* const* layers) {
   gm::GridMap m;
   m.length = gm::Vec2{d->length_x, d->length_y};
@@ -38,6 +41,8 @@ ref::Planner make_planner(const fhp_params& fp, const fhp_query& q) {
   pl.p.h = fp.h;
   pl.p.driftPerCycle = fp.drift_per_cycle;
   pl.p.spiralMode = fp.spiral_mode == FHP_SPIRAL_FAITHFUL ? ref::SPIRAL_FAITHFUL : ref::SPIRAL_WRAP_CORRECT;
+  pl.p.heading = fp.heading;
+  pl.p.forceHeadingPath = g_force_heading.load() != 0;
   if (fp.gait == FHP_GAIT_CUSTOM) {
     pl.p.useCustomBias = true;
     for (int f = 0; f < 4; ++f) {
@@ -104,6 +109,8 @@ void plan_one(const gm::GridMap& map, const fhp_params* params, const fhp_query&
 
 extern "C" {
 
+void oracle_force_heading_path(int32_t on) { g_force_heading.store(on); }
+
 // Whole plans for n_queries (same contract as fhp_plan).  n_threads <= 1: serial.
 int oracle_plan(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params, int32_t n_params,
                 const fhp_query* queries, int64_t n_queries, int32_t gait_cycles, fhp_foothold* out_nominal,
@@ -152,6 +159,32 @@ int oracle_plan_ex(const fhp_map_desc* desc, const float* const* layers, const f
     plan_one(map, params, queries[q], gait_cycles, out_nominal + q * R, out_centroid ? out_centroid + q * R : nullptr,
              status + q, out_default ? out_default + q * R : nullptr,
              out_kpi ? out_kpi + q * static_cast<int64_t>(gait_cycles) * 8 : nullptr);
+  }
+  return FHP_OK;
+}
+
+// Latency of ONE plan_global_footholds call: `repeats` timed calls of the same query, milliseconds
+// each into out_ms.  leg_threads != 0: the reference's threading (four std::threads per cycle, FP.cpp:863-909).
+int oracle_plan_latency(const fhp_map_desc* desc, const float* const* layers, const fhp_params* params,
+                        const fhp_query* query, int32_t gait_cycles, int32_t repeats, int32_t leg_threads, double* out_ms,
+                        fhp_query_status* status) {
+  if (!desc || !layers || !params || !query || !out_ms || gait_cycles < 0 || gait_cycles > 255) return FHP_ERR_INVALID_ARG;
+  gm::GridMap map = make_map(desc, layers);
+  if (!map.exists("traversability") || !map.exists("elevation")) return FHP_ERR_MISSING_LAYER;
+  for (int r = 0; r < repeats; ++r) {
+    const auto t0 = std::chrono::steady_clock::now();
+    ref::Planner pl = make_planner(params[0], *query);
+    pl.legThreads = leg_threads != 0;
+    ref::PlanResult res = pl.globalFootholdPlan(map, static_cast<uint8_t>(gait_cycles));
+    const auto t1 = std::chrono::steady_clock::now();
+    out_ms[r] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (status) {
+      status->success = res.success ? 1 : 0;
+      status->gait_cycles = res.gait_cycles;
+      status->gait_cycles_succeed = res.gait_cycles_succeed;
+      status->reserved = 0;
+      status->n_rows = static_cast<int32_t>(res.footholds.size());
+    }
   }
   return FHP_OK;
 }
@@ -208,7 +241,7 @@ int oracle_check_foothold(const fhp_map_desc* desc, const float* const* layers, 
     ref::Point rc;
     rc.x = rect_centres_xy[2 * i];
     rc.y = rect_centres_xy[2 * i + 1];
-    gm::Polygon poly = ref::Planner::getSearchPolygon(rc, pl.p.searchRadius);
+    gm::Polygon poly = pl.searchPolygon(rc);
     ref::Foothold fh;
     bool ok = false;
     pl.checkFoothold(map, c, pl.p.footRadius, pl.p.searchRadius, poly, fh.point, ok, &fh.kind);
@@ -277,7 +310,7 @@ int oracle_check_candidate(const fhp_map_desc* desc, const float* const* layers,
     ref::Point rc;
     rc.x = rect_centres_xy[2 * i];
     rc.y = rect_centres_xy[2 * i + 1];
-    gm::Polygon poly = ref::Planner::getSearchPolygon(rc, pl.p.searchRadius);
+    gm::Polygon poly = pl.searchPolygon(rc);
     ref::Foothold fh;
     fh.kind = ref::KIND_CANDIDATE;
     const bool ok = pl.checkCandidateFoothold(map, c, pl.p.footRadius, pl.p.searchRadius, poly, fh.point);
@@ -300,7 +333,7 @@ int oracle_check_circle_polygon(const fhp_map_desc* desc, const float* const* la
     ref::Point rc;
     rc.x = rect_centres_xy[2 * i];
     rc.y = rect_centres_xy[2 * i + 1];
-    gm::Polygon poly = ref::Planner::getSearchPolygon(rc, pl.p.searchRadius);
+    gm::Polygon poly = pl.searchPolygon(rc);
     valid_out[i] = pl.checkCirclePolygonFoothold(map, gm::Vec2{foot_centres_xy[2 * i], foot_centres_xy[2 * i + 1]},
                                                  pl.p.footRadius, poly) ? 1 : 0;
   }

@@ -38,6 +38,7 @@ class Params(C.Structure):
         ("rf_first", C.c_int32), ("gait", C.c_int32), ("spiral_mode", C.c_int32),
         ("h", C.c_double), ("drift_per_cycle", C.c_double),
         ("bias", (C.c_double * 2) * 4),
+        ("heading", C.c_double),
     ]
 
 
@@ -94,6 +95,7 @@ def yaml_params(**over) -> Params:
     p.spiral_mode = FHP_SPIRAL_WRAP_CORRECT
     p.h = 0.01
     p.drift_per_cycle = -0.007
+    p.heading = 0.0
     for k, v in over.items():
         if k == "bias":
             for f in range(4):

@@ -78,6 +78,10 @@ struct fhp_ctx {
   long long waveQueries[2] = {0, 0};  // plan_wave_queries(G, wantCen) for the cached geometry (0 = not asked yet)
   int qpwShiftForce = -1;
   int tmaBoxBudget = 8192;
+  // FHP_FORCE_HEADING=1 (test knob, read at fhp_create): run the heading expressions even for heading == 0, where they
+  // must reduce bit-exactly to the reference's (tests/test_gpu_heading.py)
+  bool forceHeading = false;
+  bool anyHeading = false;  // some parameter set of the current call has the heading expressions in force
   // D/C/F mask planes of the traversability layer for one threshold pair (rebuilt lazily after a map update)
   DevBuf dMask;
   bool maskValid = false;
@@ -270,7 +274,7 @@ int bind_layers(fhp_ctx* ctx) {
 
 // Derive what FootholdPlanner::initialize computes from the rosparams (FP.cpp:317-421), with the reference's
 // float / double member types (FootholdPlanner.hpp:609-697).
-void derive_params(const fhp_params& p, ParDev& o) {
+void derive_params(const fhp_params& p, ParDev& o, bool forceHeading = false) {
   const float lengthBase = p.kin_length;                 // FP.cpp:340
   const float widthBase = p.kin_width + p.kin_l1 * 2;    // FP.cpp:341 (float arithmetic)
   const float skew = p.skew;
@@ -314,7 +318,26 @@ void derive_params(const fhp_params& p, ParDev& o) {
   o.thrD = p.thr_default;
   o.thrC = p.thr_candidate;
   o.spiralMode = p.spiral_mode;
-  o.pad = 0;
+  // heading extension: rotate stance, bias table and rectangle vertex offsets (same expressions as the CPU checker)
+  o.heading = (p.heading != 0.0 || forceHeading) ? 1 : 0;
+  o.ch = std::cos(p.heading);
+  o.sh = std::sin(p.heading);
+  const double hR = 0.5 * p.search_radius;
+  const double vx[4] = {o.R, o.R, -o.R, -o.R}, vy[4] = {hR, -hR, -hR, hR};
+  for (int k = 0; k < 4; ++k) {
+    o.rectVx[k] = o.heading ? vx[k] * o.ch - vy[k] * o.sh : vx[k];
+    o.rectVy[k] = o.heading ? vx[k] * o.sh + vy[k] * o.ch : vy[k];
+  }
+  o.halfStepX = o.halfStep * o.ch;
+  o.halfStepY = o.halfStep * o.sh;
+  if (o.heading)
+    for (int f = 0; f < 4; ++f) {
+      const double sx = o.stancex[f], sy = o.stancey[f], bx = o.biasx[f], by = o.biasy[f];
+      o.stancex[f] = sx * o.ch - sy * o.sh;
+      o.stancey[f] = sx * o.sh + sy * o.ch;
+      o.biasx[f] = bx * o.ch - by * o.sh;
+      o.biasy[f] = bx * o.sh + by * o.ch;
+    }
 }
 
 int sgn(int v) { return (v > 0) - (v < 0); }
@@ -515,11 +538,16 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   if (stage == kStageMask && ctx->maskNegInf) stage = kStageTma;
   int rc = build_geo(ctx, params[0].foot_radius, params[0].search_radius, allowTrim, stage);
   if (rc != FHP_OK) return rc;
+  ctx->anyHeading = ctx->forceHeading;
+  for (int i = 0; i < n_params; ++i) {
+    if (!std::isfinite(params[i].heading)) return fail(ctx, FHP_ERR_INVALID_ARG, "params.heading is not finite");
+    if (params[i].heading != 0.0) ctx->anyHeading = true;
+  }
   if (ctx->dPars.p && ctx->lastParams.size() == static_cast<size_t>(n_params) &&
       std::memcmp(ctx->lastParams.data(), params, sizeof(fhp_params) * n_params) == 0)
     return FHP_OK;  // same parameter sets as the previous call: the derived table is already on the device
   std::vector<ParDev> h(n_params);
-  for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i]);
+  for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i], ctx->forceHeading);
   CU(ctx->dPars.reserve(sizeof(ParDev) * n_params));
   CU(cudaMemcpyAsync(ctx->dPars.p, h.data(), sizeof(ParDev) * n_params, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));  // h goes out of scope
@@ -612,6 +640,7 @@ int fhp_create(int device, fhp_ctx** out) {
   if (const char* v = std::getenv("FHP_CHUNK_DIV")) ctx->chunkDiv = std::max(1, atoi(v));
   if (const char* v = std::getenv("FHP_QPW_SHIFT")) ctx->qpwShiftForce = std::max(0, std::min(3, atoi(v)));
   if (const char* v = std::getenv("FHP_TMA_BOX_BUDGET")) ctx->tmaBoxBudget = std::max(1024, atoi(v));
+  if (const char* v = std::getenv("FHP_FORCE_HEADING")) ctx->forceHeading = v[0] == '1';
   if (const char* st = std::getenv("FHP_STAGING")) {
     if (!std::strcmp(st, "mask")) ctx->stagePref = kStageMask;
     else if (!std::strcmp(st, "tma")) ctx->stagePref = kStageTma;
@@ -918,7 +947,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.st = d_st;
   A.err = ctx->dErrMapped;
   {
-    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, s);
+    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, ctx->anyHeading, s);
     if (e != cudaSuccess) {
       char b[256];
       snprintf(b, sizeof b, "plan kernel launch failed: %s (queries %lld, queries/warp %d, shared memory %d B)",
@@ -1328,8 +1357,8 @@ int fhp_initial_stance(const fhp_params* params, const fhp_query* query, double*
     initial_xyz[3 * f] = d.stancex[f] + query->x;
     initial_xyz[3 * f + 1] = d.stancey[f] + query->y;
     initial_xyz[3 * f + 2] = 0.0 + query->z;
-    first_gait_xyz[3 * f] = initial_xyz[3 * f] - d.halfStep;
-    first_gait_xyz[3 * f + 1] = initial_xyz[3 * f + 1];
+    first_gait_xyz[3 * f] = initial_xyz[3 * f] - (d.heading ? d.halfStepX : d.halfStep);
+    first_gait_xyz[3 * f + 1] = d.heading ? initial_xyz[3 * f + 1] - d.halfStepY : initial_xyz[3 * f + 1];
     first_gait_xyz[3 * f + 2] = initial_xyz[3 * f + 2];
   }
   return FHP_OK;
@@ -1357,13 +1386,26 @@ int fhp_search_geometry(const fhp_params* params, const fhp_query* query, double
   center_xyz[1] = sum_y / sum_s / 3.0;
   center_xyz[2] = (cur_xyz[2] + cur_xyz[5] + cur_xyz[8] + cur_xyz[11]) / 4.0;
   // getFootholdSearchGridMap (FP.cpp:2166-2250): next centre, getDefaultFootholdNext (:2411-2418), getSearchPolygon
-  const double ncx = center_xyz[0] + d.stepLength;  // :2199
-  const double ncy = query->y + adjusted_y;         // :2201
+  double ncx = center_xyz[0] + d.stepLength;  // :2199
+  double ncy = query->y + adjusted_y;         // :2201
+  if (d.heading) {  // heading extension (fhp_params.heading): forward coordinate from the centroid, lateral one pinned
+    const double fwd = (center_xyz[0] * d.ch + center_xyz[1] * d.sh) + d.stepLength;
+    const double lat = (query->y * d.ch - query->x * d.sh) + adjusted_y;
+    ncx = fwd * d.ch - lat * d.sh;
+    ncy = fwd * d.sh + lat * d.ch;
+  }
   for (int f = 0; f < 4; ++f) {
     const double nx = ncx + d.biasx[f], ny = ncy + d.biasy[f];
     next_xy[2 * f] = nx;
     next_xy[2 * f + 1] = ny;
     double* v = polygon_xy + 8 * f;  // :2496-2517, vertex order leftup, rightup, rightdown, leftdown
+    if (d.heading) {
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] = nx + d.rectVx[k];
+        v[2 * k + 1] = ny + d.rectVy[k];
+      }
+      continue;
+    }
     v[0] = nx + d.R;  v[1] = ny + 0.5 * d.R;
     v[2] = nx + d.R;  v[3] = ny - 0.5 * d.R;
     v[4] = nx - d.R;  v[5] = ny - 0.5 * d.R;

@@ -829,6 +829,16 @@ struct NominalOut {
 struct Box {
   double xlo, xhi, ylo, yhi;
 };
+// heading extension: the rectangle is rotated (centre + ParDev::rectV), the slow paths only need its centre, which
+// travels in the same struct (xlo = centre x, ylo = centre y) so that the reference-shaped kernels keep their frame
+__device__ __forceinline__ Box centre_box(double rx, double ry) {
+  Box b;
+  b.xlo = rx;
+  b.xhi = rx;
+  b.ylo = ry;
+  b.yhi = ry;
+  return b;
+}
 __device__ __forceinline__ Box search_box(const ParDev& P, double rx, double ry) {
   Box b;
   b.xhi = rx + P.R;
@@ -913,8 +923,51 @@ __device__ __forceinline__ void box_masks(const MapDev& M, const GeoDev& G, cons
                          first_below(M.fcy, M.res, M.rinv, w1, G.WIN, bx.ylo));
 }
 
+// ---- heading extension: the search rectangle is a ROTATED rectangle, so grid_map::Polygon::isInside is the general
+// W. R. Franklin PNPOLY (upstream's operand order; gm::Polygon::isInside in the CPU checker):
+//   for every edge (i, j = i-1):  (v[i].y > p.y) != (v[j].y > p.y)  &&  p.x < (v[j].x-v[i].x)*(p.y-v[i].y)/(v[j].y-v[i].y) + v[i].x
+// an odd number of such edges <=> inside.  Vertices = rectangle centre + ParDev::rectV (rotated on the host).
+__device__ __noinline__ bool pnpoly_point(const ParDev& P, double rx, double ry, double X, double Y) {
+  int cross = 0;
+  double jx = rx + P.rectVx[3], jy = ry + P.rectVy[3];
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const double ix = rx + P.rectVx[i], iy = ry + P.rectVy[i];
+    if ((iy > Y) != (jy > Y)) {
+      if (X < div_rn((jx - ix) * (Y - iy), jy - iy) + ix) ++cross;
+    }
+    jx = ix;
+    jy = iy;
+  }
+  return (cross & 1) != 0;
+}
+// The window rows of ONE window column (cell index u1 along y) whose cell centre is inside the polygon.  Along a column
+// p.y is fixed, so every edge that straddles it contributes ONE threshold X_e (computed exactly as upstream does) and
+// the test p.x < X_e; cell-centre x strictly decreases with the row, so "p.x < X_e" holds from first_below(X_e) on and
+// the parity of the crossings is the XOR of those suffix masks.  Exact for any polygon, ~2 divisions per column.
+__device__ __noinline__ uint32_t poly_col_rows(const MapDev& M, const ParDev& P, double rx, double ry, int w0, int nRows,
+                                               int u1) {
+  const double Y = pos_axis(M.fcy, M.res, u1);
+  uint32_t m = 0u;
+  double jx = rx + P.rectVx[3], jy = ry + P.rectVy[3];
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const double ix = rx + P.rectVx[i], iy = ry + P.rectVy[i];
+    if ((iy > Y) != (jy > Y)) {
+      const double X = div_rn((jx - ix) * (Y - iy), jy - iy) + ix;
+      const int a = first_below(M.fcx, M.res, M.rinv, w0, nRows, X);
+      if (a < 32) m ^= 0xffffffffu << a;
+    }
+    jx = ix;
+    jy = iy;
+  }
+  return m;
+}
+
 // checkCirclePolygonFoothold (FP.cpp:2117-2163) for the candidate at window coordinates (qa,qb), on the planes:
-// every finite cell of the foot disc must be >= candidateFootholdThreshold and inside the box.
+// every finite cell of the foot disc must be >= candidateFootholdThreshold and inside the box.  HEADING: the owning
+// lane has left the finished "bad cell" masks (polygon included) in plane 3 of its slot (nominal_eval).
+template <bool HEADING>
 __device__ __forceinline__ bool candidate_on_planes(const GeoDev& G, const Planes& pl, int qa, int qb, uint32_t rowsBox,
                                                     uint32_t colsBox) {
   bool good = true;
@@ -922,9 +975,14 @@ __device__ __forceinline__ bool candidate_on_planes(const GeoDev& G, const Plane
     const int a = qa + G.sten[s][0], b = qb + G.sten[s][1];
     // a,b are inside the window by construction (|d| <= nRings, |sten| <= ra); cells outside the map have
     // F = 0 and are skipped like the iterator skips them
-    const uint32_t F = pl.col(PL_F, b), C = pl.col(PL_C, b);
-    const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
-    const uint32_t bad = F & (C | ~box);
+    uint32_t bad;
+    if (HEADING) {
+      bad = pl.col(3, b);
+    } else {
+      const uint32_t F = pl.col(PL_F, b), C = pl.col(PL_C, b);
+      const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
+      bad = F & (C | ~box);
+    }
     good = !((bad >> a) & 1u);
   }
   return good;
@@ -933,8 +991,8 @@ __device__ __forceinline__ bool candidate_on_planes(const GeoDev& G, const Plane
 // checkCirclePolygonFoothold (FP.cpp:2117-2163) at an ARBITRARY foot centre, straight from global memory (the public
 // member; the plan's own candidates sit on cell centres and use the planes): walk CircleIterator's window, every finite
 // member cell must be >= candidateFootholdThreshold and inside the box; a disc without member cells is invalid.
-__device__ __noinline__ bool circle_polygon_direct(const MapDev& M, const ParDev& P, double cx, double cy, double xlo,
-                                                   double xhi, double ylo, double yhi) {
+__device__ __noinline__ bool circle_polygon_direct(const MapDev& M, const ParDev& P, double cx, double cy, const Box& bx) {
+  const double xlo = bx.xlo, xhi = bx.xhi, ylo = bx.ylo, yhi = bx.yhi, rx = bx.xlo, ry = bx.ylo;  // (HEADING: centre)
   const DiscWin dw = disc_window_generic(M, cx, cy, P.r);
   bool validation = false;  // FP.cpp:2122: stays false when the iterator visits nothing
   for (int u0 = dw.tl0; u0 <= dw.br0; ++u0) {
@@ -946,7 +1004,7 @@ __device__ __noinline__ bool circle_polygon_direct(const MapDev& M, const ParDev
       validation = true;  // :2159 — every visited cell, valid or not, ends its iteration with validation = true
       const float v = load_cell(M, M.trav, u0, u1);
       if (!(fabsf(v) < __int_as_float(0x7f800000))) continue;  // :2132 invalid cells are not tested
-      const bool inside = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
+      const bool inside = P.heading ? pnpoly_point(P, rx, ry, X, Y) : ((X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi));
       if (v < P.thrC || !inside) return false;  // :2138-2143 (break with validation = false)
     }
   }
@@ -955,15 +1013,17 @@ __device__ __noinline__ bool circle_polygon_direct(const MapDev& M, const ParDev
 
 // One candidate evaluated straight from global memory (faithful-mode candidates that wrap to the far side of the
 // circular buffer): checkCirclePolygonFoothold (FP.cpp:2117-2163).
-__device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, float thrC, int q0, int q1, double xlo,
-                                            double xhi, double ylo, double yhi) {
+template <bool HEADING>
+__device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, const ParDev& P, int q0, int q1, const Box& bx) {
+  const float thrC = P.thrC;
+  const double xlo = bx.xlo, xhi = bx.xhi, ylo = bx.ylo, yhi = bx.yhi, rx = bx.xlo, ry = bx.ylo;  // (HEADING: centre)
   for (int s = 0; s < G.nSten; ++s) {
     const int u0 = q0 + G.sten[s][0], u1 = q1 + G.sten[s][1];
     if (!in_map(M, u0, u1)) continue;
     const float v = load_cell(M, M.trav, u0, u1);
     if (!(fabsf(v) < __int_as_float(0x7f800000))) continue;
     const double X = pos_axis(M.fcx, M.res, u0), Y = pos_axis(M.fcy, M.res, u1);
-    const bool inside = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
+    const bool inside = HEADING ? pnpoly_point(P, rx, ry, X, Y) : ((X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi));
     if (v < thrC || !inside) return false;
   }
   return true;
@@ -995,7 +1055,7 @@ __device__ __forceinline__ uint32_t in_range_mask(int org, int n, int nBits) {
 //      one bit test, plus the exact last-two-rings distance filter; the first set bit of the ballot is the first
 //      valid cell in spiral order and the scan stops at the first 32-block that has one.
 // Handles wrap_correct mode, and faithful mode when the start index is (0,0) (identical there).
-template <bool PAD>
+template <bool PAD, bool HEADING>
 __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
                                                  uint32_t smemWarp, int lane, bool need, int uc0, int uc1,
                                                  int w0, double cx, double cy, double R2, uint32_t rowsBox,
@@ -1011,6 +1071,9 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
     uint32_t bad = 0;
     if (PAD) {
       if (lane < G.WIN) bad = lds_u32(smemWarp + static_cast<uint32_t>(j * G.stride + lane * 4 + 3) * 4u);
+    } else if (HEADING) {  // the owning lane has left the finished masks (rotated rectangle included) in plane 3
+      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
+      if (lane < G.WIN) bad = pj.col(3, lane);
     } else {
       const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
       const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
@@ -1084,8 +1147,9 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
 // The same scan for FHP_SPIRAL_FAITHFUL with a non-zero start index (bug-compatible with upstream):
 // the centre index is the BUFFER index, ring neighbours are taken in buffer space without wrapping, and the
 // distance filter evaluates positions as if the start index were 0.  Per-lane scalar loop (compatibility path).
-__device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
-                                                  const Planes& pl, float thrC, int uc0, int uc1, int w0, double cx,
+template <bool HEADING>
+__device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev& G, const ParDev& P, const uint16_t* sSpiral,
+                                                  const Planes& pl, int uc0, int uc1, int w0, double cx,
                                                   double cy, double R2, const Box& bx, uint32_t rowsBox,
                                                   uint32_t colsBox, bool& found, int& fq0, int& fq1) {
   int cb0 = uc0 + M.start0, cb1 = uc1 + M.start1;  // getBufferIndexFromIndex + wrapIndexToRange
@@ -1106,8 +1170,8 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
     if (q0 < 0) q0 += M.rows;
     if (q1 < 0) q1 += M.cols;
     const bool far = (q0 != uc0 + d0) || (q1 != uc1 + d1);
-    const bool good = far ? candidate_slow(M, G, thrC, q0, q1, bx.xlo, bx.xhi, bx.ylo, bx.yhi)
-                          : candidate_on_planes(G, pl, d0 + (uc0 - w0), d1 + G.HW, rowsBox, colsBox);
+    const bool good = far ? candidate_slow<HEADING>(M, G, P, q0, q1, bx)
+                          : candidate_on_planes<HEADING>(G, pl, d0 + (uc0 - w0), d1 + G.HW, rowsBox, colsBox);
     if (good) {
       found = true;
       fq0 = q0;
@@ -1122,7 +1186,7 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
 // WARP-COLLECTIVE: every lane of the warp must call it (inactive lanes pass active = false).
 // (cx,cy): search centre; (rx,ry): centre of the search rectangle; (uc0,uc1): raw unwrapped index of the centre;
 // (w0,w1): unwrapped origin of the staged window (uc-HW, minus the TMA row-alignment shift).
-template <bool DEFAULT_ONLY, bool PAD>
+template <bool DEFAULT_ONLY, bool PAD, bool HEADING>
 __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P,
                                                    const uint16_t* sSpiral, uint32_t smemWarp, int lane,
                                                    bool active, int uc0, int uc1, int w0, int w1, double cx, double cy,
@@ -1153,11 +1217,32 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
   bool pend = need && !faithful;
   if (need) {
     o.kind = FHP_KIND_CANDIDATE;
-    bx = search_box(P, rx, ry);
-    box_masks(M, G, bx, w0, w1, rowsBox, colsBox);
+    if (HEADING) {
+      bx = centre_box(rx, ry);
+    } else {
+      bx = search_box(P, rx, ry);
+      box_masks(M, G, bx, w0, w1, rowsBox, colsBox);
+    }
     rowsIn = in_range_mask(w0, M.rows, 32);
     colsIn = in_range_mask(w1, M.cols, G.WIN);
-    if (PAD && pend) {
+    if (HEADING && !PAD) {
+      // rotated rectangle on the packed plane layouts: the owning lane builds the finished "bad cell" masks
+      // (finite & (below the candidate threshold | centre outside the polygon)) into plane 3 of its slot
+      const int rp = 1 << G.rpShift;  // rows per packed column (32 / pack)
+      const uint32_t rm = rp >= 32 ? 0xffffffffu : ((1u << rp) - 1u);
+      for (int k = 0; k < G.nIter; ++k) {
+        uint32_t word = 0u;
+        for (int c = 0; c < G.pack; ++c) {
+          const int b = k * G.pack + c;
+          if (b >= G.WIN) break;
+          const uint32_t inside = poly_col_rows(M, P, rx, ry, w0, G.winRows, w1 + b);
+          const uint32_t bad = pl.col(PL_F, b) & (pl.col(PL_C, b) | ~inside) & rm;
+          word |= bad << (c * rp);
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(k * 4 + 3) * 4u), "r"(word) : "memory");
+      }
+    }
+    if (PAD && (pend || HEADING)) {
       // The owning lane turns its planes into per-column "bad cell" masks once (left in the pad word of each column
       // entry for the cooperative scan) and, for a single-cell foot stencil, settles the two most common outcomes
       // itself: no acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
@@ -1165,27 +1250,30 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
       uint32_t anyOk = 0, okCentre = 0;
       for (int b = 0; b < G.WIN; ++b) {
         const uint4 e = lds_v4(mine + static_cast<uint32_t>(b) * 16u);  // {D, C, F, pad} of column b (pack = 1 layout)
-        const uint32_t box = ((colsBox >> b) & 1u) ? rowsBox : 0u;
+        const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows, w1 + b)
+                                     : (((colsBox >> b) & 1u) ? rowsBox : 0u);
         const uint32_t bad = e.z & (e.y | ~box);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(b * 4 + 3) * 4u), "r"(bad) : "memory");
         const uint32_t okb = ((colsIn >> b) & 1u) ? ((G.candRows[b] << sh) & ~bad & rowsIn) : 0u;
         anyOk |= okb;
         if (b == G.HW) okCentre = okb;
       }
-      if (G.lastTwoStart > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
-        found = true;
-        fq0 = uc0;
-        fq1 = uc1;
+      if (pend) {
+        if (G.lastTwoStart > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
+          found = true;
+          fq0 = uc0;
+          fq1 = uc1;
+        }
+        if (G.nSten == 1 && (found || anyOk == 0u)) pend = false;
+        if (G.nSten > 1) found = false;  // the shortcuts need the dilated masks
       }
-      if (G.nSten == 1 && (found || anyOk == 0u)) pend = false;
-      if (G.nSten > 1) found = false;  // the shortcuts need the dilated masks
     }
   }
-  if (PAD) __syncwarp();  // pad words visible to the cooperating lanes
-  spiral_scan_coop<PAD>(M, G, sSpiral, smemWarp, lane, pend, uc0, uc1, w0, cx, cy, P.R2, rowsBox, colsBox, rowsIn, colsIn,
-                        found, fq0, fq1);
+  if (PAD || HEADING) __syncwarp();  // pad words visible to the cooperating lanes
+  spiral_scan_coop<PAD, HEADING>(M, G, sSpiral, smemWarp, lane, pend, uc0, uc1, w0, cx, cy, P.R2, rowsBox, colsBox, rowsIn,
+                                 colsIn, found, fq0, fq1);
   if (need && faithful)
-    spiral_scan_faithful(M, G, sSpiral, pl, P.thrC, uc0, uc1, w0, cx, cy, P.R2, bx, rowsBox, colsBox, found, fq0, fq1);
+    spiral_scan_faithful<HEADING>(M, G, P, sSpiral, pl, uc0, uc1, w0, cx, cy, P.R2, bx, rowsBox, colsBox, found, fq0, fq1);
   if (found) {
     o.ok = true;
     o.x = pos_axis(M.fcx, M.res, fq0);  // gridmap.getPosition(index) (FP.cpp:2105-2107)

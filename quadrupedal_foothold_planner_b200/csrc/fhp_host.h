@@ -42,7 +42,7 @@ struct TaskArgs {
   unsigned* err;
 };
 
-cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream);
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, cudaStream_t stream);
 long long plan_wave_queries(const GeoDev& G, bool wantCen);
 cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, unsigned* flags,
                               cudaStream_t stream);

@@ -71,7 +71,7 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
 #define FHP_PLAN_MIN_BLOCKS_MASK 7
 #endif
-template <bool WANT_CEN, int STAGE, bool WANT_DEF>
+template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING>
 __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem_raw[];
@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
 
   // initialize() stance (FP.cpp:350-378) and setFirstGait (FP.cpp:2679-2699) for both chains
   const double stx = P.stancex[f] + qu.x, sty = P.stancey[f] + qu.y, stz = 0.0 + qu.z;
-  double nomx = stx - P.halfStep, nomy = sty;
+  // (HEADING: half a step back along the heading; include/fhp.h fhp_params.heading)
+  double nomx = stx - (HEADING ? P.halfStepX : P.halfStep), nomy = HEADING ? sty - P.halfStepY : sty;
   double cenx = nomx, ceny = nomy;
   double defx = nomx, defy = nomy;  // default chain: setFirstGait too (FP.cpp:562)
   if (active) {  // FP.cpp:685-699 (and :713-727 for the centroid message, :666-671 for the default chain)
@@ -152,6 +153,9 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
                    shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
                    ncx, ncy);
     const double nextY = qu.y + adjY;                                 // :2201
+    // HEADING: next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n — forward coordinate from the stance centroid,
+    // lateral coordinate pinned to the initial pose plus the drift (reduces bit-exactly to :2199-2201 at cos 1, sin 0)
+    const double hLat = HEADING ? (qu.y * P.ch - qu.x * P.sh) + adjY : 0.0;
     // (per-leg bias and thresholds are re-read from the parameter table each cycle: L1 hits, fewer live registers)
     const double bx = P.biasx[f], by = P.biasy[f];
     double dnx = 0.0, dny = 0.0, dnz = 0.0;                           // getDefaultFootholds (FP.cpp:2253-2304)
@@ -160,12 +164,25 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
       polygon_center(shfl_d(defx, quad0), shfl_d(defy, quad0), shfl_d(defx, quad0 + 1), shfl_d(defy, quad0 + 1),
                      shfl_d(defx, quad0 + 2), shfl_d(defy, quad0 + 2), shfl_d(defx, quad0 + 3), shfl_d(defy, quad0 + 3),
                      dcx, dcy);
-      dnx = (dcx + P.stepLength) + bx;
-      dny = nextY + by;
+      if (HEADING) {
+        const double fwd = (dcx * P.ch + dcy * P.sh) + P.stepLength;
+        dnx = (fwd * P.ch - hLat * P.sh) + bx;
+        dny = (fwd * P.sh + hLat * P.ch) + by;
+      } else {
+        dnx = (dcx + P.stepLength) + bx;
+        dny = nextY + by;
+      }
       if (active) dnz = static_cast<double>(mean_height(M, G, P, dnx, dny));
     }
-    const double px = (ccx + P.stepLength) + bx, py = nextY + by;     // centroid-chain next foothold (:2199,:2414)
-    const double rx = (ncx + P.stepLength) + bx, ry = nextY + by;     // nominal-chain next foothold = rectangle centre
+    double px = (ccx + P.stepLength) + bx, py = nextY + by;           // centroid-chain next foothold (:2199,:2414)
+    double rx = (ncx + P.stepLength) + bx, ry = nextY + by;           // nominal-chain next foothold = rectangle centre
+    if (HEADING) {
+      const double fwdC = (ccx * P.ch + ccy * P.sh) + P.stepLength, fwdN = (ncx * P.ch + ncy * P.sh) + P.stepLength;
+      px = (fwdC * P.ch - hLat * P.sh) + bx;
+      py = (fwdC * P.sh + hLat * P.ch) + by;
+      rx = (fwdN * P.ch - hLat * P.sh) + bx;
+      ry = (fwdN * P.sh + hLat * P.ch) + by;
+    }
 
     // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
     const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
@@ -212,7 +229,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     __syncthreads();
 #endif
     const NominalOut no =
-        nominal_eval<false, STAGE == kStageMask>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
+        nominal_eval<false, STAGE == kStageMask, HEADING>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
     const bool ok = no.ok;
 #if FHP_SYNC_LEVEL >= 3
     __syncthreads();
@@ -298,8 +315,8 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   }
   if (MODE == 5) {
     if (active) {
-      const Box b = search_box(P, rx, ry);
-      A.valid[i] = circle_polygon_direct(M, P, px, py, b.xlo, b.xhi, b.ylo, b.yhi) ? 1 : 0;
+      const Box b = P.heading ? centre_box(rx, ry) : search_box(P, rx, ry);
+      A.valid[i] = circle_polygon_direct(M, P, px, py, b) ? 1 : 0;
     }
     return;
   }
@@ -312,10 +329,12 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     if (active) dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
     NominalOut no;
     const bool okDef = (MODE != 4) && active && default_eval(M, G, P, pl, w0, w1, px, py, dw, err);
-    if (MODE == 0 || MODE == 4)
-      no = nominal_eval<false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
+    if (MODE == 3)
+      no = nominal_eval<true, false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
+    else if (P.heading)  // uniform: one parameter set per task launch
+      no = nominal_eval<false, false, true>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     else
-      no = nominal_eval<true, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
+      no = nominal_eval<false, false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     if (active) {
       if (MODE == 0) {
         double z = 0.0;
@@ -500,26 +519,33 @@ cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st,
 
 typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
 // the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
-template <int STAGE>
+template <int STAGE, bool HEADING>
 static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef) {
-  if (wantDef) return plan_kernel<true, STAGE, true>;
-  return wantCen ? plan_kernel<true, STAGE, false> : plan_kernel<false, STAGE, false>;
+  if (wantDef) return plan_kernel<true, STAGE, true, HEADING>;
+  return wantCen ? plan_kernel<true, STAGE, false, HEADING> : plan_kernel<false, STAGE, false, HEADING>;
 }
-static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef) {
-  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask>(wantCen, wantDef);
-  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma>(wantCen, wantDef);
-  return pick_plan_kernel_s<kStageLdg>(wantCen, wantDef);
+// heading: some parameter set of the call carries a non-zero heading -> the variant with the rotated expressions
+// (the reference-shaped variant stays exactly what it was)
+static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading) {
+  if (heading) {
+    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef);
+    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef);
+    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef);
+  }
+  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef);
+  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef);
+  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef);
 }
 
 // ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
-cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaStream_t stream) {
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, cudaStream_t stream) {
   if (A.nq <= 0) return cudaSuccess;
   const int warps = kPlanThreads / 32;
   const int qpw = 1 << A.qpwShift;
   const long long nWarps = (A.nq + qpw - 1) / qpw;
   const long long blocks = (nWarps + warps - 1) / warps;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
@@ -532,7 +558,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, cudaSt
 // the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
 // a wave takes as long as a full one).
 long long plan_wave_queries(const GeoDev& G, bool wantCen) {
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false);
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
   if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
   int perSm = 0, dev = 0, sms = 0;

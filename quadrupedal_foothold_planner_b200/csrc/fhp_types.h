@@ -72,7 +72,12 @@ struct ParDev {  // one per fhp_params, derived on the host exactly as FootholdP
   double h, drift;
   float thrD, thrC;
   int spiralMode;
-  int pad;
+  int heading;                    // 1: fhp_params.heading != 0 (the rotated expressions below are in force)
+  // heading extension (include/fhp.h); stance and bias above are already rotated.  With heading == 0
+  // these hold cos = 1, sin = 0 and the reference's own offsets, and every rotated expression reduces bit-exactly.
+  double ch, sh;                  // cos / sin of the heading
+  double halfStepX, halfStepY;    // halfStep * ch, halfStep * sh (setFirstGait steps half a step back along u)
+  double rectVx[4], rectVy[4];    // rot() of getSearchPolygon's vertex offsets (+R,+R/2) (+R,-R/2) (-R,-R/2) (-R,+R/2)
 };
 
 }  // namespace fhp

@@ -184,21 +184,30 @@ def config_c5(n_queries=262144, rows=16000, cols=16000, seed_map=6, seed_q=7, st
     return m, q, 32
 
 
-def config_c4(n_poses=64, n_steps=64, rows=1500, cols=1500, seed_map=5, seed_q=6):
-    """The heading-0 slice of BASELINE config 4: {trot, walk} x n_steps step lengths in [0.10, 0.26] (skew =
-    stepLength/4, yaml:44) x n_poses start poses, 8 cycles, on a C3-style rough map with start index (0,0).
-    -> (map, params list [2*n_steps], queries [2*n_steps*n_poses] with param_id, cycles).
-    The heading sweep itself is an extension the reference does not have (the body always advances along +x,
-    FP.cpp:2199-2202) and is not implemented."""
+def config_c4(n_poses=64, n_steps=64, rows=1500, cols=1500, seed_map=5, seed_q=6, n_headings=1, with_map=True):
+    """BASELINE config 4: {trot, walk} x n_steps step lengths in [0.10, 0.26] (skew = stepLength/4, yaml:44) x
+    n_headings headings in [0, 2 pi) x n_poses start poses, 8 cycles, on a C3-style rough map with start index (0,0).
+    -> (map, params list [2*n_steps*n_headings], queries [len(params)*n_poses] with param_id, cycles); parameter set
+    index = (gait*n_steps + step)*n_headings + heading.  n_headings = 1 is the heading-0 slice, which is the
+    reference's own behaviour (the body always advances along +x, FP.cpp:2199-2202); the heading sweep is the
+    extension defined by fhp_params.heading.  with_map=False returns the geometry only."""
     from ._abi import FHP_GAIT_TROT, FHP_GAIT_WALK, yaml_params
-    m = rough_map(rows, cols, 0.02, seed=seed_map, start=(0, 0))
+    if with_map:
+        m = rough_map(rows, cols, 0.02, seed=seed_map, start=(0, 0))
+    else:
+        m = HostMap(rows, cols, 0.02, (0.0, 0.0), (0, 0))
     params = []
     for gait in (FHP_GAIT_TROT, FHP_GAIT_WALK):
         for sl in np.linspace(0.10, 0.26, n_steps):
             sl32 = float(np.float32(sl))
-            params.append(yaml_params(gait=gait, step_length=sl32, skew=float(np.float32(sl32 / 4))))
+            for k in range(n_headings):
+                params.append(yaml_params(gait=gait, step_length=sl32, skew=float(np.float32(sl32 / 4)),
+                                          heading=2.0 * np.pi * k / n_headings))
     half = rows * 0.02 / 2
-    poses = uniform_queries(n_poses, (-half + 1.0, half - 3.5), (-half + 1.0, half - 1.0), seed=seed_q)
+    # 8 cycles advance <= 2.1 m in the heading direction; keep every window >= 0.5 m inside the map
+    lo, hi = (-half + 1.0, half - 3.5) if n_headings == 1 else (-half + 3.5, half - 3.5)
+    ylo, yhi = (-half + 1.0, half - 1.0) if n_headings == 1 else (lo, hi)
+    poses = uniform_queries(n_poses, (lo, hi), (ylo, yhi), seed=seed_q)
     q = np.tile(poses, len(params))
     q["param_id"] = np.repeat(np.arange(len(params), dtype=np.int32), n_poses)
     return m, params, q, 8
