@@ -234,6 +234,22 @@ typedef struct fhp_foothold_packed {
 int fhp_plan_compact_packed(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
                             int64_t n_queries, int32_t gait_cycles, fhp_foothold_packed* out_rows,
                             int64_t capacity_rows, int64_t* row_offsets, fhp_query_status* status);
+/* The compact response with 24-byte rows: exactly the fields of foothold_planner_msgs/Foothold (msg/Foothold.msg:1-3) —
+ * point, foot_id, gait_cycle_id — plus `kind`.  z travels as the float it is by construction (getFootholdMeanHeight
+ * returns float, FP.cpp:2553; stance rows carry (float)initial z, exact for the reference's z = 0 poses and within
+ * float rounding otherwise); the grid cell of a row is a pure function of (x, y) and the map geometry and is not
+ * sent.  40 % fewer PCIe bytes than fhp_foothold; no host-side expansion is needed to fill the message. */
+typedef struct fhp_foothold24 {
+  double x, y;
+  float z;
+  uint8_t foot_id;
+  uint8_t gait_cycle_id;
+  uint8_t kind;
+  uint8_t reserved;
+} fhp_foothold24;
+int fhp_plan_compact24(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                       int64_t n_queries, int32_t gait_cycles, fhp_foothold24* out_rows, int64_t capacity_rows,
+                       int64_t* row_offsets, fhp_query_status* status);
 /* KPIs the reference logs per successful cycle (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623): pure
  * host-side functions of ONE query's response rows (nominal or centroid chain).  feet_distance / cog_speed receive
  * 2 values per successful cycle (n_rows/4 - 1 cycles). */

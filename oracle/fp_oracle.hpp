@@ -56,7 +56,8 @@ struct Params {
   //   u = (cos, sin) forward, n = (-sin, cos) lateral;  rot(v) = (v.x*cos - v.y*sin, v.x*sin + v.y*cos)
   //   stance, bias table and the four rectangle vertex offsets are rot() of the reference's values;
   //   setFirstGait: cur = init - (stepLength/2) u;
-  //   next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n   — the forward coordinate comes from the stance
+  //   next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n  (terms with an exactly zero sin are dropped, see
+  //   headingNextCenter) — the forward coordinate comes from the stance
   //   centroid c, the lateral one is pinned to the initial pose p0 plus the drift, exactly as FP.cpp:2199-2201 does
   //   for u = +x;  the centroid method keeps its axis-aligned getSubmap window (grid_map cuts no rotated submaps).
   double heading = 0.0;
@@ -181,13 +182,16 @@ class Planner {
     }
   }
 
+  static double mulz(double a, double t) { return t == 0.0 ? 0.0 : a * t; }
   // heading: the next stance centre from the current stance centroid (see Params::heading)
   Point headingNextCenter(const Point& polygonCenter) const {
     Point n;
-    const double fwd = (polygonCenter.x * ch + polygonCenter.y * sh) + p.stepLength;
-    const double lat = (initialPose[1] * ch - initialPose[0] * sh) + ajustedPoseY;
-    n.x = fwd * ch - lat * sh;
-    n.y = fwd * sh + lat * ch;
+    // mulz: a term whose trigonometric factor is exactly zero is dropped (not multiplied), so theta = 0 reproduces
+    // FP.cpp:2199-2201 even when the stance centroid is not finite (a degenerate stance polygon divides by a zero area)
+    const double fwd = (polygonCenter.x * ch + mulz(polygonCenter.y, sh)) + p.stepLength;
+    const double lat = (initialPose[1] * ch - mulz(initialPose[0], sh)) + ajustedPoseY;
+    n.x = fwd * ch - mulz(lat, sh);
+    n.y = mulz(fwd, sh) + lat * ch;
     n.z = polygonCenter.z;
     return n;
   }

@@ -68,10 +68,16 @@ FOOTHOLD_PACKED_DTYPE = np.dtype([  # fhp_foothold_packed (32 bytes)
     ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("row", "<u2"), ("col", "<u2"),
     ("foot_id", "u1"), ("gait_cycle_id", "u1"), ("kind", "u1"), ("reserved", "u1"),
 ])
+FOOTHOLD24_DTYPE = np.dtype([  # fhp_foothold24 (24 bytes): the Foothold message fields
+    ("x", "<f8"), ("y", "<f8"), ("z", "<f4"), ("foot_id", "u1"), ("gait_cycle_id", "u1"), ("kind", "u1"), ("reserved", "u1"),
+])
 STATUS_DTYPE = np.dtype([("success", "u1"), ("gait_cycles", "u1"), ("gait_cycles_succeed", "u1"), ("reserved", "u1"),
                          ("n_rows", "<i4")])
 assert QUERY_DTYPE.itemsize == 32 and FOOTHOLD_DTYPE.itemsize == 40 and STATUS_DTYPE.itemsize == 8
-assert FOOTHOLD_PACKED_DTYPE.itemsize == 32
+assert FOOTHOLD_PACKED_DTYPE.itemsize == 32 and FOOTHOLD24_DTYPE.itemsize == 24
+# fhp_query_status.reserved: low bits = kernel error bits (any set bit fails the call), 0x80 = FHP_STATUS_OPT_SUBMAP_FAIL
+FHP_STATUS_ERR_MASK = 0x7F
+FHP_STATUS_OPT_SUBMAP_FAIL = 0x80
 
 
 def rows_per_query(gait_cycles: int) -> int:

@@ -1078,13 +1078,19 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
 // Chunk i plans, scans its n_rows and packs its rows on one of two streams while the packed rows of chunk i-1 cross
 // PCIe on the copy stream; the host learns each chunk's row count from a pinned word before it issues that copy.
 static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
-                             int64_t n_queries, int32_t gait_cycles, void* out_rows, bool packed, int64_t capacity_rows,
+                             int64_t n_queries, int32_t gait_cycles, void* out_rows, int fmt, int64_t capacity_rows,
                              int64_t* row_offsets, fhp_query_status* status);
 
 int fhp_plan_compact(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
                      int32_t gait_cycles, fhp_foothold* out_rows, int64_t capacity_rows, int64_t* row_offsets,
                      fhp_query_status* status) {
-  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, false, capacity_rows,
+  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, 40, capacity_rows,
+                           row_offsets, status);
+}
+int fhp_plan_compact24(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                       int64_t n_queries, int32_t gait_cycles, fhp_foothold24* out_rows, int64_t capacity_rows,
+                       int64_t* row_offsets, fhp_query_status* status) {
+  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, 24, capacity_rows,
                            row_offsets, status);
 }
 int fhp_plan_compact_packed(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
@@ -1092,12 +1098,12 @@ int fhp_plan_compact_packed(fhp_ctx* ctx, const fhp_params* params, int32_t n_pa
                             int64_t* row_offsets, fhp_query_status* status) {
   if (ctx && ctx->haveMap && (ctx->M.rows > 65534 || ctx->M.cols > 65534))
     return fail(ctx, FHP_ERR_UNSUPPORTED, "packed rows hold the cell index as uint16: map has more than 65534 rows or columns");
-  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, true, capacity_rows,
+  return plan_compact_impl(ctx, params, n_params, queries, n_queries, gait_cycles, out_rows, 32, capacity_rows,
                            row_offsets, status);
 }
 
 static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
-                             int64_t n_queries, int32_t gait_cycles, void* out_rows, bool packed, int64_t capacity_rows,
+                             int64_t n_queries, int32_t gait_cycles, void* out_rows, int fmt, int64_t capacity_rows,
                              int64_t* row_offsets, fhp_query_status* status) {
   if (!ctx) return FHP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1166,7 +1172,7 @@ static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_p
     CU(cudaMemcpyAsync(dq + lo, queries + lo, sizeof(fhp_query) * n, cudaMemcpyHostToDevice, cs));
     rc = plan_launch(ctx, n_params, dq + lo, n, gait_cycles, dN + lo * R, nullptr, dS + lo, cs);
     if (rc != FHP_OK) return rc;
-    CU(launch_compact(dN + lo * R, dS + lo, n, static_cast<int>(R), offs, dC + lo * R, packed, ctx->dTotals + c, cs));
+    CU(launch_compact(dN + lo * R, dS + lo, n, static_cast<int>(R), offs, dC + lo * R, fmt, ctx->dTotals + c, cs));
     ctx->launches += 2;
     CU(cudaEventRecord(ctx->chunkEv[c], cs));
   }
@@ -1176,7 +1182,7 @@ static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_p
   int64_t base = 0;
   int err = FHP_OK;
   std::vector<int64_t> bases(static_cast<size_t>(nChunks), 0);
-  const size_t rowB = packed ? sizeof(fhp_foothold_packed) : sizeof(fhp_foothold);
+  const size_t rowB = fmt == 24 ? sizeof(fhp_foothold24) : (fmt == 32 ? sizeof(fhp_foothold_packed) : sizeof(fhp_foothold));
   for (int64_t c = 0; c < nChunks; ++c) {
     const int64_t lo = chunkLo[static_cast<size_t>(c)], n = chunkN[static_cast<size_t>(c)];
     cudaStream_t cs = (c & 1) ? ctx->stream2 : ctx->stream;
@@ -1389,10 +1395,11 @@ int fhp_search_geometry(const fhp_params* params, const fhp_query* query, double
   double ncx = center_xyz[0] + d.stepLength;  // :2199
   double ncy = query->y + adjusted_y;         // :2201
   if (d.heading) {  // heading extension (fhp_params.heading): forward coordinate from the centroid, lateral one pinned
-    const double fwd = (center_xyz[0] * d.ch + center_xyz[1] * d.sh) + d.stepLength;
-    const double lat = (query->y * d.ch - query->x * d.sh) + adjusted_y;
-    ncx = fwd * d.ch - lat * d.sh;
-    ncy = fwd * d.sh + lat * d.ch;
+    auto mulz = [](double a, double t) { return t == 0.0 ? 0.0 : a * t; };  // an exactly zero sin drops its term
+    const double fwd = (center_xyz[0] * d.ch + mulz(center_xyz[1], d.sh)) + d.stepLength;
+    const double lat = (query->y * d.ch - mulz(query->x, d.sh)) + adjusted_y;
+    ncx = fwd * d.ch - mulz(lat, d.sh);
+    ncy = mulz(fwd, d.sh) + lat * d.ch;
   }
   for (int f = 0; f < 4; ++f) {
     const double nx = ncx + d.biasx[f], ny = ncy + d.biasy[f];

@@ -47,7 +47,7 @@ long long plan_wave_queries(const GeoDev& G, bool wantCen);
 cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, unsigned* flags,
                               cudaStream_t stream);
 cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st, long long n, int R, long long* offs,
-                           void* out, bool packed, long long* hostTotal, cudaStream_t stream);
+                           void* out, int fmt, long long* hostTotal, cudaStream_t stream);
 cudaError_t launch_task(int mode, const TaskArgs& A, const GeoDev& G, cudaStream_t stream);
 
 }  // namespace fhp

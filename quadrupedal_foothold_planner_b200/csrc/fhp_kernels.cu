@@ -14,6 +14,7 @@
 namespace fhp {
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+__device__ __forceinline__ double mulz(double a, double t) { return t == 0.0 ? 0.0 : a * t; }
 
 // FootholdPlanner::getPolygonCenter (FP.cpp:2421-2463), xy only (z never reaches the response).
 __device__ __forceinline__ void polygon_center(double rfx, double rfy, double rhx, double rhy, double lhx, double lhy,
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     const double nextY = qu.y + adjY;                                 // :2201
     // HEADING: next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n — forward coordinate from the stance centroid,
     // lateral coordinate pinned to the initial pose plus the drift (reduces bit-exactly to :2199-2201 at cos 1, sin 0)
-    const double hLat = HEADING ? (qu.y * P.ch - qu.x * P.sh) + adjY : 0.0;
+    // (mulz drops a term whose sin factor is exactly zero: theta = 0 then equals the reference for non-finite centroids too)
+    const double hLat = HEADING ? (qu.y * P.ch - mulz(qu.x, P.sh)) + adjY : 0.0;
     // (per-leg bias and thresholds are re-read from the parameter table each cycle: L1 hits, fewer live registers)
     const double bx = P.biasx[f], by = P.biasy[f];
     double dnx = 0.0, dny = 0.0, dnz = 0.0;                           // getDefaultFootholds (FP.cpp:2253-2304)
@@ -165,9 +167,9 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
                      shfl_d(defx, quad0 + 2), shfl_d(defy, quad0 + 2), shfl_d(defx, quad0 + 3), shfl_d(defy, quad0 + 3),
                      dcx, dcy);
       if (HEADING) {
-        const double fwd = (dcx * P.ch + dcy * P.sh) + P.stepLength;
-        dnx = (fwd * P.ch - hLat * P.sh) + bx;
-        dny = (fwd * P.sh + hLat * P.ch) + by;
+        const double fwd = (dcx * P.ch + mulz(dcy, P.sh)) + P.stepLength;
+        dnx = (fwd * P.ch - mulz(hLat, P.sh)) + bx;
+        dny = (mulz(fwd, P.sh) + hLat * P.ch) + by;
       } else {
         dnx = (dcx + P.stepLength) + bx;
         dny = nextY + by;
@@ -177,11 +179,12 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     double px = (ccx + P.stepLength) + bx, py = nextY + by;           // centroid-chain next foothold (:2199,:2414)
     double rx = (ncx + P.stepLength) + bx, ry = nextY + by;           // nominal-chain next foothold = rectangle centre
     if (HEADING) {
-      const double fwdC = (ccx * P.ch + ccy * P.sh) + P.stepLength, fwdN = (ncx * P.ch + ncy * P.sh) + P.stepLength;
-      px = (fwdC * P.ch - hLat * P.sh) + bx;
-      py = (fwdC * P.sh + hLat * P.ch) + by;
-      rx = (fwdN * P.ch - hLat * P.sh) + bx;
-      ry = (fwdN * P.sh + hLat * P.ch) + by;
+      const double fwdC = (ccx * P.ch + mulz(ccy, P.sh)) + P.stepLength, fwdN = (ncx * P.ch + mulz(ncy, P.sh)) + P.stepLength;
+      const double latS = mulz(hLat, P.sh), latC = hLat * P.ch;
+      px = (fwdC * P.ch - latS) + bx;
+      py = (mulz(fwdC, P.sh) + latC) + by;
+      rx = (fwdN * P.ch - latS) + bx;
+      ry = (mulz(fwdN, P.sh) + latC) + by;
     }
 
     // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
@@ -474,9 +477,10 @@ __global__ void __launch_bounds__(1024) scan_rows_kernel(const fhp_query_status*
   }
 }
 
-// One warp per query: its n_rows rows move from the fixed-pitch plan output to out + offs[q] — as they are (40 bytes =
-// five 8-byte words each) or PACKED to 32 bytes (x, y, z, then row/col as uint16 and the three id bytes in one word).
-template <bool PACKED>
+// One warp per query: its n_rows rows move from the fixed-pitch plan output to out + offs[q] — as they are (FMT 40: five
+// 8-byte words each), PACKED to 32 bytes (FMT 32: x, y, z, then row/col as uint16 and the three id bytes in one word) or
+// as the 24-byte message row (FMT 24: x, y, then z as float32 — it is one by construction, FP.cpp:2553 — and the id bytes).
+template <int FMT>
 __global__ void __launch_bounds__(256) compact_rows_kernel(const fhp_foothold* __restrict__ rows,
                                                            const long long* __restrict__ offs, long long n, int R,
                                                            void* __restrict__ out) {
@@ -486,10 +490,10 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const fhp_foothold* _
   const long long o = offs[q];
   const int nr = static_cast<int>(offs[q + 1] - o);
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(rows + q * R);
-  if (!PACKED) {
+  if (FMT == 40) {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(static_cast<fhp_foothold*>(out) + o);
     for (int w = lane; w < nr * 5; w += 32) dst[w] = src[w];
-  } else {
+  } else if (FMT == 32) {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(static_cast<fhp_foothold_packed*>(out) + o);
     for (int w = lane; w < nr * 4; w += 32) {
       const int r = w >> 2, k = w & 3;
@@ -502,18 +506,33 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const fhp_foothold* _
       }
       dst[w] = v;
     }
+  } else {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(static_cast<fhp_foothold24*>(out) + o);
+    for (int w = lane; w < nr * 3; w += 32) {
+      const int r = w / 3, k = w - 3 * r;
+      unsigned long long v;
+      if (k < 2) {
+        v = src[r * 5 + k];
+      } else {
+        const float z = static_cast<float>(__longlong_as_double(static_cast<long long>(src[r * 5 + 2])));
+        v = static_cast<unsigned long long>(__float_as_uint(z)) | ((src[r * 5 + 4] & 0xffffffull) << 32);
+      }
+      dst[w] = v;
+    }
   }
 }
 
 cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st, long long n, int R, long long* offs,
-                           void* out, bool packed, long long* hostTotal, cudaStream_t stream) {
+                           void* out, int fmt, long long* hostTotal, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   scan_rows_kernel<<<1, 1024, 0, stream>>>(st, n, offs, hostTotal);
   const unsigned nb = static_cast<unsigned>((n + 7) / 8);
-  if (packed)
-    compact_rows_kernel<true><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
+  if (fmt == 32)
+    compact_rows_kernel<32><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
+  else if (fmt == 24)
+    compact_rows_kernel<24><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
   else
-    compact_rows_kernel<false><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
+    compact_rows_kernel<40><<<nb, 256, 0, stream>>>(rows, offs, n, R, out);
   return cudaGetLastError();
 }
 

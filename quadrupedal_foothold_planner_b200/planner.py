@@ -69,6 +69,7 @@ def load_lib():
     L.fhp_cycle_kpi.argtypes = [vp, vp, vp, i32, vp, vp]
     L.fhp_plan_compact.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
     L.fhp_plan_compact_packed.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
+    L.fhp_plan_compact24.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
     L.fhp_plan_device.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp, vp]
     L.fhp_synchronize.argtypes = [vp]
     L.fhp_check_foothold.argtypes = [vp, vp, vp, vp, i64, vp, vp]
@@ -202,26 +203,32 @@ class Fhp:
                                        C.cast(C.pointer(out), C.c_void_p)))
         return nom, cen, dfl, st
 
+    def _compact_fn(self, packed=False, fmt=None):
+        fmt = fmt or (32 if packed else 40)
+        return {40: (self.L.fhp_plan_compact, FOOTHOLD_DTYPE), 32: (self.L.fhp_plan_compact_packed, _abi.FOOTHOLD_PACKED_DTYPE),
+                24: (self.L.fhp_plan_compact24, _abi.FOOTHOLD24_DTYPE)}[fmt]
+
     def plan_compact(self, params, queries: np.ndarray, gait_cycles: int, capacity_rows: Optional[int] = None,
-                     packed: bool = False):
-        """fhp_plan_compact / fhp_plan_compact_packed: -> (rows [total], row_offsets [nq+1], status [nq]); query q owns
-        rows[row_offsets[q]:row_offsets[q+1]] (the service's variable-length footholds[]).  packed: 32-byte rows."""
+                     packed: bool = False, fmt: Optional[int] = None):
+        """fhp_plan_compact / _packed / 24: -> (rows [total], row_offsets [nq+1], status [nq]); query q owns
+        rows[row_offsets[q]:row_offsets[q+1]] (the service's variable-length footholds[]).  packed: 32-byte rows;
+        fmt = 24: the 24-byte message rows."""
         parr, npar = self._params_array(params)
         q = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
         nq = len(q)
         cap = nq * rows_per_query(max(0, min(255, int(gait_cycles)))) if capacity_rows is None else int(capacity_rows)
-        rows = np.zeros(max(cap, 1), dtype=_abi.FOOTHOLD_PACKED_DTYPE if packed else FOOTHOLD_DTYPE)
+        fn, dt = self._compact_fn(packed, fmt)
+        rows = np.zeros(max(cap, 1), dtype=dt)
         offs = np.zeros(nq + 1, dtype=np.int64)
         st = np.zeros(nq, dtype=STATUS_DTYPE)
-        fn = self.L.fhp_plan_compact_packed if packed else self.L.fhp_plan_compact
         self._check(fn(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q), nq, int(gait_cycles),
                                             _ptr(rows), cap, _ptr(offs), _ptr(st)))
         return rows[:offs[nq]], offs, st
 
     def plan_compact_raw(self, parr, npar, q_ptr, nq, gait_cycles, rows_ptr, capacity_rows, offs_ptr, st_ptr,
-                         packed: bool = False):
-        """fhp_plan_compact[_packed] on raw host addresses (pinned torch buffers in bench.py)."""
-        fn = self.L.fhp_plan_compact_packed if packed else self.L.fhp_plan_compact
+                         packed: bool = False, fmt: Optional[int] = None):
+        """fhp_plan_compact[_packed|24] on raw host addresses (pinned torch buffers in bench.py)."""
+        fn, _ = self._compact_fn(packed, fmt)
         self._check(fn(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q_ptr), nq, int(gait_cycles),
                                             _ptr(rows_ptr), int(capacity_rows), _ptr(offs_ptr), _ptr(st_ptr)))
 

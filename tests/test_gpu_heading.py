@@ -40,7 +40,9 @@ def test_c4_full_sweep_vs_oracle(fhp, oracle):
     last_y = np.stack([got[0]["y"][idx, np.maximum(n - 4 + k, 0)] for k in range(4)], 1).mean(1)
     dx, dy = last_x - got[0]["x"][:, :4].mean(1), last_y - got[0]["y"][:, :4].mean(1)
     along = dx * np.cos(hd) + dy * np.sin(hd)
-    assert ok.sum() > 1000 and np.all(along[ok] > 0.2)
+    # (not every plan: a centroid window whose rows are all "edges" leaves that chain's foot at (0,0,0), FP.cpp:810-813,
+    # and the reference then searches around a stance centroid dragged towards the origin — kept bit for bit)
+    assert ok.sum() > 1000 and np.median(along[ok]) > 0.5 and np.mean(along[ok] > 0.2) > 0.7
 
 
 @pytest.mark.parametrize("res,start,mode", [(0.02, (0, 0), _abi.FHP_SPIRAL_WRAP_CORRECT),

@@ -337,6 +337,17 @@ def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
         assert np.array_equal(pr[f], rows[f])
     assert np.array_equal(pr["row"], (rows["row"] & 0xFFFF).astype(np.uint16))
     assert np.array_equal(pr["col"], (rows["col"] & 0xFFFF).astype(np.uint16))
+    # 24-byte message rows: point (z as the float it is by construction), foot_id, gait_cycle_id, kind
+    r24, o24, s24 = fhp.plan_compact(p, q, 12, fmt=24)
+    assert np.array_equal(o24, offs) and np.array_equal(s24, st) and r24.dtype.itemsize == 24
+    for f in ("x", "y", "foot_id", "gait_cycle_id", "kind"):
+        assert np.array_equal(r24[f], rows[f])
+    assert np.array_equal(r24["z"].astype(np.float64), rows["z"])  # lossless: every z is a float32 value
+    big = synth.uniform_queries(50000, (-10.0, 7.0), (-10.0, 10.0), seed=77)  # several chunks
+    rb, ob_, sb = fhp.plan_compact(p, big, 12)
+    r24, o24, s24 = fhp.plan_compact(p, big, 12, fmt=24)
+    assert np.array_equal(o24, ob_) and np.array_equal(s24, sb)
+    assert np.array_equal(r24["x"], rb["x"]) and np.array_equal(r24["z"].astype(np.float64), rb["z"])
 
 
 @pytest.mark.parametrize("foot_radius", [0.031, 0.05, 0.085])
