@@ -114,9 +114,19 @@ typedef struct fhp_query_status {
   uint8_t success;             /* outcome of the LAST cycle, FP.cpp:1380 / :1574 */
   uint8_t gait_cycles;         /* the request, FP.cpp:592-593 */
   uint8_t gait_cycles_succeed; /* index+1 of the last successful cycle, FP.cpp:1379 */
-  uint8_t reserved;
+  uint8_t reserved;            /* flags: FHP_STATUS_* below */
   int32_t n_rows;              /* rows written for this query: 4 + 4*(successful cycles) */
 } fhp_query_status;
+
+/* fhp_query_status.reserved: the low 7 bits are kernel error bits (never set in a call that returned FHP_OK).
+ * FHP_STATUS_OPT_SUBMAP_FAIL: the reference would have ABORTED this service call at gait cycle 0 (`return false`,
+ * FP.cpp:931-934) because the gait-cycle submap of its third, NLopt-driven "opt" chain (getGaitCycleSearchGridMap
+ * FP.cpp:2307-2350, rect = isos_.length x isos_.width around the next stance centre) does not fit the map.  libfhp does
+ * not run that chain; at cycle 0 its state is still the first-gait stance, so the predicate is exact there (later cycles
+ * depend on NLopt's output and are not modelled).  A host shim that wants the reference's bool returns false when the
+ * bit is set (csrc/FootholdPlannerGpu.hpp does); the rows are planned regardless. */
+#define FHP_STATUS_ERR_MASK 0x7f
+#define FHP_STATUS_OPT_SUBMAP_FAIL 0x80
 
 typedef struct fhp_ctx fhp_ctx;
 
@@ -250,6 +260,38 @@ typedef struct fhp_foothold24 {
 int fhp_plan_compact24(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
                        int64_t n_queries, int32_t gait_cycles, fhp_foothold24* out_rows, int64_t capacity_rows,
                        int64_t* row_offsets, fhp_query_status* status);
+/* STREAMED batch response: one launch plans the whole batch and WRITES every produced foothold straight into the
+ * caller's page-locked host buffer while it runs (zero-copy over PCIe: no staging copy, no compaction pass; the transfer
+ * overlaps the planning, failed cycles cost no bytes).  A row is the point alone, 20 bytes {x, y double, z float — it is a
+ * float by construction, FP.cpp:2553}; foot_id and gait_cycle_id are positional.
+ *   Queries are grouped in runs of 8 (group G = q / 8).  out_blocks holds (gait_cycles + 1) * ceil(n_queries / 8) blocks
+ *   of 32 rows (640 bytes).  Block (0, G) holds the stance rows of its queries in query order; block (g + 1, G) holds the
+ *   rows of gait cycle g of those queries of the group whose cycle g succeeded (FP.cpp:1323), packed to the front in query
+ *   order, 4 rows (RF, RH, LH, LF) each.  masks[(q * FHP_STREAM_MASK_WORDS(gait_cycles) + g / 32) * 4 + f]: bit g % 32 of
+ *   .success = cycle g of query q succeeded (same value for the 4 feet), of .candidate = that foot came from the spiral
+ *   search (kind FHP_KIND_CANDIDATE instead of FHP_KIND_DEFAULT).  fhp_stream_row() below locates a row.
+ * The rows are exactly those of fhp_plan / fhp_plan_compact24 ((float)z is lossless for every planned row; stance rows
+ * carry (float)initial z).  out_blocks (128-byte aligned), masks and status must be page-locked and mapped
+ * (cudaHostAlloc, cudaHostRegister, torch pin_memory): FHP_ERR_INVALID_ARG otherwise — pageable callers use
+ * fhp_plan_compact24. */
+#pragma pack(push, 4)
+typedef struct fhp_point20 {
+  double x, y;
+  float z;
+} fhp_point20;
+#pragma pack(pop)
+typedef struct fhp_stream_mask {
+  uint32_t success, candidate;
+} fhp_stream_mask;
+#define FHP_STREAM_MASK_WORDS(gait_cycles) (((gait_cycles) + 31) / 32)
+#define FHP_STREAM_BLOCKS(n_queries, gait_cycles) (((int64_t)(gait_cycles) + 1) * (((int64_t)(n_queries) + 7) / 8))
+int fhp_plan_stream(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                    int64_t n_queries, int32_t gait_cycles, fhp_point20* out_blocks, fhp_stream_mask* masks,
+                    fhp_query_status* status);
+/* Row of foot f of query q in gait cycle g (g = -1: stance) inside the streamed blocks, or NULL when that cycle
+ * failed: rank = the successful queries before q in its group of 8.  Pure host-side function. */
+const fhp_point20* fhp_stream_row(const fhp_point20* blocks, const fhp_stream_mask* masks, int64_t n_queries,
+                                  int32_t gait_cycles, int64_t q, int32_t g, int32_t f);
 /* KPIs the reference logs per successful cycle (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623): pure
  * host-side functions of ONE query's response rows (nominal or centroid chain).  feet_distance / cog_speed receive
  * 2 values per successful cycle (n_rows/4 - 1 cycles). */

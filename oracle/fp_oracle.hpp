@@ -81,6 +81,11 @@ struct PlanResult {  // foothold_planner_msgs/GlobalFootholds
   std::vector<Foothold> defaultFootholds;    // "default" chain rows (globalFootholdsResult_.defaultFootholds, FP.cpp:1344-1348)
   // KPIs per successful cycle, two values each (FP.cpp:1357-1368, :1422-1433): getHipDistance / getCogSpeed
   std::vector<double> feetDistanceNominal, cogSpeedNominal, feetDistanceCentroid, cogSpeedCentroid;
+  // at gait cycle 0 the opt (NLopt) chain still holds the setFirstGait state (FP.cpp:583-588), so its
+  // gait-cycle submap request (getGaitCycleSearchGridMap FP.cpp:2307-2350 with rect = isos_.length x isos_.width,
+  // FP.cpp:391-394) is a pure function of the query; when that getSubmap fails the reference aborts the whole service
+  // call (`return false`, FP.cpp:931-934) before anything of cycle 0 is appended.  Later cycles depend on NLopt output.
+  bool optSubmapWouldFail = false;
 };
 
 class Planner {
@@ -474,6 +479,23 @@ class Planner {
     return true;  // policy C.2
   }
 
+  // The success predicate of the opt chain's gait-cycle submap at cycle 0 (FP.cpp:916-934 -> :2307-2350): centre =
+  // (stance centroid x + stepLength, initialPose y + adjusted y) (:2333-2336; heading extension: the rotated next
+  // centre), rect = (isos_.length, isos_.width) with the reference's float/double mix (FP.hpp:677-703, FP.cpp:384-394).
+  bool optGaitSubmapOk(const gm::GridMap& gridmap, const Point cur[4]) const {
+    Point c = getPolygonCenter(cur[0], cur[1], cur[2], cur[3]);
+    Point n;
+    n.x = c.x + p.stepLength;
+    n.y = initialPose[1] + ajustedPoseY;
+    if (useHeading) n = headingNextCenter(c);
+    const double longEdge = lengthBase + p.skew * 2;  // float arithmetic, stored in a double member
+    const double shortEdge = widthBase;
+    const double rectLength = p.searchRadius * 2, rectWidth = p.searchRadius;  // footSearchRect_ (float arithmetic)
+    gm::SubmapInfo info;
+    return gm::getSubmapInformation(info, gm::Vec2{n.x, n.y}, gm::Vec2{longEdge + rectLength, shortEdge + rectWidth},
+                                    gridmap.length, gridmap.position, gridmap.resolution, gridmap.size, gridmap.startIndex);
+  }
+
   // FP.cpp:2253-2304 — un-searched default footholds of the next cycle (z = mean height at the default position)
   void getDefaultFootholds(const gm::GridMap& gridmap, const Point cur[4], Point next[4]) const {
     Point polygonCenter = getPolygonCenter(cur[0], cur[1], cur[2], cur[3]);
@@ -541,6 +563,7 @@ class Planner {
       res.defaultFootholds.push_back(fh);   // :666-671
     }
     ajustedPoseY = 0.0;  // :759
+    if (gaitCycles > 0) res.optSubmapWouldFail = !optGaitSubmapOk(gridmap, nomCur);
     const int gaitCycleNum = gaitCycles;
     for (int g = 0; g < gaitCycleNum; ++g) {  // :762
       // --- default chain (:774-781)

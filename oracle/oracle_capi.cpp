@@ -101,7 +101,7 @@ void plan_one(const gm::GridMap& map, const fhp_params* params, const fhp_query&
   st->success = r.success ? 1 : 0;
   st->gait_cycles = r.gait_cycles;
   st->gait_cycles_succeed = r.gait_cycles_succeed;
-  st->reserved = 0;
+  st->reserved = r.optSubmapWouldFail ? FHP_STATUS_OPT_SUBMAP_FAIL : 0;
   st->n_rows = static_cast<int32_t>(r.footholds.size());
 }
 
@@ -182,7 +182,7 @@ int oracle_plan_latency(const fhp_map_desc* desc, const float* const* layers, co
       status->success = res.success ? 1 : 0;
       status->gait_cycles = res.gait_cycles;
       status->gait_cycles_succeed = res.gait_cycles_succeed;
-      status->reserved = 0;
+      status->reserved = res.optSubmapWouldFail ? FHP_STATUS_OPT_SUBMAP_FAIL : 0;
       status->n_rows = static_cast<int32_t>(res.footholds.size());
     }
   }

@@ -71,6 +71,9 @@ FOOTHOLD_PACKED_DTYPE = np.dtype([  # fhp_foothold_packed (32 bytes)
 FOOTHOLD24_DTYPE = np.dtype([  # fhp_foothold24 (24 bytes): the Foothold message fields
     ("x", "<f8"), ("y", "<f8"), ("z", "<f4"), ("foot_id", "u1"), ("gait_cycle_id", "u1"), ("kind", "u1"), ("reserved", "u1"),
 ])
+POINT20_DTYPE = np.dtype({"names": ["x", "y", "z"], "formats": ["<f8", "<f8", "<f4"], "offsets": [0, 8, 16],
+                          "itemsize": 20})  # fhp_point20 (packed)
+STREAM_MASK_DTYPE = np.dtype([("success", "<u4"), ("candidate", "<u4")])  # fhp_stream_mask
 STATUS_DTYPE = np.dtype([("success", "u1"), ("gait_cycles", "u1"), ("gait_cycles_succeed", "u1"), ("reserved", "u1"),
                          ("n_rows", "<i4")])
 assert QUERY_DTYPE.itemsize == 32 and FOOTHOLD_DTYPE.itemsize == 40 and STATUS_DTYPE.itemsize == 8

@@ -328,6 +328,11 @@ void derive_params(const fhp_params& p, ParDev& o, bool forceHeading = false) {
     o.rectVx[k] = o.heading ? vx[k] * o.ch - vy[k] * o.sh : vx[k];
     o.rectVy[k] = o.heading ? vx[k] * o.sh + vy[k] * o.ch : vy[k];
   }
+  {  // isos_ (FP.hpp:677-703): longEdge = lengthBase + skew*2 in float arithmetic, stored in doubles (FP.cpp:384-394)
+    const double longEdge = lengthBase + skew * 2, shortEdge = widthBase;
+    o.isosLx = longEdge + o.rectLx;
+    o.isosLy = shortEdge + o.rectLy;
+  }
   o.halfStepX = o.halfStep * o.ch;
   o.halfStepY = o.halfStep * o.sh;
   if (o.heading)
@@ -555,8 +560,21 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   return FHP_OK;
 }
 
+// Small batches are validated on the host before anything is launched; large ones (a walk over every query would
+// cost as much as a tenth of the plan itself) by the kernel, which reports kErrParam.
+bool param_ids_ok(const fhp_query* queries, int64_t n_queries, int32_t n_params) {
+  if (n_queries > 4096) return true;
+  for (int64_t i = 0; i < n_queries; ++i)
+    if (queries[i].param_id < 0 || queries[i].param_id >= n_params) return false;
+  return true;
+}
+
 int check_dev_err(fhp_ctx* ctx) {
   const unsigned e = ctx->hErr ? *static_cast<volatile unsigned*>(ctx->hErr) : 0u;
+  if (e & kErrParam) {
+    *ctx->hErr = 0;
+    return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range (reported by the kernel; the response is not valid)");
+  }
   if (e) {
     *ctx->hErr = 0;
     char b[160];
@@ -923,10 +941,19 @@ static int64_t chunk_queries(fhp_ctx* ctx, bool wantCen) {
   return std::max<int64_t>(1024, wave_queries(ctx, wantCen) / ctx->chunkDiv);
 }
 
+struct StreamOut {  // fhp_plan_stream: device aliases of the caller's mapped host buffers
+  fhp_point20* slots;
+  uint32_t* mask;
+  long long nq, q0;
+};
 static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_queries, int64_t n_queries,
                        int32_t gait_cycles, fhp_foothold* d_outN, fhp_foothold* d_outC, fhp_query_status* d_st,
-                       cudaStream_t s, fhp_foothold* d_outD = nullptr) {
+                       cudaStream_t s, fhp_foothold* d_outD = nullptr, const StreamOut* so = nullptr) {
   PlanArgs A;
+  A.sOut = so ? so->slots : nullptr;
+  A.sMask = so ? so->mask : nullptr;
+  A.sNq = so ? so->nq : 0;
+  A.sQ0 = so ? so->q0 : 0;
   A.tmap = ctx->tmapTrav;
   A.M = ctx->M;
   A.mask = static_cast<const uint4*>(ctx->dMask.p);
@@ -940,6 +967,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
     const long long need = (n_queries + waveWarps - 1) / waveWarps;
     A.qpwShift = need <= 1 ? 0 : (need <= 2 ? 1 : (need <= 4 ? 2 : 3));
     if (ctx->qpwShiftForce >= 0) A.qpwShift = ctx->qpwShiftForce;
+    if (so) A.qpwShift = 3;  // the streamed buffer format groups 8 queries per block
   }
   A.outN = d_outN;
   A.outC = d_outC;
@@ -991,9 +1019,7 @@ int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const 
   if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 || (n_queries > 0 && (!queries || !out_nominal || !status)))
     return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments (gait_cycles is a uint8 in the service request)");
   if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan before fhp_set_map");
-  for (int64_t i = 0; i < n_queries; ++i)
-    if (queries[i].param_id < 0 || queries[i].param_id >= n_params)
-      return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
+  if (!param_ids_ok(queries, n_queries, n_params)) return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
   CU(cudaSetDevice(ctx->device));
   if (n_queries == 0) return FHP_OK;
   cudaStream_t s = ctx->stream;
@@ -1111,9 +1137,7 @@ static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_p
       (n_queries > 0 && (!queries || !out_rows || !status)))
     return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments (gait_cycles is a uint8 in the service request)");
   if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan_compact before fhp_set_map");
-  for (int64_t i = 0; i < n_queries; ++i)
-    if (queries[i].param_id < 0 || queries[i].param_id >= n_params)
-      return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
+  if (!param_ids_ok(queries, n_queries, n_params)) return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
   CU(cudaSetDevice(ctx->device));
   row_offsets[0] = 0;
   if (n_queries == 0) return FHP_OK;
@@ -1226,6 +1250,78 @@ static int plan_compact_impl(fhp_ctx* ctx, const fhp_params* params, int32_t n_p
   row_offsets[n_queries] = base;
   if (err != FHP_OK) return fail(ctx, err, "capacity_rows is smaller than the rows the queries produced (row_offsets[n] holds the need)");
   return check_dev_err(ctx);
+}
+
+// Streamed response: ONE launch plans the whole batch and writes every produced row straight into the caller's pinned,
+// device-mapped host buffer while it runs — PCIe carries the rows as they are produced, there is no staging copy, no
+// compaction pass and no chunking; the call ends with one stream synchronisation.
+int fhp_plan_stream(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
+                    int32_t gait_cycles, fhp_point20* out_blocks, fhp_stream_mask* masks, fhp_query_status* status) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 ||
+      (n_queries > 0 && (!queries || !out_blocks || !status || (gait_cycles > 0 && !masks))))
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments (gait_cycles is a uint8 in the service request)");
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "fhp_plan_stream before fhp_set_map");
+  if (!param_ids_ok(queries, n_queries, n_params)) return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
+  CU(cudaSetDevice(ctx->device));
+  if (n_queries == 0) return FHP_OK;
+  if ((reinterpret_cast<uintptr_t>(out_blocks) & 127u) != 0 || (reinterpret_cast<uintptr_t>(masks) & 7u) != 0)
+    return fail(ctx, FHP_ERR_INVALID_ARG, "fhp_plan_stream: out_blocks must be 128-byte aligned, masks 8-byte aligned");
+  void *dSlots = nullptr, *dMask = nullptr, *dStat = nullptr;
+  if (cudaHostGetDevicePointer(&dSlots, out_blocks, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer(&dStat, status, 0) != cudaSuccess ||
+      (masks && cudaHostGetDevicePointer(&dMask, masks, 0) != cudaSuccess)) {
+    cudaGetLastError();
+    return fail(ctx, FHP_ERR_INVALID_ARG,
+                "fhp_plan_stream: out_blocks, masks and status must be page-locked host memory (cudaHostAlloc / "
+                "cudaHostRegister): the kernel writes them directly");
+  }
+  cudaStream_t s = ctx->stream;
+  int rc = prepare_params(ctx, params, n_params, s);
+  if (rc != FHP_OK) return rc;
+  rc = ensure_err_word(ctx);
+  if (rc != FHP_OK) return rc;
+  // queries: read in place over PCIe when they sit in mapped pinned memory too (32 bytes per query, coalesced per warp;
+  // the link is full duplex, so these reads do not compete with the row writes); copied first otherwise
+  const fhp_query* dQueries = nullptr;
+  {
+    void* dq = nullptr;
+    if (cudaHostGetDevicePointer(&dq, const_cast<fhp_query*>(queries), 0) == cudaSuccess) {
+      dQueries = static_cast<const fhp_query*>(dq);
+    } else {
+      cudaGetLastError();
+      CU(ctx->dQ.reserve(sizeof(fhp_query) * n_queries));
+      CU(cudaMemcpyAsync(ctx->dQ.p, queries, sizeof(fhp_query) * n_queries, cudaMemcpyHostToDevice, s));
+      dQueries = static_cast<const fhp_query*>(ctx->dQ.p);
+    }
+  }
+  StreamOut so;
+  so.slots = static_cast<fhp_point20*>(dSlots);
+  so.mask = static_cast<uint32_t*>(dMask);
+  so.nq = n_queries;
+  so.q0 = 0;
+  rc = plan_launch(ctx, n_params, dQueries, n_queries, gait_cycles, nullptr, nullptr,
+                   static_cast<fhp_query_status*>(dStat), s, nullptr, &so);
+  if (rc != FHP_OK) return rc;
+  CU(cudaStreamSynchronize(s));
+  return check_dev_err(ctx);
+}
+
+const fhp_point20* fhp_stream_row(const fhp_point20* blocks, const fhp_stream_mask* masks, int64_t n_queries,
+                                  int32_t gait_cycles, int64_t q, int32_t g, int32_t f) {
+  if (!blocks || q < 0 || q >= n_queries || g < -1 || g >= gait_cycles || f < 0 || f > 3) return nullptr;
+  const int64_t groups = (n_queries + 7) / 8, G = q >> 3;
+  int rank = static_cast<int>(q & 7);
+  if (g >= 0) {
+    if (!masks) return nullptr;
+    const int words = FHP_STREAM_MASK_WORDS(gait_cycles);
+    const uint32_t bit = 1u << (g & 31);
+    if (!(masks[(q * words + (g >> 5)) * 4].success & bit)) return nullptr;
+    rank = 0;
+    for (int64_t p = G * 8; p < q; ++p) rank += (masks[(p * words + (g >> 5)) * 4].success & bit) ? 1 : 0;
+  }
+  return blocks + ((static_cast<int64_t>(g + 1) * groups + G) * 32 + rank * 4 + f);
 }
 
 // KPIs of the reference's logs (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623, gaitCycle_ = 1.0 :332) —

@@ -816,6 +816,22 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
   return o;
 }
 
+// GridMap::getSubmap's success predicate (getSubmapInformation, GridMapMath.cpp) for a request of size (lx, ly) around
+// (px, py): what decides whether the reference's opt chain aborts the service call at cycle 0 (FP.cpp:931-934, :2345).
+__device__ __noinline__ bool submap_request_ok(const MapDev& M, double px, double py, double lx, double ly) {
+  const double tlx = bound_axis(px + 0.5 * lx, M.lenx, M.posx, M.halfx), tly = bound_axis(py + 0.5 * ly, M.leny, M.posy, M.halfy);
+  if (!(within_axis(tlx, M.lenx, M.posx, M.halfx) && within_axis(tly, M.leny, M.posy, M.halfy))) return false;
+  const int tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res, M.rinv), tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res, M.rinv);
+  const double brx = bound_axis(px - 0.5 * lx, M.lenx, M.posx, M.halfx), bry = bound_axis(py - 0.5 * ly, M.leny, M.posy, M.halfy);
+  if (!(within_axis(brx, M.lenx, M.posx, M.halfx) && within_axis(bry, M.leny, M.posy, M.halfy))) return false;
+  const int br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv), br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
+  if (!in_map(M, tl0, tl1)) return false;
+  const double cornx = pos_axis(M.fcx, M.res, tl0) + 0.5 * M.res, corny = pos_axis(M.fcy, M.res, tl1) + 0.5 * M.res;
+  const double slx = static_cast<double>(br0 - tl0 + 1) * M.res, sly = static_cast<double>(br1 - tl1 + 1) * M.res;
+  const double shx = 0.5 * slx, shy = 0.5 * sly;
+  return within_axis(px, slx, cornx - shx, shx) && within_axis(py, sly, corny - shy, shy);
+}
+
 // ------------------------------------------------------------------------------------------------ a5..a8 nominal
 struct NominalOut {
   double x, y;

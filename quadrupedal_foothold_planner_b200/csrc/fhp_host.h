@@ -27,6 +27,11 @@ struct PlanArgs {
   fhp_foothold* outD;  // optional: "default" chain rows
   fhp_query_status* st;
   unsigned* err;  // device word, OR of the kErr* bits of every query
+  // streamed response (fhp_plan_stream): rows go straight into the caller's mapped host buffer, cycle-major blocks
+  fhp_point20* sOut;     // block (g + 1, q / 8): 32 row slots, successful queries packed to the front
+  uint32_t* sMask;       // per (query, 32-cycle word, foot): {success bits, kind bits} (fhp_stream_mask)
+  long long sNq;         // queries of the whole call (the slot pitch of a cycle block)
+  long long sQ0;         // index of this launch's first query within the call
 };
 
 struct TaskArgs {
@@ -43,6 +48,7 @@ struct TaskArgs {
 };
 
 cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, cudaStream_t stream);
+constexpr int kStreamWarpBytes = 32 * 20;  // shared-memory staging of one warp's rows in stream mode
 long long plan_wave_queries(const GeoDev& G, bool wantCen);
 cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, unsigned* flags,
                               cudaStream_t stream);

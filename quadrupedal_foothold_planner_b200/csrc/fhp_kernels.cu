@@ -52,6 +52,40 @@ __device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y,
   reinterpret_cast<unsigned long long*>(dst)[4] = ids;
 }
 
+// Streamed response (fhp_plan_stream): the rows a warp produces in one gait cycle — 8 queries x 4 feet x 20 bytes
+// {x, y double, z float} — go straight into the caller's mapped HOST buffer.  The quads whose cycle succeeded are packed
+// to the front of the warp's 640-byte block (query order) through shared memory, so every store instruction writes 16
+// contiguous bytes per lane from a 128-byte aligned base: PCIe carries full write packets while the kernel keeps
+// planning, and failed cycles cost no bytes.  The per-query cycle masks tell the reader which quads are there.
+// WARP-COLLECTIVE.
+__device__ __forceinline__ void stream_rows(uint32_t stg, int lane, bool mine, double x, double y, float z, char* dstWarp) {
+  const unsigned okl = __ballot_sync(kFull, mine);
+  const unsigned okq = okl & 0x11111111u;  // one bit per quad (its foot 0)
+  const int rank = __popc(okq & ((1u << (lane & ~3)) - 1u));
+  if (mine) {
+    const uint32_t a = stg + static_cast<uint32_t>(rank * 4 + (lane & 3)) * 20u;
+    const unsigned long long xb = static_cast<unsigned long long>(__double_as_longlong(x));
+    const unsigned long long yb = static_cast<unsigned long long>(__double_as_longlong(y));
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(static_cast<uint32_t>(xb)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 4u), "r"(static_cast<uint32_t>(xb >> 32)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 8u), "r"(static_cast<uint32_t>(yb)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 12u), "r"(static_cast<uint32_t>(yb >> 32)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 16u), "r"(__float_as_uint(z)) : "memory");
+  }
+  __syncwarp();
+  const int nChunks = __popc(okq) * 5;  // 16-byte chunks: 80 bytes per successful quad
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int c = k * 32 + lane;
+    if (c < nChunks) {
+      const uint4 v = lds_v4(stg + static_cast<uint32_t>(c) * 16u);
+      asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dstWarp + c * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+  }
+  __syncwarp();
+}
+
 // Block-wide copy of the SpiralIterator table into shared memory (ranks are looked up with a per-lane index in the
 // cooperative scan; the constant bank would serialise those).  Returns the table; ends with __syncthreads.
 __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, uint32_t* smem) {
@@ -72,7 +106,7 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
 #define FHP_PLAN_MIN_BLOCKS_MASK 7
 #endif
-template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING>
+template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM>
 __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev G) {
   extern __shared__ __align__(16) uint32_t smem_raw[];
@@ -115,6 +149,11 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     qu.z = src->z;
     qu.param_id = src->param_id;
   }
+  unsigned err = 0;
+  if (static_cast<unsigned>(qu.param_id) >= static_cast<unsigned>(A.nPars)) {  // validated here: large batches are not
+    err = kErrParam;                                                           // walked on the host
+    qu.param_id = 0;
+  }
   const ParDev& P = A.pars[qu.param_id];
   const long long R = 4 + 4 * static_cast<long long>(A.cycles);
   fhp_foothold* outN = A.outN + q * R;
@@ -128,18 +167,41 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
   double nomx = stx - (HEADING ? P.halfStepX : P.halfStep), nomy = HEADING ? sty - P.halfStepY : sty;
   double cenx = nomx, ceny = nomy;
   double defx = nomx, defy = nomy;  // default chain: setFirstGait too (FP.cpp:562)
-  if (active) {  // FP.cpp:685-699 (and :713-727 for the centroid message, :666-671 for the default chain)
+  // stream mode: this warp's staging block (behind everything else in shared memory) and its first query's slot
+  // (stream mode always runs 8 queries per warp: the group of 8 queries is part of the buffer format)
+  const uint32_t sStg = STREAM ? smem_u32(smem + G.smemWords) + static_cast<uint32_t>(warpInBlock) * kStreamWarpBytes : 0u;
+  char* const sBase = STREAM ? reinterpret_cast<char*>(A.sOut) + ((A.sQ0 >> 3) + gwarp) * 640 : nullptr;
+  const long long sPitch = STREAM ? ((A.sNq + 7) >> 3) * 640 : 0;  // bytes of one cycle block
+  uint32_t succMask = 0u, kindMask = 0u;
+  if (STREAM) stream_rows(sStg, lane, active, stx, sty, static_cast<float>(stz), sBase);
+  if (active && !STREAM) {  // FP.cpp:685-699 (and :713-727 for the centroid message, :666-671 for the default chain)
     int r0, c0;
     cell_of_position(M, stx, sty, r0, c0);
     write_row(outN + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
     if (WANT_CEN) write_row(outC + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
     if (wantDef) write_row(outD + f, stx, sty, stz, r0, c0, f, 0, FHP_KIND_STANCE);
   }
+  // would the reference's opt chain abort this service call at cycle 0 (FP.cpp:931-934)?  Its state is
+  // still the first-gait stance there, so the submap request is the nominal chain's next centre with isos_ extents.
+  bool optFail = false;
+  if (A.cycles > 0) {
+    double ocx, ocy;
+    polygon_center(shfl_d(nomx, quad0), shfl_d(nomy, quad0), shfl_d(nomx, quad0 + 1), shfl_d(nomy, quad0 + 1),
+                   shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
+                   ocx, ocy);
+    double onx = ocx + P.stepLength, ony = qu.y + 0.0;
+    if (HEADING) {
+      const double lat0 = (qu.y * P.ch - mulz(qu.x, P.sh)) + 0.0;
+      const double fwd = (ocx * P.ch + mulz(ocy, P.sh)) + P.stepLength;
+      onx = fwd * P.ch - mulz(lat0, P.sh);
+      ony = mulz(fwd, P.sh) + lat0 * P.ch;
+    }
+    if (active && f == 0) optFail = !submap_request_ok(M, onx, ony, P.isosLx, P.isosLy);
+  }
   double adjY = 0.0;  // ajustedPose_[1] (FP.cpp:759)
   int prevW0 = -0x7fffffff, prevW1 = -0x7fffffff;  // window staged in the previous cycle (still in this lane's slot)
   int nrows = 4, succeed = 0;
   bool success = false;
-  unsigned err = 0;
 
   for (int g = 0; g < A.cycles; ++g) {
 #if FHP_SYNC_LEVEL >= 1
@@ -244,9 +306,22 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     // footholdValidation_ = RF & RH & LH & LF (FP.cpp:1323)
     const unsigned okb = __ballot_sync(kFull, ok);
     const bool all_ok = ((okb >> quad0) & 0xfu) == 0xfu;
+    if (STREAM) {
+      stream_rows(sStg, lane, active && all_ok, no.x, no.y, static_cast<float>(nz),
+                  sBase + static_cast<long long>(g + 1) * sPitch);
+      if (all_ok) {
+        succMask |= 1u << (g & 31);
+        if (no.kind == FHP_KIND_CANDIDATE) kindMask |= 1u << (g & 31);
+      }
+      if ((g & 31) == 31 || g + 1 == A.cycles) {  // per lane: {cycle succeeded, this foot came from the spiral} bits
+        if (active)
+          reinterpret_cast<uint2*>(A.sMask)[((A.sQ0 + q) * ((A.cycles + 31) >> 5) + (g >> 5)) * 4 + f] = make_uint2(succMask, kindMask);
+        succMask = kindMask = 0u;
+      }
+    }
     if (active) {
       if (all_ok) {
-        write_row(outN + nrows + f, no.x, no.y, nz, no.row, no.col, f, g, no.kind);  // :1378-1396
+        if (!STREAM) write_row(outN + nrows + f, no.x, no.y, nz, no.row, no.col, f, g, no.kind);  // :1378-1396
         if (WANT_CEN) {
           int r0, c0;
           cell_of_position(M, co.x, co.y, r0, c0);
@@ -281,7 +356,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     s.success = success ? 1 : 0;
     s.gait_cycles = static_cast<uint8_t>(A.cycles);
     s.gait_cycles_succeed = static_cast<uint8_t>(succeed);
-    s.reserved = static_cast<uint8_t>(e4);
+    s.reserved = static_cast<uint8_t>((e4 & FHP_STATUS_ERR_MASK) | (optFail ? FHP_STATUS_OPT_SUBMAP_FAIL : 0));
     s.n_rows = nrows;
     A.st[q] = s;
   }
@@ -539,21 +614,22 @@ cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st,
 typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
 // the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
 template <int STAGE, bool HEADING>
-static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef) {
-  if (wantDef) return plan_kernel<true, STAGE, true, HEADING>;
-  return wantCen ? plan_kernel<true, STAGE, false, HEADING> : plan_kernel<false, STAGE, false, HEADING>;
+static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef, bool stream) {
+  if (stream) return plan_kernel<false, STAGE, false, HEADING, true>;  // nominal rows only
+  if (wantDef) return plan_kernel<true, STAGE, true, HEADING, false>;
+  return wantCen ? plan_kernel<true, STAGE, false, HEADING, false> : plan_kernel<false, STAGE, false, HEADING, false>;
 }
 // heading: some parameter set of the call carries a non-zero heading -> the variant with the rotated expressions
 // (the reference-shaped variant stays exactly what it was)
-static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading) {
+static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading, bool stream) {
   if (heading) {
-    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef);
-    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef);
-    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef);
+    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef, stream);
+    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef, stream);
+    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef, stream);
   }
-  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef);
-  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef);
-  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef);
+  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef, stream);
+  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef, stream);
+  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef, stream);
 }
 
 // ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
@@ -563,8 +639,10 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
   const int qpw = 1 << A.qpwShift;
   const long long nWarps = (A.nq + qpw - 1) / qpw;
   const long long blocks = (nWarps + warps - 1) / warps;
-  const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;  // + alignment slack
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading);
+  const bool streamMode = A.sOut != nullptr;
+  const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128 +  // + alignment slack
+                     (streamMode ? static_cast<size_t>(warps) * kStreamWarpBytes : 0);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading, streamMode);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
@@ -577,7 +655,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
 // the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
 // a wave takes as long as a full one).
 long long plan_wave_queries(const GeoDev& G, bool wantCen) {
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false, false);
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
   if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
   int perSm = 0, dev = 0, sms = 0;

@@ -16,6 +16,7 @@ constexpr int kStageMask = 2;  // funnel-shifted words of the precomputed D/C/F 
 
 // error bits reported per query (status.reserved) — any non-zero bit fails the whole call loudly
 constexpr unsigned kErrWindow = 1u;   // a cell needed by the reference lies outside the staged window
+constexpr unsigned kErrParam = 2u;    // a query's param_id is outside the parameter table (the query planned with set 0)
 
 struct MapDev {
   const float* trav;
@@ -78,6 +79,7 @@ struct ParDev {  // one per fhp_params, derived on the host exactly as FootholdP
   double ch, sh;                  // cos / sin of the heading
   double halfStepX, halfStepY;    // halfStep * ch, halfStep * sh (setFirstGait steps half a step back along u)
   double rectVx[4], rectVy[4];    // rot() of getSearchPolygon's vertex offsets (+R,+R/2) (+R,-R/2) (-R,-R/2) (-R,+R/2)
+  double isosLx, isosLy;          // isos_.length, isos_.width (FP.cpp:384-394): the opt chain's gait-cycle submap request
 };
 
 }  // namespace fhp

@@ -70,6 +70,7 @@ def load_lib():
     L.fhp_plan_compact.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
     L.fhp_plan_compact_packed.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
     L.fhp_plan_compact24.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
+    L.fhp_plan_stream.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp]
     L.fhp_plan_device.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp, vp]
     L.fhp_synchronize.argtypes = [vp]
     L.fhp_check_foothold.argtypes = [vp, vp, vp, vp, i64, vp, vp]
@@ -231,6 +232,48 @@ class Fhp:
         fn, _ = self._compact_fn(packed, fmt)
         self._check(fn(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q_ptr), nq, int(gait_cycles),
                                             _ptr(rows_ptr), int(capacity_rows), _ptr(offs_ptr), _ptr(st_ptr)))
+
+    def plan_stream_raw(self, parr, npar, q_ptr, nq, gait_cycles, blocks_ptr, mask_ptr, st_ptr):
+        """fhp_plan_stream on raw PINNED host addresses (see include/fhp.h for the block format)."""
+        self._check(self.L.fhp_plan_stream(self.h, C.cast(parr, C.c_void_p), npar, _ptr(q_ptr), nq, int(gait_cycles),
+                                           _ptr(blocks_ptr), _ptr(mask_ptr), _ptr(st_ptr)))
+
+    def plan_stream(self, params, queries: np.ndarray, gait_cycles: int):
+        """fhp_plan_stream with pinned buffers allocated here (torch).  -> (blocks [cycles+1, groups, 32] of POINT20_DTYPE,
+        masks [nq, words, 4] of STREAM_MASK_DTYPE, status [nq]).  stream_rows_of() extracts one query's rows."""
+        import torch
+        parr, npar = self._params_array(params)
+        q = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
+        nq = len(q)
+        cycles = int(gait_cycles)
+        words = max(1, (cycles + 31) // 32)
+        groups = max(1, (nq + 7) // 8)
+        raw = torch.zeros((cycles + 1) * groups * 640 + 128, dtype=torch.uint8).pin_memory()
+        off = (-raw.data_ptr()) % 128
+        blocks = raw[off: off + (cycles + 1) * groups * 640]
+        mask = torch.zeros(max(nq, 1) * words * 4 * 2, dtype=torch.int32).pin_memory()
+        st = torch.zeros(max(nq, 1) * STATUS_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self.plan_stream_raw(parr, npar, q, nq, cycles, blocks, mask, st)
+        self._stream_keep = raw
+        return (blocks.numpy().view(_abi.POINT20_DTYPE).reshape(cycles + 1, groups, 32),
+                mask.numpy().view(_abi.STREAM_MASK_DTYPE).reshape(max(nq, 1), words, 4)[:nq], st.numpy().view(STATUS_DTYPE)[:nq])
+
+    @staticmethod
+    def stream_rows_of(blocks, masks, q: int):
+        """One query's response rows from the streamed blocks: -> (points [n_rows] POINT20, foot_id, gait_cycle_id, kind)."""
+        cycles = blocks.shape[0] - 1
+        G, lo = q >> 3, (q >> 3) << 3
+        pts, foot, cyc, kind = [blocks[0, G, (q & 7) * 4:(q & 7) * 4 + 4]], [0, 1, 2, 3], [0] * 4, [0] * 4
+        for g in range(cycles):
+            w, bit = g >> 5, np.uint32(1 << (g & 31))
+            if not (masks[q, w, 0]["success"] & bit):
+                continue
+            rank = int(sum(1 for p in range(lo, q) if masks[p, w, 0]["success"] & bit))
+            pts.append(blocks[g + 1, G, rank * 4: rank * 4 + 4])
+            foot += [0, 1, 2, 3]
+            cyc += [g] * 4
+            kind += [2 if (masks[q, w, f]["candidate"] & bit) else 1 for f in range(4)]
+        return np.concatenate(pts), np.array(foot), np.array(cyc), np.array(kind)
 
     def cycle_kpi(self, params: Params, query, rows: np.ndarray, n_rows: int):
         """fhp_cycle_kpi: (feet_distance [cycles,2], cog_speed [cycles,2]) of one query's rows (FP.cpp:2571-2623)."""

@@ -69,6 +69,11 @@ def ref_cases():
     m = synth.stairs_stones_map(700, 400, 0.01, start=(0, 0))
     q = synth.uniform_queries(40, (-2.9, -1.2), (-1.2, 1.2), seed=11)
     out["ref_stairs_001_rf_first"] = (m, _abi.yaml_params(rf_first=1, step_length=0.16, skew=0.04), q, 8, True)
+    # poses up to the map border, ONE gait cycle: the only abort the service can take is the opt chain's cycle-0 submap
+    # failure (FP.cpp:931-934) — pins FHP_STATUS_OPT_SUBMAP_FAIL
+    m = synth.rough_map(200, 200, 0.02, seed=13, start=(0, 0))
+    q = synth.uniform_queries(80, (-2.8, 2.4), (-2.6, 2.6), seed=14)
+    out["ref_border_002_one_cycle"] = (m, _abi.yaml_params(), q, 1, True)
     return out
 
 

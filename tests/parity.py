@@ -12,7 +12,9 @@ def compare_plans(got, exp, what=""):
     for f in ("success", "gait_cycles", "gait_cycles_succeed", "n_rows"):
         bad = np.nonzero(gs[f] != es[f])[0]
         assert bad.size == 0, f"{what}: status.{f} differs for queries {bad[:8]} got {gs[f][bad[:8]]} exp {es[f][bad[:8]]}"
-    assert np.all(gs["reserved"] == 0), f"{what}: kernel error bits set"
+    assert np.all((gs["reserved"] & 0x7F) == 0), f"{what}: kernel error bits set"
+    bad = np.nonzero(gs["reserved"] != es["reserved"])[0]  # FHP_STATUS_OPT_SUBMAP_FAIL (0x80)
+    assert bad.size == 0, f"{what}: status flags differ for queries {bad[:8]} got {gs['reserved'][bad[:8]]} exp {es['reserved'][bad[:8]]}"
     R = gn.shape[1]
     owned = np.arange(R)[None, :] < es["n_rows"][:, None]
     maxd = 0.0

@@ -350,6 +350,47 @@ def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
     assert np.array_equal(r24["x"], rb["x"]) and np.array_equal(r24["z"].astype(np.float64), rb["z"])
 
 
+def test_streamed_response_equals_plan_rows(fhp):
+    """fhp_plan_stream (the kernel writes 20-byte points straight into pinned host memory, cycle-major blocks of 8
+    queries with the successful ones packed to the front) carries exactly the rows fhp_plan returns; the masks give
+    success and kind; bytes past a block's packed rows stay as the caller left them.  Partial last group, several waves,
+    > 32 cycles (two mask words), a heading."""
+    from quadrupedal_foothold_planner_b200.planner import Fhp, FhpError
+    m = synth.rough_map(1200, 1200, 0.02, seed=71, start=(100, 900))
+    fhp.set_map(m)
+    for nq, cycles, p in ((1, 8, _abi.yaml_params()), (37, 12, _abi.yaml_params(gait=_abi.FHP_GAIT_WALK)),
+                          (3000, 40, _abi.yaml_params()), (70000, 6, _abi.yaml_params(heading=0.7))):
+        q = synth.uniform_queries(nq, (-10.0, 3.0), (-10.0, 10.0), seed=nq)
+        nom, _, st = fhp.plan(p, q, cycles)
+        blocks, masks, st2 = fhp.plan_stream(p, q, cycles)
+        assert np.array_equal(st, st2)
+        assert blocks.shape == (cycles + 1, (nq + 7) // 8, 32) and masks.shape == (nq, (cycles + 31) // 32, 4)
+        for qi in range(0, nq, max(1, nq // 257)):
+            rows = nom[qi][: st[qi]["n_rows"]]
+            pts, foot, cyc, kind = Fhp.stream_rows_of(blocks, masks, qi)
+            assert len(pts) == len(rows)
+            assert np.array_equal(pts["x"], rows["x"]) and np.array_equal(pts["y"], rows["y"])
+            assert np.array_equal(pts["z"].astype(np.float64), rows["z"])
+            assert np.array_equal(foot, rows["foot_id"]) and np.array_equal(cyc, rows["gait_cycle_id"])
+            assert np.array_equal(kind[4:], rows["kind"][4:])
+        # whole batch: the four feet agree on success, popcount == successful cycles, unwritten row slots are still zero
+        succ = masks["success"]
+        assert np.all(succ == succ[:, :, :1])
+        pop = np.array([bin(int(w)).count("1") for w in succ[:, :, 0].reshape(-1)]).reshape(nq, -1).sum(1)
+        assert np.array_equal(pop, (st["n_rows"] - 4) // 4)
+        groups = (nq + 7) // 8
+        for g in range(cycles):
+            ok = ((succ[:, g // 32, 0] >> np.uint32(g % 32)) & 1).astype(np.int64)
+            per_group = np.bincount(np.arange(nq) // 8, weights=ok, minlength=groups).astype(np.int64)
+            tail = np.arange(32)[None, :] >= (per_group * 4)[:, None]
+            assert not blocks[g + 1][tail].view(np.uint8).any()
+    q = synth.uniform_queries(8, (-10.0, 3.0), (-10.0, 10.0), seed=3)
+    parr, npar = fhp._params_array(_abi.yaml_params())
+    pageable = np.zeros(9 * 32 + 16, dtype=_abi.POINT20_DTYPE)
+    with pytest.raises(FhpError, match="page-locked|aligned"):
+        fhp.plan_stream_raw(parr, npar, q, 8, 8, pageable, np.zeros(64, np.uint32), np.zeros(8, _abi.STATUS_DTYPE))
+
+
 @pytest.mark.parametrize("foot_radius", [0.031, 0.05, 0.085])
 def test_wide_foot_discs(fhp, oracle, foot_radius):
     """Foot discs of 1.5 / 2.5 / 4.25 cells: the disc-membership fast path (k = 2, 3) and, for the widest, the generic
