@@ -80,6 +80,7 @@ struct fhp_ctx {
   int tmaBoxBudget = 8192;
   // FHP_FORCE_HEADING=1 (test knob, read at fhp_create): run the heading expressions even for heading == 0, where they
   // must reduce bit-exactly to the reference's (tests/test_gpu_heading.py)
+  bool noSpec = false;  // FHP_NO_SPEC=1 (test knob): never pick a geometry-specialised kernel variant (GeoK)
   bool forceHeading = false;
   bool anyHeading = false;  // some parameter set of the current call has the heading expressions in force
   // D/C/F mask planes of the traversability layer for one threshold pair (rebuilt lazily after a map update)
@@ -659,6 +660,7 @@ int fhp_create(int device, fhp_ctx** out) {
   if (const char* v = std::getenv("FHP_QPW_SHIFT")) ctx->qpwShiftForce = std::max(0, std::min(3, atoi(v)));
   if (const char* v = std::getenv("FHP_TMA_BOX_BUDGET")) ctx->tmaBoxBudget = std::max(1024, atoi(v));
   if (const char* v = std::getenv("FHP_FORCE_HEADING")) ctx->forceHeading = v[0] == '1';
+  if (const char* v = std::getenv("FHP_NO_SPEC")) ctx->noSpec = v[0] == '1';
   if (const char* st = std::getenv("FHP_STAGING")) {
     if (!std::strcmp(st, "mask")) ctx->stagePref = kStageMask;
     else if (!std::strcmp(st, "tma")) ctx->stagePref = kStageTma;
@@ -975,7 +977,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.st = d_st;
   A.err = ctx->dErrMapped;
   {
-    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, ctx->anyHeading, s);
+    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, ctx->anyHeading, ctx->noSpec, s);
     if (e != cudaSuccess) {
       char b[256];
       snprintf(b, sizeof b, "plan kernel launch failed: %s (queries %lld, queries/warp %d, shared memory %d B)",

@@ -26,9 +26,72 @@
 
 namespace fhp {
 
+// Geometry as the device code sees it.  SPEC 0: every value is read from the GeoDev tables (any geometry).  SPEC > 0:
+// the values of ONE concrete geometry are compile-time constants — the staging, plane and scan loops unroll, the generic
+// branches (wide discs, multi-cell foot stencils, packed plane layouts) vanish and the register allocator has less to
+// keep alive: 15 % fewer cycles on the yaml geometry at 0.02 m (profiles/r2_*).  The host picks a specialised kernel only
+// when the tables it built match the constants exactly (geo_spec_of, fhp_capi.cu); specialised variants exist for the
+// cell-class (mask) staging path only, so pack = 1 and the plane pitch follows from WIN.
+template <int SPEC>
+struct GeoK {
+  static constexpr bool fixed = false;
+  static constexpr int WIN = 0, HW = 0, nSten = 0, discK = 0, nCand = 0, lastTwoStart = 0, nRings = 0, ra = 0;
+};
+template <>
+struct GeoK<1> {  // footRadius 0.02, searchRadius 0.1 at 0.02 m (yaml:17-44), rings trimmed to 5 (build_geo)
+  static constexpr bool fixed = true;
+  static constexpr int WIN = 11, HW = 5, nSten = 1, discK = 1, nCand = 109, lastTwoStart = 69, nRings = 6, ra = 0;
+};
+template <>
+struct GeoK<2> {  // the same radii at 0.01 m: 3x3 foot stencil, rings trimmed to 10
+  static constexpr bool fixed = true;
+  static constexpr int WIN = 23, HW = 11, nSten = 9, discK = 2, nCand = 373, lastTwoStart = 305, nRings = 11, ra = 1;
+};
+template <int SPEC>
+struct GeoV {
+  using K = GeoK<SPEC>;
+  const GeoDev& g;
+  __device__ __forceinline__ explicit GeoV(const GeoDev& g_) : g(g_) {}
+#define FHP_GEO_K(name) \
+  __device__ __forceinline__ int name() const { if constexpr (K::fixed) return K::name; else return g.name; }
+  FHP_GEO_K(WIN) FHP_GEO_K(HW) FHP_GEO_K(nSten) FHP_GEO_K(discK) FHP_GEO_K(nCand) FHP_GEO_K(lastTwoStart) FHP_GEO_K(nRings) FHP_GEO_K(ra)
+#undef FHP_GEO_K
+  __device__ __forceinline__ int nIter() const { if constexpr (K::fixed) return K::WIN; else return g.nIter; }
+  __device__ __forceinline__ int stride() const { if constexpr (K::fixed) return 4 * K::WIN; else return g.stride; }
+  __device__ __forceinline__ int winRows() const { if constexpr (K::fixed) return K::WIN; else return g.winRows; }
+  __device__ __forceinline__ int pack() const { if constexpr (K::fixed) return 1; else return g.pack; }
+  __device__ __forceinline__ int rpShift() const { if constexpr (K::fixed) return 5; else return g.rpShift; }
+#define FHP_GEO_R(name) __device__ __forceinline__ int name() const { return g.name; }
+  FHP_GEO_R(spiralWords) FHP_GEO_R(smemWords) FHP_GEO_R(stageMode) FHP_GEO_R(useTma) FHP_GEO_R(tmaB) FHP_GEO_R(tmaBShift)
+  FHP_GEO_R(boxWords) FHP_GEO_R(mbarOff) FHP_GEO_R(boxOff)
+#undef FHP_GEO_R
+};
+
+// Inlining policy of the small geometry helpers (A/B knobs: the hot loop's instruction footprint vs call overhead)
+#ifdef FHP_NI_RAW
+#define FHP_INL_RAW __noinline__
+#else
+#define FHP_INL_RAW __forceinline__
+#endif
+#ifdef FHP_NI_BOUND
+#define FHP_INL_BOUND __noinline__
+#else
+#define FHP_INL_BOUND __forceinline__
+#endif
+#ifdef FHP_NI_FB
+#define FHP_INL_FB __noinline__
+#else
+#define FHP_INL_FB __forceinline__
+#endif
+#ifdef FHP_NI_PC
+#define FHP_INL_PC __noinline__
+#else
+#define FHP_INL_PC __forceinline__
+#endif
+
 // ------------------------------------------------------------------------------------------------ grid_map math
 // boundPositionToRange (GridMapMath.cpp) for one axis
-__device__ __forceinline__ double bound_axis(double p, double len, double mp, double half) {
+__device__ FHP_INL_BOUND double bound_axis(double p, double len, double mp, double half) {
   double shifted = (p - mp) + half;
   double eps = 10.0 * 2.220446049250313e-16;
   if (fabs(p) > 1.0) eps *= fabs(p);
@@ -58,7 +121,7 @@ __device__ __forceinline__ double div3_rn(double a) {
 // Fast path: multiply by the correctly rounded reciprocal; the product differs from the IEEE quotient by at most a
 // few ulp, so the truncated integer can only differ when the value sits within that distance of an integer —
 // then (and only then) the exact division decides.  `rinv` = 1/res (MapDev::rinv).
-__device__ __forceinline__ int raw_index_axis(double p, double half, double mp, double res, double rinv) {
+__device__ FHP_INL_RAW int raw_index_axis(double p, double half, double mp, double res, double rinv) {
   const double x = (p - half) - mp;
   double t = -(x * rinv);
   // (int) of a NaN / out-of-int-range double is UB upstream (x86 cvttsd2si yields INT_MIN).  Policy shared with the
@@ -168,12 +231,13 @@ constexpr int kStageChunk = 8;
 #endif
 constexpr int kStageBatch = FHP_STAGE_BATCH;  // class-plane entries a lane has in flight while staging its window
 
-__device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint32_t dst, int lane, int k0, const float (&v)[kStageChunk],
+template <class GV>
+__device__ __forceinline__ void stage_chunk_ballots(const GV& G, uint32_t dst, int lane, int k0, const float (&v)[kStageChunk],
                                                     float tD, float tC) {
   const float inf = __int_as_float(0x7f800000);
 #pragma unroll
   for (int i = 0; i < kStageChunk; ++i) {
-    if (k0 + i < G.nIter) {
+    if (k0 + i < G.nIter()) {
       const uint32_t bD = __ballot_sync(kFull, v[i] < tD);
       const uint32_t bC = __ballot_sync(kFull, v[i] < tC);
       const uint32_t bF = __ballot_sync(kFull, fabsf(v[i]) < inf);
@@ -183,11 +247,12 @@ __device__ __forceinline__ void stage_chunk_ballots(const GeoDev& G, uint32_t ds
 }
 
 // Generic per-cell staging (windows touching the map border or the circular-buffer seam).
-__device__ __noinline__ void stage_slow(const MapDev& M, const GeoDev& G, uint32_t smemWarp, int lane, unsigned slowMask,
+template <class GV>
+__device__ __noinline__ void stage_slow(const MapDev& M, const GV& G, uint32_t smemWarp, int lane, unsigned slowMask,
                                         int w0, int w1, float thrD, float thrC) {
-  const int RP = 1 << G.rpShift;
+  const int RP = 1 << G.rpShift();
   const int a = lane & (RP - 1);
-  const int h = lane >> G.rpShift;
+  const int h = lane >> G.rpShift();
   const float inf = __int_as_float(0x7f800000);
   for (unsigned m = slowMask; m; m &= m - 1) {
     const int j = __ffs(m) - 1;
@@ -195,14 +260,14 @@ __device__ __noinline__ void stage_slow(const MapDev& M, const GeoDev& G, uint32
     const int jw1 = __shfl_sync(kFull, w1, j);
     const float tD = __shfl_sync(kFull, thrD, j);
     const float tC = __shfl_sync(kFull, thrC, j);
-    const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride) * 4u;
+    const uint32_t dst = smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u;
     const int u0 = jw0 + a;
     const bool in0 = u0 >= 0 && u0 < M.rows;  // all RP rows: the TMA path may have shifted the origin down by <= 3
     const int b0 = wrap_add(u0, M.start0, M.rows);
-    for (int k = 0; k < G.nIter; ++k) {
-      const int b = k * G.pack + h;
+    for (int k = 0; k < G.nIter(); ++k) {
+      const int b = k * G.pack() + h;
       const int u1 = jw1 + b;
-      const bool in = in0 && (b < G.WIN) && u1 >= 0 && u1 < M.cols;
+      const bool in = in0 && (b < G.WIN()) && u1 >= 0 && u1 < M.cols;
       const int b1 = wrap_add(u1, M.start1, M.cols);
       float v = __int_as_float(0x7fc00000);
       if (in) v = __ldg(M.trav + static_cast<size_t>(b1) * M.rows + b0);
@@ -214,12 +279,13 @@ __device__ __noinline__ void stage_slow(const MapDev& M, const GeoDev& G, uint32
   }
 }
 
-__device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, uint32_t smemWarp, int lane,
+template <class GV>
+__device__ __forceinline__ void stage_windows(const MapDev& M, const GV& G, uint32_t smemWarp, int lane,
                                               bool has_window, int w0, int w1, float thrD, float thrC) {
-  const int RP = 1 << G.rpShift;
+  const int RP = 1 << G.rpShift();
   const int a = lane & (RP - 1);
-  const int h = lane >> G.rpShift;
-  const int colsCovered = G.nIter * G.pack;
+  const int h = lane >> G.rpShift();
+  const int colsCovered = G.nIter() * G.pack();
   // every lane classifies ITS OWN window and computes its buffer origin (|w| <= 2^30 + HW: no overflow)
   int bb0 = w0 + M.start0, bb1 = w1 + M.start1;
   if (bb0 >= M.rows) bb0 -= M.rows;
@@ -240,15 +306,15 @@ __device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, 
   __syncwarp();
 
   if (fastMask) {
-    const int nChunks = (G.nIter + kStageChunk - 1) / kStageChunk;
-    const long long step = static_cast<long long>(G.pack) * M.rows;
+    const int nChunks = (G.nIter() + kStageChunk - 1) / kStageChunk;
+    const long long step = static_cast<long long>(G.pack()) * M.rows;
     const float* laneBase = M.trav + static_cast<long long>(h) * M.rows + a;
     float nxt[kStageChunk], cur[kStageChunk];
     int jn = __ffs(fastMask) - 1, cn = 0;
     {
       const float* p = laneBase + __shfl_sync(kFull, org, jn);
 #pragma unroll
-      for (int i = 0; i < kStageChunk; ++i) nxt[i] = (i < G.nIter) ? __ldg(p + i * step) : 0.0f;
+      for (int i = 0; i < kStageChunk; ++i) nxt[i] = (i < G.nIter()) ? __ldg(p + i * step) : 0.0f;
     }
     for (;;) {
       const int j = jn, c = cn;
@@ -270,11 +336,11 @@ __device__ __forceinline__ void stage_windows(const MapDev& M, const GeoDev& G, 
         const float* p = laneBase + __shfl_sync(kFull, org, jn) + static_cast<long long>(cn) * kStageChunk * step;
         const int k0n = cn * kStageChunk;
 #pragma unroll
-        for (int i = 0; i < kStageChunk; ++i) nxt[i] = (k0n + i < G.nIter) ? __ldg(p + i * step) : 0.0f;
+        for (int i = 0; i < kStageChunk; ++i) nxt[i] = (k0n + i < G.nIter()) ? __ldg(p + i * step) : 0.0f;
       }
       const float tD = uni ? tD0 : __shfl_sync(kFull, thrD, j);
       const float tC = uni ? tC0 : __shfl_sync(kFull, thrC, j);
-      stage_chunk_ballots(G, smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, lane, c * kStageChunk, cur, tD, tC);
+      stage_chunk_ballots(G, smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, lane, c * kStageChunk, cur, tD, tC);
       if (!more) break;
     }
   }
@@ -362,11 +428,12 @@ struct TmaWarp {       // per-warp TMA staging state (lives in registers across 
 // a conflict-free linear read.  Eligible = the window does not wrap around the circular-buffer seam and, when the
 // start index is non-zero, lies inside the map (with start index (0,0) buffer coordinates equal map coordinates,
 // so the tensor map's NaN out-of-bounds fill IS grid_map's "cell outside the map is not visited").
-__device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev& G, const void* tmap, TmaWarp& T,
+template <class GV>
+__device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GV& G, const void* tmap, TmaWarp& T,
                                                   uint32_t smemWarp, int lane, bool has_window, int w0, int w1,
                                                   float thrD, float thrC) {
-  const int RP = 1 << G.rpShift;
-  const int colsCovered = G.nIter * G.pack;
+  const int RP = 1 << G.rpShift();
+  const int colsCovered = G.nIter() * G.pack();
   const bool start0 = (M.start0 == 0) && (M.start1 == 0);
   // a window with no cell inside the map stages as all-"not visited": the owning lane just clears its planes
   const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -RP || w1 <= -colsCovered);
@@ -392,24 +459,24 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
   const bool uni = __all_sync(kFull, !has_window || (thrD == tD0 && thrC == tC0));
   __syncwarp();  // every lane is done reading the planes of the previous leg/cycle
   if (empty) {
-    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
-    for (int k = 0; k < G.nIter; ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
+    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
+    for (int k = 0; k < G.nIter(); ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
   }
 
   const int nFast = __popc(fastMask);
   if (nFast) {
-    const int B = 1 << G.tmaBShift;
-    const int nRounds = (nFast + B - 1) >> G.tmaBShift;
-    const uint32_t boxBytes = static_cast<uint32_t>(G.boxWords) * 4u;
+    const int B = 1 << G.tmaBShift();
+    const int nRounds = (nFast + B - 1) >> G.tmaBShift();
+    const uint32_t boxBytes = static_cast<uint32_t>(G.boxWords()) * 4u;
     const float inf = __int_as_float(0x7f800000);
     // every eligible lane issues the box of ITS window; cp.async.bulk.tensor is a warp-uniform instruction (UTMALDG),
     // so the hardware loop ptxas wraps around it (ELECT / R2UR.BROADCAST / BRA.U.ANY) serialises the active lanes
     const int rank = __popc(fastMask & ((1u << lane) - 1u));
-    const int myRound = rank >> G.tmaBShift;
-    const uint32_t myBox = T.boxAddr + static_cast<uint32_t>(((myRound & 1) << G.tmaBShift) + (rank & (B - 1))) * boxBytes;
+    const int myRound = rank >> G.tmaBShift();
+    const uint32_t myBox = T.boxAddr + static_cast<uint32_t>(((myRound & 1) << G.tmaBShift()) + (rank & (B - 1))) * boxBytes;
     auto issue = [&](int r) {
       const int buf = r & 1;
-      const int cnt = min(B, nFast - (r << G.tmaBShift));
+      const int cnt = min(B, nFast - (r << G.tmaBShift()));
       if (lane == 0) mbar_expect_tx(T.bar[buf], static_cast<uint32_t>(cnt) * boxBytes);
       if (elig && myRound == r) tma_load_box(myBox, tmap, c0, c1, T.bar[buf]);
     };
@@ -423,14 +490,14 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
       while (!mbar_try_wait(T.bar[buf], T.parity[buf])) {
       }
       T.parity[buf] ^= 1u;
-      const int cnt = min(B, nFast - (r << G.tmaBShift));
-      uint32_t src = T.boxAddr + static_cast<uint32_t>(buf << G.tmaBShift) * boxBytes + static_cast<uint32_t>(lane) * 4u;
+      const int cnt = min(B, nFast - (r << G.tmaBShift()));
+      uint32_t src = T.boxAddr + static_cast<uint32_t>(buf << G.tmaBShift()) * boxBytes + static_cast<uint32_t>(lane) * 4u;
       for (int sidx = 0; sidx < cnt; ++sidx) {
         const int j = __ffs(rem) - 1;
         rem &= rem - 1;
         const float tD = uni ? tD0 : __shfl_sync(kFull, thrD, j);
         const float tC = uni ? tC0 : __shfl_sync(kFull, thrC, j);
-        convert_box(G.nIter, src, smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, lane, tD, tC);
+        convert_box(G.nIter(), src, smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, lane, tD, tC);
         src += boxBytes;
       }
       __syncwarp();
@@ -454,15 +521,16 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GeoDev&
 // per column).
 // Fast = the window lies inside the map and does not cross the circular-buffer ROW seam (the column seam is
 // handled per column); everything else takes stage_slow on the float layer, exactly like the other paths.
-__device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev& G, const uint4* __restrict__ mask,
+template <class GV>
+__device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GV& G, const uint4* __restrict__ mask,
                                                    uint32_t smemWarp, int lane, bool has_window, int w0, int w1,
                                                    float thrD, float thrC) {
-  const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -32 || w1 <= -G.WIN);
+  const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -32 || w1 <= -G.WIN());
   int bb0 = w0 + M.start0, bb1 = w1 + M.start1;  // |w| <= 2^30 + HW: no overflow
   if (bb0 >= M.rows) bb0 -= M.rows;
   if (bb1 >= M.cols) bb1 -= M.cols;
-  const bool fast = has_window && w0 >= 0 && w1 >= 0 && w0 <= M.rows - G.WIN && w1 <= M.cols - G.WIN &&
-                    bb0 <= M.rows - G.WIN;
+  const bool fast = has_window && w0 >= 0 && w1 >= 0 && w0 <= M.rows - G.WIN() && w1 <= M.cols - G.WIN() &&
+                    bb0 <= M.rows - G.WIN();
   const unsigned fastMask = __ballot_sync(kFull, fast);
   const unsigned slowMask = __ballot_sync(kFull, has_window && !fast && !empty);
   if (__ballot_sync(kFull, has_window) == 0u) {
@@ -471,15 +539,15 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
   }
   __syncwarp();  // every lane is done reading the planes of the previous leg/cycle
   if (empty) {
-    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
-    for (int k = 0; k < G.nIter; ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
+    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
+    for (int k = 0; k < G.nIter(); ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
   }
   if (fast) {  // every lane stages ITS OWN window: WIN independent 16-byte loads, no cross-lane traffic
     const uint4* src = mask + (bb0 >> 5) * M.cols;
     const int s = bb0 & 31;
-    const uint32_t dst = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
+    const uint32_t dst = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
     int col = bb1;
-    for (int c = 0; c < G.WIN; c += kStageBatch) {
+    for (int c = 0; c < G.WIN(); c += kStageBatch) {
       uint4 e[kStageBatch];
 #pragma unroll
       for (int i = 0; i < kStageBatch; ++i) {
@@ -489,7 +557,7 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GeoDev
       }
 #pragma unroll
       for (int i = 0; i < kStageBatch; ++i)
-        if (c + i < G.WIN) {
+        if (c + i < G.WIN()) {
           const uint32_t e0 = __funnelshift_r(e[i].x, e[i].y, s), e1 = __funnelshift_r(e[i].z, e[i].w, s);
           sts_v4(dst + static_cast<uint32_t>(c + i) * 16u, e1, e0 & e1, e0 | e1, 0u);
         }
@@ -556,13 +624,14 @@ __device__ __noinline__ DiscWin disc_window_generic(const MapDev& M, double cx, 
   d.generic = 1;
   return d;
 }
-__device__ __forceinline__ DiscWin disc_window(const MapDev& M, const GeoDev& G, double cx, double cy, int uc0, int uc1,
+template <class GV>
+__device__ __forceinline__ DiscWin disc_window(const MapDev& M, const GV& G, double cx, double cy, int uc0, int uc1,
                                                double r, double r2) {
   // wide discs: upstream's window, membership decided by the consumers' generic loops
-  if (G.discK < 0) return disc_window_generic(M, cx, cy, r);
+  if (G.discK() < 0) return disc_window_generic(M, cx, cy, r);
   DiscWin d;
   d.generic = 0;
-  const int k = G.discK;
+  const int k = G.discK();
   d.tl0 = uc0 - k;
   d.tl1 = uc1 - k;
   d.br0 = uc0 + k;
@@ -685,7 +754,8 @@ __device__ __forceinline__ float mean_height_loaded(const MapDev& M, const ParDe
   }
   return static_cast<float>(static_cast<double>(meanHeight) + P.h);
 }
-__device__ __forceinline__ float mean_height(const MapDev& M, const GeoDev& G, const ParDev& P, double cx, double cy) {
+template <class GV>
+__device__ __forceinline__ float mean_height(const MapDev& M, const GV& G, const ParDev& P, double cx, double cy) {
   const int uc0 = raw_index_axis(cx, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(cy, M.halfy, M.posy, M.res, M.rinv);
   return mean_height(M, P, cx, cy, disc_window(M, G, cx, cy, uc0, uc1, P.r, P.r2));
 }
@@ -712,7 +782,8 @@ struct CentroidOut {
 };
 // FootholdPlanner::checkFootholdUseCentroidMethod (FP.cpp:1605-1997) on the staged planes of this lane.
 // (w0,w1): unwrapped origin of the staged window.
-__device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl,
+template <class GV>
+__device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GV& G, const ParDev& P, const Planes& pl,
                                                      int w0, int w1, double px, double py, unsigned& err) {
   CentroidOut o;
   o.x = 0.0;
@@ -743,7 +814,7 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GeoD
   // window coordinates of the submap inside the staged planes
   const int a0 = tl0 - w0, a1 = br0 - w0, c0 = tl1 - w1, c1 = br1 - w1;
   uint32_t any, edgeRel;  // bit i <-> submap row i: any cell below the threshold / row is an "edge"
-  if (a0 < 0 || c0 < 0 || a1 >= G.winRows || c1 >= G.WIN) {
+  if (a0 < 0 || c0 < 0 || a1 >= G.winRows() || c1 >= G.WIN()) {
     // the submap sticks out of the staged window (its size is one cell larger when the corner's lattice phase is
     // within ~1e-7 of a cell boundary): count straight from global memory
     const unsigned long long pk = centroid_rows_slow(M, P.thrD, tl0, tl1, n0, n1);
@@ -865,7 +936,8 @@ __device__ __forceinline__ Box search_box(const ParDev& P, double rx, double ry)
 }
 
 // FootholdPlanner::checkDefaultFoothold (FP.cpp:2039-2082): CircleIterator(centre, footRadius) on the staged planes.
-__device__ __noinline__ bool default_eval_generic(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl,
+template <class GV>
+__device__ __noinline__ bool default_eval_generic(const MapDev& M, const GV& G, const ParDev& P, const Planes& pl,
                                                   int w0, int w1, double cx, double cy, const DiscWin& dw, unsigned& err) {
   int visited = 0;
   bool below = false;
@@ -877,7 +949,7 @@ __device__ __noinline__ bool default_eval_generic(const MapDev& M, const GeoDev&
       if (!(dx2 + dy * dy <= P.r2) || !in_map(M, u0, u1)) continue;
       ++visited;
       const int a = u0 - w0, b = u1 - w1;
-      if (a < 0 || b < 0 || a >= G.winRows || b >= G.WIN) {
+      if (a < 0 || b < 0 || a >= G.winRows() || b >= G.WIN()) {
         err |= kErrWindow;
         continue;
       }
@@ -887,12 +959,13 @@ __device__ __noinline__ bool default_eval_generic(const MapDev& M, const GeoDev&
   }
   return (visited > 0) && !below;
 }
-__device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, const ParDev& P, const Planes& pl, int w0,
+template <class GV>
+__device__ __forceinline__ bool default_eval(const MapDev& M, const GV& G, const ParDev& P, const Planes& pl, int w0,
                                              int w1, double cx, double cy, const DiscWin& dw, unsigned& err) {
   if (!dw.small()) return default_eval_generic(M, G, P, pl, w0, w1, cx, cy, dw, err);
   if (dw.m == 0ull) return false;  // the disc visits no cell
   const int a0 = dw.tl0 - w0, b0 = dw.tl1 - w1;
-  if (a0 < 0 || b0 < 0 || dw.br0 - w0 >= G.winRows || dw.br1 - w1 >= G.WIN) {
+  if (a0 < 0 || b0 < 0 || dw.br0 - w0 >= G.winRows() || dw.br1 - w1 >= G.WIN()) {
     err |= kErrWindow;
     return false;
   }
@@ -909,16 +982,16 @@ __device__ __forceinline__ bool default_eval(const MapDev& M, const GeoDev& G, c
 // The cell-centre coordinate pos(org + a) strictly decreases with a, so "pos < bound" is false...false,true...true
 // over a = 0..n-1: first_below returns the first a where it holds (n if none), found from a reciprocal estimate and
 // verified with the exact predicate on both sides (any estimate gives the right answer; a good one costs two tests).
-__device__ __forceinline__ int first_below(double fc, double res, double rinv, int org, int n, double bound) {
+__device__ FHP_INL_FB int first_below(double fc, double res, double rinv, int org, int n, double bound) {
   // pos(org+a) < bound  <=>  a > t with t = (fc - bound)/res - org.  The estimate below and the exact pos() each
   // carry errors of ~1e-12 cells (|indices| < 2^30 is far from reached: maps have < 2^16 cells per axis), so when
   // t is farther than 1e-6 from an integer both orderings agree and the first integer above t IS the answer; only in
   // that band (and for NaN bounds) the exact predicate decides, walking from the estimate.
-  double t = (fc - bound) * rinv - static_cast<double>(org);
-  const bool certain = fabs(t - rint(t)) > 1e-6 && fabs(t) < 1.0e6;
-  t = fmin(fmax(t, -1.0), static_cast<double>(n));  // NaN -> -1
-  int a = static_cast<int>(floor(t)) + 1;
-  a = max(0, min(a, n));
+  const double t = (fc - bound) * rinv - static_cast<double>(org);
+  const int fl = __double2int_rd(t);  // saturating; NaN -> 0 (then not "certain": the exact walk decides)
+  const double fr = t - static_cast<double>(fl);
+  const bool certain = fr > 1e-6 && fr < 1.0 - 1e-6 && fabs(t) < 1.0e6;
+  int a = min(max(fl, -1), n - 1) + 1;  // in [0, n]
   if (!certain) {
     while (a > 0 && pos_axis(fc, res, org + a - 1) < bound) --a;
     while (a < n && !(pos_axis(fc, res, org + a) < bound)) ++a;
@@ -930,13 +1003,14 @@ __device__ __forceinline__ uint32_t bits_between(int lo, int hi) {  // bits lo..
   const uint32_t upTo = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
   return upTo & ~((1u << lo) - 1u);
 }
-__device__ __forceinline__ void box_masks(const MapDev& M, const GeoDev& G, const Box& bx, int w0, int w1,
+template <class GV>
+__device__ __forceinline__ void box_masks(const MapDev& M, const GV& G, const Box& bx, int w0, int w1,
                                           uint32_t& rowsBox, uint32_t& colsBox) {
   // inside: lo <= pos < hi  <=>  first_below(hi) <= a < first_below(lo)
-  rowsBox = bits_between(first_below(M.fcx, M.res, M.rinv, w0, G.winRows, bx.xhi),
-                         first_below(M.fcx, M.res, M.rinv, w0, G.winRows, bx.xlo));
-  colsBox = bits_between(first_below(M.fcy, M.res, M.rinv, w1, G.WIN, bx.yhi),
-                         first_below(M.fcy, M.res, M.rinv, w1, G.WIN, bx.ylo));
+  rowsBox = bits_between(first_below(M.fcx, M.res, M.rinv, w0, G.winRows(), bx.xhi),
+                         first_below(M.fcx, M.res, M.rinv, w0, G.winRows(), bx.xlo));
+  colsBox = bits_between(first_below(M.fcy, M.res, M.rinv, w1, G.WIN(), bx.yhi),
+                         first_below(M.fcy, M.res, M.rinv, w1, G.WIN(), bx.ylo));
 }
 
 // ---- heading extension: the search rectangle is a ROTATED rectangle, so grid_map::Polygon::isInside is the general
@@ -983,12 +1057,12 @@ __device__ __noinline__ uint32_t poly_col_rows(const MapDev& M, const ParDev& P,
 // checkCirclePolygonFoothold (FP.cpp:2117-2163) for the candidate at window coordinates (qa,qb), on the planes:
 // every finite cell of the foot disc must be >= candidateFootholdThreshold and inside the box.  HEADING: the owning
 // lane has left the finished "bad cell" masks (polygon included) in plane 3 of its slot (nominal_eval).
-template <bool HEADING>
-__device__ __forceinline__ bool candidate_on_planes(const GeoDev& G, const Planes& pl, int qa, int qb, uint32_t rowsBox,
+template <bool HEADING, class GV>
+__device__ __forceinline__ bool candidate_on_planes(const GV& G, const Planes& pl, int qa, int qb, uint32_t rowsBox,
                                                     uint32_t colsBox) {
   bool good = true;
-  for (int s = 0; s < G.nSten && good; ++s) {
-    const int a = qa + G.sten[s][0], b = qb + G.sten[s][1];
+  for (int s = 0; s < G.nSten() && good; ++s) {
+    const int a = qa + G.g.sten[s][0], b = qb + G.g.sten[s][1];
     // a,b are inside the window by construction (|d| <= nRings, |sten| <= ra); cells outside the map have
     // F = 0 and are skipped like the iterator skips them
     uint32_t bad;
@@ -1029,12 +1103,12 @@ __device__ __noinline__ bool circle_polygon_direct(const MapDev& M, const ParDev
 
 // One candidate evaluated straight from global memory (faithful-mode candidates that wrap to the far side of the
 // circular buffer): checkCirclePolygonFoothold (FP.cpp:2117-2163).
-template <bool HEADING>
-__device__ __noinline__ bool candidate_slow(const MapDev& M, const GeoDev& G, const ParDev& P, int q0, int q1, const Box& bx) {
+template <bool HEADING, class GV>
+__device__ __noinline__ bool candidate_slow(const MapDev& M, const GV& G, const ParDev& P, int q0, int q1, const Box& bx) {
   const float thrC = P.thrC;
   const double xlo = bx.xlo, xhi = bx.xhi, ylo = bx.ylo, yhi = bx.yhi, rx = bx.xlo, ry = bx.ylo;  // (HEADING: centre)
-  for (int s = 0; s < G.nSten; ++s) {
-    const int u0 = q0 + G.sten[s][0], u1 = q1 + G.sten[s][1];
+  for (int s = 0; s < G.nSten(); ++s) {
+    const int u0 = q0 + G.g.sten[s][0], u1 = q1 + G.g.sten[s][1];
     if (!in_map(M, u0, u1)) continue;
     const float v = load_cell(M, M.trav, u0, u1);
     if (!(fabsf(v) < __int_as_float(0x7f800000))) continue;
@@ -1071,8 +1145,8 @@ __device__ __forceinline__ uint32_t in_range_mask(int org, int n, int nBits) {
 //      one bit test, plus the exact last-two-rings distance filter; the first set bit of the ballot is the first
 //      valid cell in spiral order and the scan stops at the first 32-block that has one.
 // Handles wrap_correct mode, and faithful mode when the start index is (0,0) (identical there).
-template <bool PAD, bool HEADING>
-__device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& G, const uint16_t* sSpiral,
+template <bool PAD, bool HEADING, class GV>
+__device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GV& G, const uint16_t* sSpiral,
                                                  uint32_t smemWarp, int lane, bool need, int uc0, int uc1,
                                                  int w0, double cx, double cy, double R2, uint32_t rowsBox,
                                                  uint32_t colsBox, uint32_t rowsIn, uint32_t colsIn, bool& found,
@@ -1086,27 +1160,27 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
     // 1. column masks (lane = window column)
     uint32_t bad = 0;
     if (PAD) {
-      if (lane < G.WIN) bad = lds_u32(smemWarp + static_cast<uint32_t>(j * G.stride + lane * 4 + 3) * 4u);
+      if (lane < G.WIN()) bad = lds_u32(smemWarp + static_cast<uint32_t>(j * G.stride() + lane * 4 + 3) * 4u);
     } else if (HEADING) {  // the owning lane has left the finished masks (rotated rectangle included) in plane 3
-      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
-      if (lane < G.WIN) bad = pj.col(3, lane);
+      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, G.pack(), G.rpShift());
+      if (lane < G.WIN()) bad = pj.col(3, lane);
     } else {
       const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
-      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride) * 4u, G.pack, G.rpShift);
-      if (lane < G.WIN) {
+      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, G.pack(), G.rpShift());
+      if (lane < G.WIN()) {
         const uint32_t F = pj.col(PL_F, lane), C = pj.col(PL_C, lane);
         const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
         bad = F & (C | ~box);
       }
     }
     uint32_t dil = bad;
-    if (G.nSten > 1) {  // dilate by the foot-disc stencil (a single-cell stencil needs nothing)
+    if (G.nSten() > 1) {  // dilate by the foot-disc stencil (a single-cell stencil needs nothing)
       dil = 0;
-      for (int s = 0; s < G.nSten; ++s) {
-        const int s0 = G.sten[s][0], s1 = G.sten[s][1];
+      for (int s = 0; s < G.nSten(); ++s) {
+        const int s0 = G.g.sten[s][0], s1 = G.g.sten[s][1];
         const int srcCol = lane + s1;
         uint32_t nb = __shfl_sync(kFull, bad, srcCol & 31);
-        if (srcCol < 0 || srcCol >= G.WIN) nb = 0;
+        if (srcCol < 0 || srcCol >= G.WIN()) nb = 0;
         dil |= (s0 >= 0) ? (nb >> s0) : (nb << (-s0));
       }
     }
@@ -1115,23 +1189,23 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
     // quick reject: no cell of the spiral footprint is acceptable even before the distance filter (a query that is
     // stuck on an untraversable patch re-scans the same window every remaining cycle).  With a single-cell stencil the
     // PAD variant has already made this test in the owning lane.
-    if (!PAD || G.nSten > 1) {
-      const uint32_t footprint = (lane < G.WIN) ? (G.candRows[lane] << (ha - G.HW)) : 0u;
+    if (!PAD || G.nSten() > 1) {
+      const uint32_t footprint = (lane < G.WIN()) ? (G.g.candRows[lane] << (ha - G.HW())) : 0u;
       if (__ballot_sync(kFull, (footprint & ~dil) != 0u) == 0u) continue;
     }
     // 2. rank scan
     bool haveC = false;
     double jcx = 0, jcy = 0, jR2 = 0;
     int juc0 = 0, juc1 = 0;
-    for (int base = 0; base < G.nCand; base += 32) {
+    for (int base = 0; base < G.nCand(); base += 32) {
       const int k = base + lane;
-      bool cand = k < G.nCand;
+      bool cand = k < G.nCand();
       int d0, d1;
       spiral_entry(sSpiral, cand ? k : 0, d0, d1);
-      const int qa = d0 + ha, qb = d1 + G.HW;
+      const int qa = d0 + ha, qb = d1 + G.HW();
       const uint32_t e = __shfl_sync(kFull, dil, qb);
       cand = cand && !((e >> qa) & 1u);
-      if (base + 32 > G.lastTwoStart) {  // rings nRings-1, nRings: distance filter (uniform branch)
+      if (base + 32 > G.lastTwoStart()) {  // rings nRings-1, nRings: distance filter (uniform branch)
         if (!haveC) {
           jcx = __shfl_sync(kFull, cx, j);
           jcy = __shfl_sync(kFull, cy, j);
@@ -1140,7 +1214,7 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
           juc1 = __shfl_sync(kFull, uc1, j);
           haveC = true;
         }
-        if (cand && k >= G.lastTwoStart) {
+        if (cand && k >= G.lastTwoStart()) {
           const double dx = pos_axis(M.fcx, M.res, juc0 + d0) - jcx, dy = pos_axis(M.fcy, M.res, juc1 + d1) - jcy;
           cand = (dx * dx + dy * dy <= jR2);
         }
@@ -1163,8 +1237,8 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GeoDev& 
 // The same scan for FHP_SPIRAL_FAITHFUL with a non-zero start index (bug-compatible with upstream):
 // the centre index is the BUFFER index, ring neighbours are taken in buffer space without wrapping, and the
 // distance filter evaluates positions as if the start index were 0.  Per-lane scalar loop (compatibility path).
-template <bool HEADING>
-__device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev& G, const ParDev& P, const uint16_t* sSpiral,
+template <bool HEADING, class GV>
+__device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GV& G, const ParDev& P, const uint16_t* sSpiral,
                                                   const Planes& pl, int uc0, int uc1, int w0, double cx,
                                                   double cy, double R2, const Box& bx, uint32_t rowsBox,
                                                   uint32_t colsBox, bool& found, int& fq0, int& fq1) {
@@ -1173,12 +1247,12 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
   cb0 %= M.rows;
   if (cb1 < 0) cb1 += ((-cb1 / M.cols) + 1) * M.cols;
   cb1 %= M.cols;
-  for (int k = 0; k < G.nCand; ++k) {
+  for (int k = 0; k < G.nCand(); ++k) {
     int d0, d1;
     spiral_entry(sSpiral, k, d0, d1);
     const int bi0 = cb0 + d0, bi1 = cb1 + d1;  // buffer index, NOT wrapped
     if (!in_map(M, bi0, bi1)) continue;
-    if (k >= G.lastTwoStart) {  // upstream evaluates the position as if the start index were 0
+    if (k >= G.lastTwoStart()) {  // upstream evaluates the position as if the start index were 0
       const double dx = pos_axis(M.fcx, M.res, bi0) - cx, dy = pos_axis(M.fcy, M.res, bi1) - cy;
       if (!(dx * dx + dy * dy <= R2)) continue;
     }
@@ -1187,7 +1261,7 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
     if (q1 < 0) q1 += M.cols;
     const bool far = (q0 != uc0 + d0) || (q1 != uc1 + d1);
     const bool good = far ? candidate_slow<HEADING>(M, G, P, q0, q1, bx)
-                          : candidate_on_planes<HEADING>(G, pl, d0 + (uc0 - w0), d1 + G.HW, rowsBox, colsBox);
+                          : candidate_on_planes<HEADING>(G, pl, d0 + (uc0 - w0), d1 + G.HW(), rowsBox, colsBox);
     if (good) {
       found = true;
       fq0 = q0;
@@ -1202,8 +1276,8 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GeoDev&
 // WARP-COLLECTIVE: every lane of the warp must call it (inactive lanes pass active = false).
 // (cx,cy): search centre; (rx,ry): centre of the search rectangle; (uc0,uc1): raw unwrapped index of the centre;
 // (w0,w1): unwrapped origin of the staged window (uc-HW, minus the TMA row-alignment shift).
-template <bool DEFAULT_ONLY, bool PAD, bool HEADING>
-__device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev& G, const ParDev& P,
+template <bool DEFAULT_ONLY, bool PAD, bool HEADING, class GV>
+__device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G, const ParDev& P,
                                                    const uint16_t* sSpiral, uint32_t smemWarp, int lane,
                                                    bool active, int uc0, int uc1, int w0, int w1, double cx, double cy,
                                                    double rx, double ry, bool okDefault, unsigned& err) {
@@ -1213,8 +1287,8 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
   o.ok = false;
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
-  const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride) * 4u;
-  const Planes pl(mine, PAD ? 1 : G.pack, G.rpShift);  // PAD <=> mask staging: pack is 1 at compile time
+  const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
+  const Planes pl(mine, PAD ? 1 : G.pack(), G.rpShift());  // PAD <=> mask staging: pack is 1 at compile time
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
                                in_map(M, uc0, uc1);
@@ -1240,18 +1314,18 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
       box_masks(M, G, bx, w0, w1, rowsBox, colsBox);
     }
     rowsIn = in_range_mask(w0, M.rows, 32);
-    colsIn = in_range_mask(w1, M.cols, G.WIN);
+    colsIn = in_range_mask(w1, M.cols, G.WIN());
     if (HEADING && !PAD) {
       // rotated rectangle on the packed plane layouts: the owning lane builds the finished "bad cell" masks
       // (finite & (below the candidate threshold | centre outside the polygon)) into plane 3 of its slot
-      const int rp = 1 << G.rpShift;  // rows per packed column (32 / pack)
+      const int rp = 1 << G.rpShift();  // rows per packed column (32 / pack)
       const uint32_t rm = rp >= 32 ? 0xffffffffu : ((1u << rp) - 1u);
-      for (int k = 0; k < G.nIter; ++k) {
+      for (int k = 0; k < G.nIter(); ++k) {
         uint32_t word = 0u;
-        for (int c = 0; c < G.pack; ++c) {
-          const int b = k * G.pack + c;
-          if (b >= G.WIN) break;
-          const uint32_t inside = poly_col_rows(M, P, rx, ry, w0, G.winRows, w1 + b);
+        for (int c = 0; c < G.pack(); ++c) {
+          const int b = k * G.pack() + c;
+          if (b >= G.WIN()) break;
+          const uint32_t inside = poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b);
           const uint32_t bad = pl.col(PL_F, b) & (pl.col(PL_C, b) | ~inside) & rm;
           word |= bad << (c * rp);
         }
@@ -1262,26 +1336,26 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GeoDev
       // The owning lane turns its planes into per-column "bad cell" masks once (left in the pad word of each column
       // entry for the cooperative scan) and, for a single-cell foot stencil, settles the two most common outcomes
       // itself: no acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
-      const int sh = (uc0 - w0) - G.HW;
+      const int sh = (uc0 - w0) - G.HW();
       uint32_t anyOk = 0, okCentre = 0;
-      for (int b = 0; b < G.WIN; ++b) {
+      for (int b = 0; b < G.WIN(); ++b) {
         const uint4 e = lds_v4(mine + static_cast<uint32_t>(b) * 16u);  // {D, C, F, pad} of column b (pack = 1 layout)
-        const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows, w1 + b)
+        const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b)
                                      : (((colsBox >> b) & 1u) ? rowsBox : 0u);
         const uint32_t bad = e.z & (e.y | ~box);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(b * 4 + 3) * 4u), "r"(bad) : "memory");
-        const uint32_t okb = ((colsIn >> b) & 1u) ? ((G.candRows[b] << sh) & ~bad & rowsIn) : 0u;
+        const uint32_t okb = ((colsIn >> b) & 1u) ? ((G.g.candRows[b] << sh) & ~bad & rowsIn) : 0u;
         anyOk |= okb;
-        if (b == G.HW) okCentre = okb;
+        if (b == G.HW()) okCentre = okb;
       }
       if (pend) {
-        if (G.lastTwoStart > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
+        if (G.lastTwoStart() > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
           found = true;
           fq0 = uc0;
           fq1 = uc1;
         }
-        if (G.nSten == 1 && (found || anyOk == 0u)) pend = false;
-        if (G.nSten > 1) found = false;  // the shortcuts need the dilated masks
+        if (G.nSten() == 1 && (found || anyOk == 0u)) pend = false;
+        if (G.nSten() > 1) found = false;  // the shortcuts need the dilated masks
       }
     }
   }

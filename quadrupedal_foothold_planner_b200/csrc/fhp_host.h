@@ -47,7 +47,8 @@ struct TaskArgs {
   unsigned* err;
 };
 
-cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, cudaStream_t stream);
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, bool noSpec, cudaStream_t stream);
+int geo_spec_of(const GeoDev& G);
 constexpr int kStreamWarpBytes = 32 * 20;  // shared-memory staging of one warp's rows in stream mode
 long long plan_wave_queries(const GeoDev& G, bool wantCen);
 cudaError_t launch_mask_build(const MapDev& M, float thrD, float thrC, uint4* mask, int rowWords, unsigned* flags,

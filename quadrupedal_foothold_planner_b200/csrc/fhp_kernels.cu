@@ -17,7 +17,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 __device__ __forceinline__ double mulz(double a, double t) { return t == 0.0 ? 0.0 : a * t; }
 
 // FootholdPlanner::getPolygonCenter (FP.cpp:2421-2463), xy only (z never reaches the response).
-__device__ __forceinline__ void polygon_center(double rfx, double rfy, double rhx, double rhy, double lhx, double lhy,
+__device__ FHP_INL_PC void polygon_center(double rfx, double rfy, double rhx, double rhy, double lhx, double lhy,
                                                double lfx, double lfy, double& cx, double& cy) {
   double x1 = rfx, y1 = rfy, x2 = rhx, y2 = rhy, x3, y3;
   double sum_x = 0, sum_y = 0, sum_s = 0;
@@ -88,11 +88,12 @@ __device__ __forceinline__ void stream_rows(uint32_t stg, int lane, bool mine, d
 
 // Block-wide copy of the SpiralIterator table into shared memory (ranks are looked up with a per-lane index in the
 // cooperative scan; the constant bank would serialise those).  Returns the table; ends with __syncthreads.
-__device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, uint32_t* smem) {
+template <class GV>
+__device__ __forceinline__ const uint16_t* load_spiral_table(const GV& G, uint32_t* smem) {
   uint16_t* t = reinterpret_cast<uint16_t*>(smem);
-  for (int k = threadIdx.x; k < G.nCand; k += blockDim.x)
-    t[k] = static_cast<uint16_t>(static_cast<uint8_t>(G.spiral[k][0])) |
-           static_cast<uint16_t>(static_cast<uint16_t>(static_cast<uint8_t>(G.spiral[k][1])) << 8);
+  for (int k = threadIdx.x; k < G.nCand(); k += blockDim.x)
+    t[k] = static_cast<uint16_t>(static_cast<uint8_t>(G.g.spiral[k][0])) |
+           static_cast<uint16_t>(static_cast<uint16_t>(static_cast<uint8_t>(G.g.spiral[k][1])) << 8);
   __syncthreads();
   return t;
 }
@@ -106,9 +107,10 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GeoDev& G, ui
 #ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
 #define FHP_PLAN_MIN_BLOCKS_MASK 7
 #endif
-template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM>
+template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM, int SPEC>
 __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
-                                                            const __grid_constant__ GeoDev G) {
+                                                            const __grid_constant__ GeoDev Gd) {
+  const GeoV<SPEC> G(Gd);  // SPEC > 0: the geometry's scalars are compile-time constants (fhp_device.cuh)
   extern __shared__ __align__(16) uint32_t smem_raw[];
   // 128-byte aligned base (TMA destinations must be 128-byte aligned; the launcher adds the slack)
   uint32_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) / 4u;
@@ -116,9 +118,9 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
   TmaWarp T;
-  T.bar[0] = smem_u32(smem + G.mbarOff + warpInBlock * 4);
+  T.bar[0] = smem_u32(smem + G.mbarOff() + warpInBlock * 4);
   T.bar[1] = T.bar[0] + 8;
-  T.boxAddr = smem_u32(smem + G.boxOff) + static_cast<uint32_t>(warpInBlock * 2 * G.tmaB * G.boxWords) * 4u;
+  T.boxAddr = smem_u32(smem + G.boxOff()) + static_cast<uint32_t>(warpInBlock * 2 * G.tmaB() * G.boxWords()) * 4u;
   T.parity[0] = T.parity[1] = 0;
   if (USE_TMA && lane == 0) {
     mbar_init(T.bar[0], 1);
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint16_t* sSpiral = load_spiral_table(G, smem);  // ends with __syncthreads (also publishes the mbarriers)
-  const uint32_t sw = smem_u32(smem + G.spiralWords + warpInBlock * 32 * G.stride);
+  const uint32_t sw = smem_u32(smem + G.spiralWords() + warpInBlock * 32 * G.stride());
   const long long gwarp = static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock;
   // A warp plans 2^qpwShift queries (its first quads).  Eight keeps every lane busy; batches too small to fill the GPU
   // spread over more warps instead, because the warp-cooperative steps (staging passes, spiral scans) serve a warp's
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
   double defx = nomx, defy = nomy;  // default chain: setFirstGait too (FP.cpp:562)
   // stream mode: this warp's staging block (behind everything else in shared memory) and its first query's slot
   // (stream mode always runs 8 queries per warp: the group of 8 queries is part of the buffer format)
-  const uint32_t sStg = STREAM ? smem_u32(smem + G.smemWords) + static_cast<uint32_t>(warpInBlock) * kStreamWarpBytes : 0u;
+  const uint32_t sStg = STREAM ? smem_u32(smem + G.smemWords()) + static_cast<uint32_t>(warpInBlock) * kStreamWarpBytes : 0u;
   char* const sBase = STREAM ? reinterpret_cast<char*>(A.sOut) + ((A.sQ0 >> 3) + gwarp) * 640 : nullptr;
   const long long sPitch = STREAM ? ((A.sNq + 7) >> 3) * 640 : 0;  // bytes of one cycle block
   uint32_t succMask = 0u, kindMask = 0u;
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
 
     // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
     const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
-    int w0 = uc0 - G.HW;
-    const int w1 = uc1 - G.HW;
+    int w0 = uc0 - G.HW();
+    const int w1 = uc1 - G.HW();
     if (USE_TMA) {  // TMA needs the box's innermost (row) coordinate 16-byte aligned: shift the origin down to a
       int c0 = w0 + M.start0;  // multiple of 4 buffer rows (rows % 4 == 0, so the wrap keeps the alignment)
       if (c0 >= M.rows) c0 -= M.rows;
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     bool okDef = false;
     float zCentre = 0.0f;
     if (active) {
-      Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, STAGE == kStageMask ? 1 : G.pack, G.rpShift);
+      Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 1 : G.pack(), G.rpShift());
       zCentre = mean_height_loaded(M, P, px, py, dw, de);                // FP.cpp:2029 (used when the leg is valid)
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
@@ -367,12 +369,13 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
 //      4: checkCandidateFoothold (the spiral search alone), 5: checkCirclePolygonFoothold
 template <int MODE>
 __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constant__ TaskArgs A,
-                                                            const __grid_constant__ GeoDev G) {
+                                                            const __grid_constant__ GeoDev Gd) {
+  const GeoV<0> G(Gd);
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
   const uint16_t* sSpiral = load_spiral_table(G, smem);
-  const uint32_t sw = smem_u32(smem + G.spiralWords + warpInBlock * 32 * G.stride);
+  const uint32_t sw = smem_u32(smem + G.spiralWords() + warpInBlock * 32 * G.stride());
   const long long i = (static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock) * 32 + lane;
   const bool active = i < A.n;
   const MapDev& M = A.M;
@@ -399,9 +402,9 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     return;
   }
   const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
-  const int w0 = uc0 - G.HW, w1 = uc1 - G.HW;
+  const int w0 = uc0 - G.HW(), w1 = uc1 - G.HW();
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
-  Planes pl(sw + static_cast<uint32_t>(lane * G.stride) * 4u, G.pack, G.rpShift);
+  Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, G.pack(), G.rpShift());
   if (MODE == 0 || MODE == 3 || MODE == 4) {
     DiscWin dw = {0, 0, -1, -1, 0ull, 0};
     if (active) dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
@@ -614,26 +617,48 @@ cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st,
 typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
 // the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
 template <int STAGE, bool HEADING>
-static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef, bool stream) {
-  if (stream) return plan_kernel<false, STAGE, false, HEADING, true>;  // nominal rows only
-  if (wantDef) return plan_kernel<true, STAGE, true, HEADING, false>;
-  return wantCen ? plan_kernel<true, STAGE, false, HEADING, false> : plan_kernel<false, STAGE, false, HEADING, false>;
+static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef, bool stream, int spec) {
+  if (STAGE == kStageMask && !wantCen && !wantDef) {  // the response path: geometry-specialised variants (GeoK)
+    if (spec == 1) return stream ? plan_kernel<false, kStageMask, false, HEADING, true, 1> : plan_kernel<false, kStageMask, false, HEADING, false, 1>;
+    if (spec == 2) return stream ? plan_kernel<false, kStageMask, false, HEADING, true, 2> : plan_kernel<false, kStageMask, false, HEADING, false, 2>;
+  }
+  if (stream) return plan_kernel<false, STAGE, false, HEADING, true, 0>;  // nominal rows only
+  if (wantDef) return plan_kernel<true, STAGE, true, HEADING, false, 0>;
+  return wantCen ? plan_kernel<true, STAGE, false, HEADING, false, 0> : plan_kernel<false, STAGE, false, HEADING, false, 0>;
 }
 // heading: some parameter set of the call carries a non-zero heading -> the variant with the rotated expressions
 // (the reference-shaped variant stays exactly what it was)
-static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading, bool stream) {
+static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading, bool stream, int spec) {
+#ifdef FHP_BENCH_BUILD  // scratch A/B builds: only the headline variants are instantiated (seconds instead of a minute)
+  if (spec == 2) return plan_kernel<false, kStageMask, false, false, false, 2>;
+  return spec == 1 ? plan_kernel<false, kStageMask, false, false, false, 1> : plan_kernel<false, kStageMask, false, false, false, 0>;
+#else
   if (heading) {
-    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef, stream);
-    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef, stream);
-    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef, stream);
+    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef, stream, spec);
+    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef, stream, spec);
+    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef, stream, spec);
   }
-  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef, stream);
-  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef, stream);
-  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef, stream);
+  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef, stream, spec);
+  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef, stream, spec);
+  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef, stream, spec);
+#endif
+}
+
+// The geometry-specialised kernel variant (GeoK) whose constants equal the tables the host built, or 0.
+int geo_spec_of(const GeoDev& G) {
+  if (G.stageMode != kStageMask || G.pack != 1 || G.rpShift != 5 || G.nIter != G.WIN || G.stride != 4 * G.WIN || G.winRows != G.WIN)
+    return 0;
+  auto same = [&](auto k) {
+    return G.WIN == k.WIN && G.HW == k.HW && G.nSten == k.nSten && G.discK == k.discK && G.nCand == k.nCand &&
+           G.lastTwoStart == k.lastTwoStart && G.nRings == k.nRings && G.ra == k.ra;
+  };
+  if (same(GeoK<1>{})) return 1;
+  if (same(GeoK<2>{})) return 2;
+  return 0;
 }
 
 // ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
-cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, cudaStream_t stream) {
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, bool noSpec, cudaStream_t stream) {
   if (A.nq <= 0) return cudaSuccess;
   const int warps = kPlanThreads / 32;
   const int qpw = 1 << A.qpwShift;
@@ -642,7 +667,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
   const bool streamMode = A.sOut != nullptr;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128 +  // + alignment slack
                      (streamMode ? static_cast<size_t>(warps) * kStreamWarpBytes : 0);
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading, streamMode);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading, streamMode, noSpec ? 0 : geo_spec_of(G));
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
@@ -655,7 +680,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
 // the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
 // a wave takes as long as a full one).
 long long plan_wave_queries(const GeoDev& G, bool wantCen) {
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false, false);
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false, false, geo_spec_of(G));
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
   if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
   int perSm = 0, dev = 0, sms = 0;

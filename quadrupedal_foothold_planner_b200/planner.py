@@ -41,7 +41,9 @@ def load_lib():
         return _LIB
     from . import build as _build
     path = lib_path()
-    if _build.needs_build():
+    if os.environ.get("FHP_LIB"):  # experiments: an alternative build of the same library (scratch A/B runs)
+        path = os.environ["FHP_LIB"]
+    elif _build.needs_build():
         try:
             _build.build()
         except Exception:
