@@ -105,6 +105,11 @@ def make_workload(name: str, rank: int = 0, world: int = 1, with_map: bool = Tru
         names = names + ["slope"]
         desc = ("C5: trot, 262144 queries x 32 cycles, 16000x16000 @0.01 m rough map, 3 layers (3.07 GB), "
                 "start index (4321,12345)")
+    elif name == "c5s":  # a C5-shaped workload on a 1/16 map (kernel experiments: same resolution, geometry and case mix)
+        m, q, cycles = synth.config_c5(n_queries=65536, rows=4000, cols=4000, start=(1321, 2345), with_map=with_map)
+        params = [_abi.yaml_params()]
+        names = names + ["slope"]
+        desc = "C5-small: trot, 65536 queries x 32 cycles, 4000x4000 @0.01 m rough map, 3 layers"
     elif name == "c2":
         m, q, cycles = synth.config_c2()
         params = [_abi.yaml_params(gait=_abi.FHP_GAIT_WALK)]

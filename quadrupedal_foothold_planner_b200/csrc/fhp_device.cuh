@@ -1132,6 +1132,13 @@ __device__ __forceinline__ uint32_t in_range_mask(int org, int n, int nBits) {
   return (hi - lo >= 31 ? 0xffffffffu : ((1u << (hi - lo + 1)) - 1u)) << lo;
 }
 
+// The foot-disc stencil around a cell centre is the full 3x3 block (footRadius in [sqrt(2), 2) cells: the yaml radius at
+// 0.01 m): 9 offsets within one cell of the centre can only be that block.
+template <class GV>
+__device__ __forceinline__ bool dilated3x3(const GV& G) {
+  return G.nSten() == 9 && G.ra() == 1;
+}
+
 // checkCandidateFoothold (FP.cpp:2085-2114) over grid_map::SpiralIterator — warp-cooperative rank scan.
 // For every lane j with `need`:
 //   1. lane b (< WIN) holds the "bad cell" mask of window column b of j's staged planes: a finite cell is bad when
@@ -1174,7 +1181,8 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GV& G, c
       }
     }
     uint32_t dil = bad;
-    if (G.nSten() > 1) {  // dilate by the foot-disc stencil (a single-cell stencil needs nothing)
+    if (G.nSten() > 1 && !(PAD && dilated3x3(G))) {  // dilate by the foot-disc stencil (nothing to do for a single cell;
+                                                      // the owning lane has done it for the 3x3 block, nominal_eval)
       dil = 0;
       for (int s = 0; s < G.nSten(); ++s) {
         const int s0 = G.g.sten[s][0], s1 = G.g.sten[s][1];
@@ -1189,7 +1197,7 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GV& G, c
     // quick reject: no cell of the spiral footprint is acceptable even before the distance filter (a query that is
     // stuck on an untraversable patch re-scans the same window every remaining cycle).  With a single-cell stencil the
     // PAD variant has already made this test in the owning lane.
-    if (!PAD || G.nSten() > 1) {
+    if (!PAD || !(G.nSten() == 1 || dilated3x3(G))) {
       const uint32_t footprint = (lane < G.WIN()) ? (G.g.candRows[lane] << (ha - G.HW())) : 0u;
       if (__ballot_sync(kFull, (footprint & ~dil) != 0u) == 0u) continue;
     }
@@ -1334,28 +1342,47 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
     }
     if (PAD && (pend || HEADING)) {
       // The owning lane turns its planes into per-column "bad cell" masks once (left in the pad word of each column
-      // entry for the cooperative scan) and, for a single-cell foot stencil, settles the two most common outcomes
-      // itself: no acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
+      // entry for the cooperative scan) — already DILATED by the foot-disc stencil when that is a single cell or the
+      // full 3x3 block (separable: a vertical OR per column, then the OR of the three neighbouring columns, carried in
+      // registers while the loop slides over the window) — and then settles the two most common outcomes itself: no
+      // acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
       const int sh = (uc0 - w0) - G.HW();
+      const bool dil3 = dilated3x3(G) && pend;  // (bug-compatible spiral lanes test stencil cells one by one: raw masks)
       uint32_t anyOk = 0, okCentre = 0;
-      for (int b = 0; b < G.WIN(); ++b) {
-        const uint4 e = lds_v4(mine + static_cast<uint32_t>(b) * 16u);  // {D, C, F, pad} of column b (pack = 1 layout)
-        const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b)
-                                     : (((colsBox >> b) & 1u) ? rowsBox : 0u);
-        const uint32_t bad = e.z & (e.y | ~box);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(b * 4 + 3) * 4u), "r"(bad) : "memory");
-        const uint32_t okb = ((colsIn >> b) & 1u) ? ((G.g.candRows[b] << sh) & ~bad & rowsIn) : 0u;
-        anyOk |= okb;
-        if (b == G.HW()) okCentre = okb;
+      uint32_t vPrev = 0u, vCur = 0u;  // vertically dilated masks of columns b-2 and b-1
+      const int nLoop = G.WIN() + (dilated3x3(G) ? 1 : 0);
+      for (int b = 0; b < nLoop; ++b) {
+        uint32_t bad = 0u;
+        if (b < G.WIN()) {
+          const uint4 e = lds_v4(mine + static_cast<uint32_t>(b) * 16u);  // {D, C, F, pad} of column b (pack = 1 layout)
+          const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b)
+                                       : (((colsBox >> b) & 1u) ? rowsBox : 0u);
+          bad = e.z & (e.y | ~box);
+        }
+        int col = b;          // the column whose finished mask this iteration emits
+        uint32_t out = bad;
+        if (dil3) {
+          const uint32_t vNext = bad | (bad << 1) | (bad >> 1);
+          col = b - 1;
+          out = vPrev | vCur | vNext;
+          vPrev = vCur;
+          vCur = vNext;
+        }
+        if (col >= 0 && col < G.WIN()) {
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(col * 4 + 3) * 4u), "r"(out) : "memory");
+          const uint32_t okb = ((colsIn >> col) & 1u) ? ((G.g.candRows[col] << sh) & ~out & rowsIn) : 0u;
+          anyOk |= okb;
+          if (col == G.HW()) okCentre = okb;
+        }
       }
       if (pend) {
-        if (G.lastTwoStart() > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
+        const bool finished = G.nSten() == 1 || dilated3x3(G);  // the masks above are the dilated ones
+        if (finished && G.lastTwoStart() > 0 && ((okCentre >> (uc0 - w0)) & 1u)) {  // rank 0: the centre cell itself
           found = true;
           fq0 = uc0;
           fq1 = uc1;
         }
-        if (G.nSten() == 1 && (found || anyOk == 0u)) pend = false;
-        if (G.nSten() > 1) found = false;  // the shortcuts need the dilated masks
+        if (finished && (found || anyOk == 0u)) pend = false;
       }
     }
   }

@@ -111,9 +111,8 @@ template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM, in
 __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev Gd) {
   const GeoV<SPEC> G(Gd);  // SPEC > 0: the geometry's scalars are compile-time constants (fhp_device.cuh)
-  extern __shared__ __align__(16) uint32_t smem_raw[];
-  // 128-byte aligned base (TMA destinations must be 128-byte aligned; the launcher adds the slack)
-  uint32_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) / 4u;
+  extern __shared__ __align__(128) uint32_t smem_raw[];  // (TMA destinations must be 128-byte aligned)
+  uint32_t* const smem = smem_raw;
   constexpr bool USE_TMA = STAGE == kStageTma;
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
