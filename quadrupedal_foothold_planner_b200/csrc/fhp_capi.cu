@@ -444,10 +444,13 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   if (G.WIN > 32)
     return fail(ctx, FHP_ERR_UNSUPPORTED, "(searchRadius+footRadius)/resolution needs a window wider than 32 cells");
   G.pack = G.WIN <= 8 ? 4 : (G.WIN <= 16 ? 2 : 1);
-  if (stage == kStageMask) G.pack = 1;  // one 16-byte {D, C, F, pad} entry per window column
+  if (stage == kStageMask) G.pack = 1;  // one entry per window column
   G.rpShift = G.pack == 4 ? 3 : (G.pack == 2 ? 4 : 5);
   G.nIter = (G.WIN + G.pack - 1) / G.pack;
   G.stride = 4 * G.nIter;
+  // mask staging keeps the class-plane pair (e0, e1) per window column plus one word per column for the finished masks
+  // (Planes, pack 0): 12 bytes per column, slot padded to a multiple of 8 bytes (WIN is odd)
+  if (stage == kStageMask) G.stride = 3 * G.WIN + 1;
 
   // ---- SpiralIterator order: centre, then ring d = 1..nRings generated by the upstream walk and consumed from
   // the BACK of the ring vector (pointsRing_.back()/pop_back()).
@@ -1422,7 +1425,9 @@ static int run_task(fhp_ctx* ctx, int mode, const fhp_params* params, const doub
   A.ccase = static_cast<int8_t*>(ctx->dC2.p);
   A.z = static_cast<float*>(ctx->dD.p);
   A.err = ctx->dErrMapped;
-  CU(launch_task(mode, A, ctx->G, s));
+  GeoDev Gt = ctx->G;  // the member kernels stage from the float layer into the {D, C, F, pad} layout (4 words per column
+  Gt.stride = 4 * Gt.nIter;  // group), whatever plane layout the plan kernels of this context use
+  CU(launch_task(mode, A, Gt, s));
   ctx->launches += 1;
   if (out) CU(cudaMemcpyAsync(out, ctx->dOutN.p, sizeof(fhp_foothold) * n, cudaMemcpyDeviceToHost, s));
   if (valid) CU(cudaMemcpyAsync(valid, ctx->dC2.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, s));

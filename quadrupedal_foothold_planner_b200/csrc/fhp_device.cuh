@@ -57,7 +57,7 @@ struct GeoV {
   FHP_GEO_K(WIN) FHP_GEO_K(HW) FHP_GEO_K(nSten) FHP_GEO_K(discK) FHP_GEO_K(nCand) FHP_GEO_K(lastTwoStart) FHP_GEO_K(nRings) FHP_GEO_K(ra)
 #undef FHP_GEO_K
   __device__ __forceinline__ int nIter() const { if constexpr (K::fixed) return K::WIN; else return g.nIter; }
-  __device__ __forceinline__ int stride() const { if constexpr (K::fixed) return 4 * K::WIN; else return g.stride; }
+  __device__ __forceinline__ int stride() const { if constexpr (K::fixed) return 3 * K::WIN + 1; else return g.stride; }
   __device__ __forceinline__ int winRows() const { if constexpr (K::fixed) return K::WIN; else return g.winRows; }
   __device__ __forceinline__ int pack() const { if constexpr (K::fixed) return 1; else return g.pack; }
   __device__ __forceinline__ int rpShift() const { if constexpr (K::fixed) return 5; else return g.rpShift; }
@@ -189,6 +189,14 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -196,11 +204,20 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 // ------------------------------------------------------------------------------------------------ bit planes
 struct Planes {  // view of one query's staged window in shared memory
   const uint32_t* w;
-  int pack, rpShift;
-  // from a shared-space byte address: plain loads (the compiler may keep words in registers between barriers)
-  __device__ __forceinline__ Planes(uint32_t addr, int pack_, int rpShift_)
-      : w(static_cast<const uint32_t*>(__cvta_shared_to_generic(addr))), pack(pack_), rpShift(rpShift_) {}
+  int pack, rpShift, win;
+  // from a shared-space byte address: plain loads (the compiler may keep words in registers between barriers).
+  // pack 1 / 2 / 4: the float paths' layout, 4 words {D, C, F, pad} per group of `pack` window columns.
+  // pack 0: the cell-class (mask) path's layout — per window column the pair (e0, e1) of class bit planes, 8 bytes, then
+  // one word per column for the owning lane's finished "bad cell" masks: D = e1, C = e0 & e1, F = e0 | e1 cost one
+  // operation at the point of use and the slot shrinks from 16 to 12 bytes per column (occupancy at 0.01 m).
+  __device__ __forceinline__ Planes(uint32_t addr, int pack_, int rpShift_, int win_)
+      : w(static_cast<const uint32_t*>(__cvta_shared_to_generic(addr))), pack(pack_), rpShift(rpShift_), win(win_) {}
   __device__ __forceinline__ uint32_t col(int plane, int b) const {  // bits over window rows a for column b
+    if (pack == 0) {
+      if (plane == 3) return w[2 * win + b];
+      const uint2 e = *reinterpret_cast<const uint2*>(w + 2 * b);
+      return plane == 0 ? e.y : (plane == 1 ? (e.x & e.y) : (e.x | e.y));
+    }
     if (pack == 1) return w[b * 4 + plane];
     int k, sh;
     if (pack == 2) {
@@ -247,7 +264,7 @@ __device__ __forceinline__ void stage_chunk_ballots(const GV& G, uint32_t dst, i
 }
 
 // Generic per-cell staging (windows touching the map border or the circular-buffer seam).
-template <class GV>
+template <bool MASKL, class GV>
 __device__ __noinline__ void stage_slow(const MapDev& M, const GV& G, uint32_t smemWarp, int lane, unsigned slowMask,
                                         int w0, int w1, float thrD, float thrC) {
   const int RP = 1 << G.rpShift();
@@ -274,7 +291,12 @@ __device__ __noinline__ void stage_slow(const MapDev& M, const GV& G, uint32_t s
       const uint32_t bD = __ballot_sync(kFull, v < tD);
       const uint32_t bC = __ballot_sync(kFull, v < tC);
       const uint32_t bF = __ballot_sync(kFull, fabsf(v) < inf);
-      if (lane == 0) sts_v4(dst + static_cast<uint32_t>(k) * 16u, bD, bC, bF, 0u);
+      if (MASKL) {  // mask path (pack 1, one column per iteration): the class-plane pair (e0, e1) — no -inf cells and
+        // thrC <= thrD on this path, so D and C are subsets of F: e1 = D, e0 = (F & ~D) | C
+        if (lane == 0) sts_v2(dst + static_cast<uint32_t>(k) * 8u, (bF & ~bD) | bC, bD);
+      } else if (lane == 0) {
+        sts_v4(dst + static_cast<uint32_t>(k) * 16u, bD, bC, bF, 0u);
+      }
     }
   }
 }
@@ -345,7 +367,7 @@ __device__ __forceinline__ void stage_windows(const MapDev& M, const GV& G, uint
     }
   }
 
-  stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
+  stage_slow<false>(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
   __syncwarp();
 }
 
@@ -504,7 +526,7 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GV& G, 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
-  if (slowMask) stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
+  if (slowMask) stage_slow<false>(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
   __syncwarp();
 }
 
@@ -540,7 +562,7 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GV& G,
   __syncwarp();  // every lane is done reading the planes of the previous leg/cycle
   if (empty) {
     const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
-    for (int k = 0; k < G.nIter(); ++k) sts_v4(mine + static_cast<uint32_t>(k) * 16u, 0u, 0u, 0u, 0u);
+    for (int k = 0; k < G.WIN(); ++k) sts_v2(mine + static_cast<uint32_t>(k) * 8u, 0u, 0u);
   }
   if (fast) {  // every lane stages ITS OWN window: WIN independent 16-byte loads, no cross-lane traffic
     const uint4* src = mask + (bb0 >> 5) * M.cols;
@@ -559,11 +581,11 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GV& G,
       for (int i = 0; i < kStageBatch; ++i)
         if (c + i < G.WIN()) {
           const uint32_t e0 = __funnelshift_r(e[i].x, e[i].y, s), e1 = __funnelshift_r(e[i].z, e[i].w, s);
-          sts_v4(dst + static_cast<uint32_t>(c + i) * 16u, e1, e0 & e1, e0 | e1, 0u);
+          sts_v2(dst + static_cast<uint32_t>(c + i) * 8u, e0, e1);
         }
     }
   }
-  if (slowMask) stage_slow(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
+  if (slowMask) stage_slow<true>(M, G, smemWarp, lane, slowMask, w0, w1, thrD, thrC);
   __syncwarp();
 }
 
@@ -1167,13 +1189,13 @@ __device__ __forceinline__ void spiral_scan_coop(const MapDev& M, const GV& G, c
     // 1. column masks (lane = window column)
     uint32_t bad = 0;
     if (PAD) {
-      if (lane < G.WIN()) bad = lds_u32(smemWarp + static_cast<uint32_t>(j * G.stride() + lane * 4 + 3) * 4u);
+      if (lane < G.WIN()) bad = lds_u32(smemWarp + static_cast<uint32_t>(j * G.stride() + 2 * G.WIN() + lane) * 4u);
     } else if (HEADING) {  // the owning lane has left the finished masks (rotated rectangle included) in plane 3
-      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, G.pack(), G.rpShift());
+      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, G.pack(), G.rpShift(), G.WIN());
       if (lane < G.WIN()) bad = pj.col(3, lane);
     } else {
       const uint32_t jrows = __shfl_sync(kFull, rowsBox, j), jcols = __shfl_sync(kFull, colsBox, j);
-      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, G.pack(), G.rpShift());
+      const Planes pj(smemWarp + static_cast<uint32_t>(j * G.stride()) * 4u, G.pack(), G.rpShift(), G.WIN());
       if (lane < G.WIN()) {
         const uint32_t F = pj.col(PL_F, lane), C = pj.col(PL_C, lane);
         const uint32_t box = ((jcols >> lane) & 1u) ? jrows : 0u;
@@ -1296,7 +1318,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
   const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
-  const Planes pl(mine, PAD ? 1 : G.pack(), G.rpShift());  // PAD <=> mask staging: pack is 1 at compile time
+  const Planes pl(mine, PAD ? 0 : G.pack(), G.rpShift(), G.WIN());  // PAD <=> mask staging: the class-pair layout
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&
                                in_map(M, uc0, uc1);
@@ -1354,10 +1376,10 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
       for (int b = 0; b < nLoop; ++b) {
         uint32_t bad = 0u;
         if (b < G.WIN()) {
-          const uint4 e = lds_v4(mine + static_cast<uint32_t>(b) * 16u);  // {D, C, F, pad} of column b (pack = 1 layout)
+          const uint2 e = lds_v2(mine + static_cast<uint32_t>(b) * 8u);  // class planes (e0, e1) of column b
           const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b)
                                        : (((colsBox >> b) & 1u) ? rowsBox : 0u);
-          bad = e.z & (e.y | ~box);
+          bad = (e.x | e.y) & ((e.x & e.y) | ~box);  // finite & (below the candidate threshold | outside the rectangle)
         }
         int col = b;          // the column whose finished mask this iteration emits
         uint32_t out = bad;
@@ -1369,7 +1391,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
           vCur = vNext;
         }
         if (col >= 0 && col < G.WIN()) {
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(col * 4 + 3) * 4u), "r"(out) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine + static_cast<uint32_t>(2 * G.WIN() + col) * 4u), "r"(out) : "memory");
           const uint32_t okb = ((colsIn >> col) & 1u) ? ((G.g.candRows[col] << sh) & ~out & rowsIn) : 0u;
           anyOk |= okb;
           if (col == G.HW()) okCentre = okb;

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     bool okDef = false;
     float zCentre = 0.0f;
     if (active) {
-      Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 1 : G.pack(), G.rpShift());
+      Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 0 : G.pack(), G.rpShift(), G.WIN());
       zCentre = mean_height_loaded(M, P, px, py, dw, de);                // FP.cpp:2029 (used when the leg is valid)
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
   const int w0 = uc0 - G.HW(), w1 = uc1 - G.HW();
   stage_windows(M, G, sw, lane, active, w0, w1, P.thrD, P.thrC);
-  Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, G.pack(), G.rpShift());
+  Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, G.pack(), G.rpShift(), G.WIN());
   if (MODE == 0 || MODE == 3 || MODE == 4) {
     DiscWin dw = {0, 0, -1, -1, 0ull, 0};
     if (active) dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
@@ -645,7 +645,7 @@ static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bo
 
 // The geometry-specialised kernel variant (GeoK) whose constants equal the tables the host built, or 0.
 int geo_spec_of(const GeoDev& G) {
-  if (G.stageMode != kStageMask || G.pack != 1 || G.rpShift != 5 || G.nIter != G.WIN || G.stride != 4 * G.WIN || G.winRows != G.WIN)
+  if (G.stageMode != kStageMask || G.pack != 1 || G.rpShift != 5 || G.nIter != G.WIN || G.stride != 3 * G.WIN + 1 || G.winRows != G.WIN)
     return 0;
   auto same = [&](auto k) {
     return G.WIN == k.WIN && G.HW == k.HW && G.nSten == k.nSten && G.discK == k.discK && G.nCand == k.nCand &&
