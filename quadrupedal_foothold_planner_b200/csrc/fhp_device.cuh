@@ -724,14 +724,38 @@ __device__ __forceinline__ void height_cell(const MapDev& M, int u0, int u1, flo
     meanHeight = meanHeight + iHeight;
   }
 }
+__device__ __forceinline__ void height_value(float e, float& iHeight, float& meanHeight, int& i) {
+  iHeight = (fabsf(e) < __int_as_float(0x7f800000)) ? e : 0.0f;
+  if (iHeight < 10.0f) {
+    i++;
+    meanHeight = meanHeight + iHeight;
+  }
+}
 __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw) {
   const int tl0 = dw.tl0, tl1 = dw.tl1, br0 = dw.br0, br1 = dw.br1;
   float iHeight = 0.0f, meanHeight = 0.0f;
   int i = 0;
-  if (dw.small()) {  // membership already decided (disc_window); same row-major visiting order
-    for (int i0 = 0; i0 <= br0 - tl0; ++i0)
-      for (int i1 = 0; i1 <= br1 - tl1; ++i1)
-        if ((dw.m >> (8 * i0 + i1)) & 1ull) height_cell(M, tl0 + i0, tl1 + i1, iHeight, meanHeight, i);
+  if (dw.small()) {  // membership already decided (disc_window); ascending bit order = the iterator's row-major order.
+    // All member cells are LOADED first, sixteen at a time in straight-line code (independent loads in flight: one
+    // memory latency per batch instead of one per cell — the height loop was 40 % of a 0.01 m plan), then accumulated.
+    unsigned long long t = dw.m;
+    while (t) {
+      float v[16];
+      int n = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        v[k] = 0.0f;
+        if (t) {
+          const int bit = __ffsll(static_cast<long long>(t)) - 1;
+          t &= t - 1;
+          v[k] = load_cell(M, M.elev, tl0 + (bit >> 3), tl1 + (bit & 7));
+          n = k + 1;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < n) height_value(v[k], iHeight, meanHeight, i);
+    }
   } else {
     for (int u0 = tl0; u0 <= br0; ++u0) {
       const double dx = pos_axis(M.fcx, M.res, u0) - cx;
@@ -752,17 +776,10 @@ __device__ __noinline__ float mean_height(const MapDev& M, const ParDev& P, doub
 }
 // getFootholdMeanHeight from the pre-loaded cells (same accumulation order); discs with more than four member cells
 // or on the generic walk take the loop above.
-__device__ __forceinline__ void height_value(float e, float& iHeight, float& meanHeight, int& i) {
-  iHeight = (fabsf(e) < __int_as_float(0x7f800000)) ? e : 0.0f;
-  if (iHeight < 10.0f) {
-    i++;
-    meanHeight = meanHeight + iHeight;
-  }
-}
 __device__ __forceinline__ float mean_height_loaded(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw,
-                                                    const DiscElev& v) {
+                                                    const DiscElev& v, bool preloaded) {
   const int n = __popcll(dw.m);
-  if (!dw.small() || n > 4) return mean_height(M, P, cx, cy, dw);
+  if (!preloaded || !dw.small() || n > 4) return mean_height(M, P, cx, cy, dw);
   float iHeight = 0.0f, meanHeight = 0.0f;
   int i = 0;
   if (n > 0) height_value(v.e0, iHeight, meanHeight, i);
