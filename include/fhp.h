@@ -195,8 +195,12 @@ int fhp_map_info(const fhp_ctx* ctx, fhp_map_desc* out);
 /* Same, but the layers are ALREADY device-resident on ctx's device (e.g. after an NCCL broadcast); the
  * pointers are adopted without a copy and must stay valid until the next fhp_set_map* / fhp_destroy. */
 int fhp_set_map_device(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* layers_colmajor_device);
-/* Device pointer of an ingested layer (NULL if absent) — lets a host fill/broadcast the map in place. */
+/* Device pointer of an ingested layer (NULL if absent) — lets a host fill/broadcast the map in place.  After rewriting
+ * a layer in place (also a layer adopted through fhp_set_map_device) call fhp_map_changed: the default staging path
+ * plans on cell-class planes derived from the traversability layer, which are rebuilt by the next plan only after a
+ * fhp_set_map*, fhp_broadcast_map or fhp_map_changed. */
 const float* fhp_map_layer_device(const fhp_ctx* ctx, const char* layer_name);
+int fhp_map_changed(fhp_ctx* ctx);
 
 /* The plan — replaces the centroid + nominal chains of FootholdPlanner::globalFootholdPlan
  * (FP.cpp:762-1579) for n_queries independent requests in ONE kernel launch.  Blocking; host buffers.
@@ -298,7 +302,8 @@ const fhp_point20* fhp_stream_row(const fhp_point20* blocks, const fhp_stream_ma
 int fhp_cycle_kpi(const fhp_params* params, const fhp_query* query, const fhp_foothold* rows, int32_t n_rows,
                   double* feet_distance, double* cog_speed);
 /* Same with DEVICE-resident queries/outputs on ctx's device; asynchronous on ctx's stream unless
- * `cuda_stream` (a cudaStream_t) is non-NULL.  The caller synchronises. */
+ * `cuda_stream` (a cudaStream_t) is non-NULL.  The caller synchronises.  Map updates, parameter changes and
+ * fhp_map_changed wait for the whole device before they rewrite state such a plan may still be reading. */
 int fhp_plan_device(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* d_queries,
                     int64_t n_queries, int32_t gait_cycles, fhp_foothold* d_out_nominal, fhp_foothold* d_out_centroid,
                     fhp_query_status* d_status, void* cuda_stream);

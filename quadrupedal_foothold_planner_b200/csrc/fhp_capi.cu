@@ -83,6 +83,7 @@ struct fhp_ctx {
   bool noSpec = false;  // FHP_NO_SPEC=1 (test knob): never pick a geometry-specialised kernel variant (GeoK)
   bool forceHeading = false;
   bool anyHeading = false;  // some parameter set of the current call has the heading expressions in force
+  bool asyncPlans = false;  // a plan was launched on a caller's stream since the last device-wide synchronisation
   // D/C/F mask planes of the traversability layer for one threshold pair (rebuilt lazily after a map update)
   DevBuf dMask;
   bool maskValid = false;
@@ -233,21 +234,36 @@ int ingest_host(fhp_ctx* ctx, const fhp_map_desc& d, const std::vector<std::stri
                 const std::vector<const void*>& ptrs) {
   for (const void* p : ptrs)
     if (!p) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer");
-  int rc = set_geometry(ctx, &d);
-  if (rc != FHP_OK) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream2));
+  if (d.rows <= 0 || d.cols <= 0 || !(d.resolution > 0) || d.n_layers < 0 || d.start_row < 0 || d.start_col < 0 ||
+      d.start_row >= d.rows || d.start_col >= d.cols)
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid map description");
+  CU(cudaDeviceSynchronize());  // plans on caller streams (fhp_plan_device) may still read the buffers reused below
   const size_t bytes = static_cast<size_t>(d.rows) * d.cols * sizeof(float);
-  if (!(ctx->owned.size() == names.size() && ctx->ownedBytes == bytes)) {
-    free_owned(ctx);
+  // New buffers are allocated BEFORE anything of the current map is touched: an allocation failure leaves the previous
+  // map fully in place (same-size updates, the steady state of a robot's periodic map, reuse the buffers).
+  std::vector<float*> fresh;
+  const bool reuse = ctx->owned.size() == names.size() && ctx->ownedBytes == bytes;
+  if (!reuse) {
     for (size_t i = 0; i < names.size(); ++i) {
       float* p = nullptr;
-      CU(cudaMalloc(&p, bytes));
-      ctx->owned.push_back(p);
+      const cudaError_t e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) {
+        for (float* q : fresh) cudaFree(q);
+        return fail(ctx, FHP_ERR_CUDA, std::string("map allocation: ") + cudaGetErrorString(e));
+      }
+      fresh.push_back(p);
     }
+  }
+  ctx->haveMap = false;  // from here on the old content is being replaced
+  ctx->layerPtrs.clear();
+  ctx->M.trav = ctx->M.elev = nullptr;
+  if (!reuse) {
+    free_owned(ctx);
+    ctx->owned = fresh;
     ctx->ownedBytes = bytes;
   }
-  ctx->haveMap = false;
+  int rc = set_geometry(ctx, &d);
+  if (rc != FHP_OK) return rc;
   ctx->layerNames = names;
   ctx->layerPtrs.assign(ctx->owned.begin(), ctx->owned.end());
   for (size_t i = 0; i < names.size(); ++i) {
@@ -531,6 +547,10 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
       !(ctx->maskValid && ctx->maskThrD == params[0].thr_default && ctx->maskThrC == params[0].thr_candidate)) {
     int rc = ensure_err_word(ctx);
     if (rc != FHP_OK) return rc;
+    if (ctx->asyncPlans) {  // a plan launched on a caller's stream (fhp_plan_device) may still be reading the planes
+      CU(cudaDeviceSynchronize());
+      ctx->asyncPlans = false;
+    }
     const int rowWords = (ctx->M.rows + 31) / 32;
     CU(ctx->dMask.reserve(static_cast<size_t>(rowWords) * ctx->M.cols * sizeof(uint4)));
     ctx->hErr[1] = 0u;
@@ -555,6 +575,10 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   if (ctx->dPars.p && ctx->lastParams.size() == static_cast<size_t>(n_params) &&
       std::memcmp(ctx->lastParams.data(), params, sizeof(fhp_params) * n_params) == 0)
     return FHP_OK;  // same parameter sets as the previous call: the derived table is already on the device
+  if (ctx->asyncPlans) {  // the parameter table is rewritten in place: wait for plans on caller streams
+    CU(cudaDeviceSynchronize());
+    ctx->asyncPlans = false;
+  }
   std::vector<ParDev> h(n_params);
   for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i], ctx->forceHeading);
   CU(ctx->dPars.reserve(sizeof(ParDev) * n_params));
@@ -915,7 +939,7 @@ int fhp_set_map_device(fhp_ctx* ctx, const fhp_map_desc* desc, const float* cons
   if (!layers || !desc || !desc->layer_names) return fail(ctx, FHP_ERR_INVALID_ARG, "null map");
   int rc = set_geometry(ctx, desc);
   if (rc != FHP_OK) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaDeviceSynchronize());  // also plans launched on caller streams
   free_owned(ctx);
   ctx->layerNames.clear();
   ctx->layerPtrs.clear();
@@ -1373,6 +1397,7 @@ int fhp_plan_device(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, co
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
   ctx->pendingErrCheck = 1;
+  if (cuda_stream) ctx->asyncPlans = true;  // shared device state is re-synchronised before it is next rewritten
   return plan_common(ctx, params, n_params, d_queries, n_queries, gait_cycles, d_out_nominal, d_out_centroid, d_status,
                      s);
 }
@@ -1560,7 +1585,7 @@ int fhp_broadcast_map(fhp_ctx* ctx, const fhp_map_desc* desc, void* nccl_comm, i
   if (rank != root) {
     int rc = set_geometry(ctx, desc);
     if (rc != FHP_OK) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaDeviceSynchronize());
     free_owned(ctx);
     ctx->layerNames.clear();
     ctx->layerPtrs.clear();
@@ -1584,7 +1609,20 @@ int fhp_broadcast_map(fhp_ctx* ctx, const fhp_map_desc* desc, void* nccl_comm, i
     if (r != 0) return fail(ctx, FHP_ERR_NCCL, "ncclBroadcast failed with code " + std::to_string(r));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->maskValid = false;  // (the root's layers may have been rewritten in place before the broadcast)
   return bind_layers(ctx);
+}
+
+// The caller rewrote an adopted / broadcast layer IN PLACE (fhp_map_layer_device, fhp_set_map_device): every derived
+// structure — the cell-class planes of the default staging path — is rebuilt by the next plan.
+int fhp_map_changed(fhp_ctx* ctx) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->haveMap) return fail(ctx, FHP_ERR_NO_MAP, "no map set");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());  // no plan may be reading the planes that are about to be rebuilt
+  ctx->maskValid = false;
+  return FHP_OK;
 }
 
 }  // extern "C"

@@ -66,6 +66,7 @@ def load_lib():
     L.fhp_map_info.argtypes = [vp, C.POINTER(MapDesc)]
     L.fhp_map_layer_device.argtypes = [vp, C.c_char_p]
     L.fhp_map_layer_device.restype = vp
+    L.fhp_map_changed.argtypes = [vp]
     L.fhp_plan.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp]
     L.fhp_plan_ex.argtypes = [vp, vp, i32, vp, i64, i32, vp]
     L.fhp_cycle_kpi.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -165,6 +166,10 @@ class Fhp:
         self._check(self.L.fhp_set_map_device(self.h, C.byref(d), C.cast(ptrs, C.c_void_p)))
         self._keep = (keepalive, arr, ptrs)
         self.map_geometry = geometry
+
+    def map_changed(self):
+        """fhp_map_changed: an adopted / broadcast layer was rewritten in place."""
+        self._check(self.L.fhp_map_changed(self.h))
 
     def layer_device_ptr(self, name: str) -> int:
         return int(self.L.fhp_map_layer_device(self.h, name.encode()) or 0)

@@ -350,6 +350,30 @@ def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
     assert np.array_equal(r24["x"], rb["x"]) and np.array_equal(r24["z"].astype(np.float64), rb["z"])
 
 
+def test_adopted_layer_rewritten_in_place_needs_map_changed(fhp, oracle):
+    """fhp_set_map_device adopts caller-owned device buffers.  When the caller rewrites the traversability layer in place
+    (e.g. re-broadcasts into the same tensors) it calls fhp_map_changed; the plan after that equals the oracle on the NEW
+    content on every staging path (the cell-class planes of the default path are rebuilt)."""
+    import torch
+    m1 = synth.rough_map(500, 500, 0.02, seed=41, start=(17, 333))
+    m2 = synth.rough_map(500, 500, 0.02, seed=42, start=(17, 333))
+    names = ["traversability", "elevation"]
+    layers = [torch.from_numpy(np.ascontiguousarray(m1.layers[n].T)).cuda() for n in names]
+    fhp.set_map_device(m1, names, [t.data_ptr() for t in layers], keepalive=layers)
+    q = synth.uniform_queries(256, (-4.0, 1.0), (-4.0, 4.0), seed=6)
+    p = _abi.yaml_params()
+    assert compare_plans(fhp.plan(p, q, 8, centroid=True), oracle.plan(m1, p, q, 8), "adopted, first content") <= XYZ_TOL
+    for t, n in zip(layers, names):  # in place: same device buffers, new content
+        t.copy_(torch.from_numpy(np.ascontiguousarray(m2.layers[n].T)))
+    torch.cuda.synchronize()
+    fhp.map_changed()
+    got = fhp.plan(p, q, 8, centroid=True)
+    exp2 = oracle.plan(m2, p, q, 8)
+    assert compare_plans(got, exp2, "adopted, rewritten in place") <= XYZ_TOL
+    assert not np.array_equal(exp2[2]["n_rows"], oracle.plan(m1, p, q, 8)[2]["n_rows"])  # the two maps really differ
+    fhp.set_map(synth.flat_map(64, 64, 0.02))  # drop the adopted pointers before the tensors go away
+
+
 def test_streamed_response_equals_plan_rows(fhp):
     """fhp_plan_stream (the kernel writes 20-byte points straight into pinned host memory, cycle-major blocks of 8
     queries with the successful ones packed to the front) carries exactly the rows fhp_plan returns; the masks give
