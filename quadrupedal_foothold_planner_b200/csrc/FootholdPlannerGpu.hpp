@@ -1,25 +1,37 @@
 // FootholdPlannerGpu.hpp — the host side a ROS node links: a C++11, header-only class with the member names,
 // argument meaning and error behaviour of foothold_planner::FootholdPlanner for the hot path
 // (foothold_planner/include/foothold_planner/FootholdPlanner.hpp:38-757), implemented on the libfhp C-ABI
-// (include/fhp.h).  ROS and grid_map stay on the host: with FHP_WITH_ROS defined the ROS/grid_map types are used
-// directly; without it (this image has no ROS) plain structs of the same shape stand in, so the file compiles and
-// is exercised by tests/test_cpp_shim.py.
+// (include/fhp.h).  ROS and grid_map stay on the host.
 //
-//   reference member                               here
-//   ---------------------------------------------  -------------------------------------------------------------
-//   gridmapCallback(grid_map_msgs::GridMap)         gridmapCallback(const GridMapView&)      FP.cpp:504-536
-//   globalFootholdPlan(Request&, Response&)         globalFootholdPlan(Request&, Response&)  FP.cpp:539-1602
-//   checkFoothold(map, center, r, R, poly, out, ok) checkFoothold(center, polyCenter, out, ok)     FP.cpp:2001-2036
-//   checkDefaultFoothold(map, center, r)            checkDefaultFoothold(center)             FP.cpp:2039-2082
-//   checkFootholdUseCentroidMethod(map, p, out,..)  checkFootholdUseCentroidMethod(p, out)   FP.cpp:1605-1997
-//   getFootholdMeanHeight(map, center, r, h)        getFootholdMeanHeight(center)            FP.cpp:2520-2554
-//   checkCandidateFoothold(map, c, r, R, poly, out) checkCandidateFoothold(c, polyCenter, out)  FP.cpp:2085-2114
-//   checkCirclePolygonFoothold(map, c, r, poly)     checkCirclePolygonFoothold(c, polyCenter)   FP.cpp:2117-2163
-//   setFirstGait / getPolygonCenter / getDefaultFootholdNext / getSearchPolygon / getFootholdSearchGridMap
-//                                                   same names, host-side (fhp_initial_stance, fhp_search_geometry)
-// The map arguments disappear because the map is device-resident after gridmapCallback (the reference passes
-// copies of the same member map); radii/thresholds come from the rosparams as in the reference.
+// Two build modes:
+//   -DFHP_WITH_ROS   the real ROS / grid_map headers are included and the class works on geometry_msgs::Point(Stamped),
+//                    foothold_planner_msgs::Foothold / GlobalFootholds, foothold_planner::GlobalFootholdPlan::Request /
+//                    Response, grid_map_msgs::GridMap, grid_map::Position / Polygon / GridMap, nav_msgs::Path and
+//                    ros::Publisher themselves.  (This image has no ROS: tests/test_cpp_shim.py compiles and runs this
+//                    mode against tests/cpp/mock_ros/, headers that declare those types with their real field names.)
+//   default          plain structs of the same shape stand in, so the file compiles anywhere.
+//
+// Every member exists twice:
+//   * with the reference's OWN signature (FootholdPlanner.hpp:51-448) — by-value maps become const references and are
+//     ignored, because the map is device-resident after gridmapCallback (the reference passes copies of the very same
+//     member map); radii arguments are honoured per call; a polygon argument must be a rectangle as getSearchPolygon
+//     builds it (its centre is recovered exactly, anything else throws std::invalid_argument);
+//   * in a short form on plain doubles (used by batch callers and the tests).
+//
+//   reference member (FootholdPlanner.hpp / FP.cpp)                                   C-ABI entry
+//   gridmapCallback(grid_map_msgs::GridMap)                         :491 / :504-536     fhp_set_map_msg / fhp_set_map
+//   globalFootholdPlan(Request&, Response&)                         :51  / :539-1602    fhp_plan_ex
+//   checkFootholdUseCentroidMethod(map, p, out, beginRow, endRow)   :71  / :1605-1997   fhp_check_centroid
+//   checkFoothold(map, center, r, R, polygon, out, ok)              :94  / :2001-2036   fhp_check_foothold
+//   checkDefaultFoothold(map, center, r)                            :110 / :2039-2082   fhp_check_default
+//   checkCandidateFoothold(map, c, r, R, polygon, out)              :124 / :2085-2114   fhp_check_candidate
+//   checkCirclePolygonFoothold(map, c, r, polygon)                  :140 / :2117-2163   fhp_check_circle_polygon
+//   getFootholdSearchGridMap(4 feet, path, 4 next, 4 polygons, 8 publishers) :169 / :2166-2250   fhp_search_geometry
+//   getDefaultFootholdNext / getPolygonCenter / getSearchPolygon    :218-240 / :2411-2517  fhp_search_geometry
+//   getFootholdMeanHeight(map, center, r, h)                        :262 / :2520-2554   fhp_mean_height
+//   setFirstGait(4 initial, 4 current)                              :345 / :2679-2699   fhp_initial_stance
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -27,7 +39,27 @@
 
 #include "fhp.h"
 
-#ifndef FHP_WITH_ROS
+#ifdef FHP_WITH_ROS
+#include <foothold_planner/GlobalFootholdPlan.h>
+#include <foothold_planner_msgs/Foothold.h>
+#include <foothold_planner_msgs/GlobalFootholds.h>
+#include <geometry_msgs/Point.h>
+#include <geometry_msgs/PointStamped.h>
+#include <grid_map_core/GridMap.hpp>
+#include <grid_map_core/Polygon.hpp>
+#include <grid_map_msgs/GridMap.h>
+#include <nav_msgs/Path.h>
+#include <ros/ros.h>
+#include <std_msgs/Float32MultiArray.h>
+namespace foothold_planner {
+typedef geometry_msgs::Point Point;
+typedef geometry_msgs::PointStamped PointStamped;
+typedef foothold_planner_msgs::Foothold Foothold;
+typedef foothold_planner_msgs::GlobalFootholds GlobalFootholds;
+typedef GlobalFootholdPlan::Request GlobalFootholdPlanRequest;
+typedef GlobalFootholdPlan::Response GlobalFootholdPlanResponse;
+}  // namespace foothold_planner
+#else
 // stand-ins with the field names of grid_map_msgs/GridMap and the std_msgs / geometry_msgs types it embeds
 namespace std_msgs {
 struct Header {
@@ -70,15 +102,41 @@ struct GridMap {
   GridMap() : outer_start_index(0), inner_start_index(0) {}
 };
 }  // namespace grid_map_msgs
-#endif
-
+namespace grid_map {  // the three grid_map_core types that appear in the reference's member signatures
+struct Position {    // Eigen::Vector2d
+  double v[2];
+  Position() { v[0] = v[1] = 0; }
+  Position(double x, double y) { v[0] = x; v[1] = y; }
+  double x() const { return v[0]; }
+  double y() const { return v[1]; }
+  double& x() { return v[0]; }
+  double& y() { return v[1]; }
+};
+class Polygon {
+ public:
+  void addVertex(const Position& p) { vertices_.push_back(p); }
+  const Position& getVertex(size_t i) const { return vertices_.at(i); }
+  size_t nVertices() const { return vertices_.size(); }
+ private:
+  std::vector<Position> vertices_;
+};
+class GridMap {};  // the map argument of the reference members: ignored (the map is device-resident)
+}  // namespace grid_map
+namespace nav_msgs {
+struct Path {};
+}
+namespace ros {
+class Publisher {};
+}
 namespace foothold_planner {
-
-#ifndef FHP_WITH_ROS
-// stand-ins with the field names of geometry_msgs/Point, foothold_planner_msgs/Foothold and GlobalFootholds
+// stand-ins with the field names of geometry_msgs/Point(Stamped), foothold_planner_msgs/Foothold and GlobalFootholds
 struct Point {
   double x, y, z;
   Point() : x(0), y(0), z(0) {}
+};
+struct PointStamped {
+  std_msgs::Header header;
+  Point point;
 };
 struct Foothold {
   Point point;
@@ -87,11 +145,11 @@ struct Foothold {
   Foothold() : foot_id(0), gait_cycle_id(0) {}
 };
 struct GlobalFootholds {
-  bool success;
+  uint8_t success;  // bool on the wire
   uint8_t gait_cycles;
   uint8_t gait_cycles_succeed;
   std::vector<Foothold> footholds;
-  GlobalFootholds() : success(false), gait_cycles(0), gait_cycles_succeed(0) {}
+  GlobalFootholds() : success(0), gait_cycles(0), gait_cycles_succeed(0) {}
 };
 struct GlobalFootholdPlanRequest {  // srv/GlobalFootholdPlan.srv:1-5
   Point FR_current_foothold, RR_current_foothold, RL_current_foothold, FL_current_foothold;  // ignored (FP.cpp:546-549)
@@ -101,7 +159,10 @@ struct GlobalFootholdPlanRequest {  // srv/GlobalFootholdPlan.srv:1-5
 struct GlobalFootholdPlanResponse {  // srv/GlobalFootholdPlan.srv:7
   GlobalFootholds footholds;
 };
+}  // namespace foothold_planner
 #endif
+
+namespace foothold_planner {
 
 // What gridmapCallback needs from a grid_map::GridMap after GridMapRosConverter::fromMessage (FP.cpp:506):
 // geometry + one column-major float pointer per layer (gridmap_[name].data()).
@@ -127,7 +188,12 @@ class FootholdPlannerGpu {
   // one SPHERE_LIST / CUBE_LIST / POINTS point array per foot, in foot order RF,RH,LH,LF
   std::vector<Point> nominalMarkerPoints[4], centroidMarkerPoints[4], defaultMarkerPoints[4];
 
-  explicit FootholdPlannerGpu(int device = 0) : ctx_(NULL) {
+  // true (default): globalFootholdPlan returns false where the reference's service call would (see there)
+  bool abortLikeReference;
+  bool optSubmapWouldFail_;
+
+  explicit FootholdPlannerGpu(int device = 0)
+      : abortLikeReference(true), optSubmapWouldFail_(false), ajustedPoseY_(0.0), ctx_(NULL) {
     fhp_default_params(&params);
     initialPose_[0] = initialPose_[1] = initialPose_[2] = 0.0;
     if (fhp_create(device, &ctx_) != FHP_OK) throw std::runtime_error(std::string("fhp_create: ") + fhp_last_error(NULL));
@@ -235,6 +301,17 @@ class FootholdPlannerGpu {
     out.default_chain = &dfl[0];
     out.status = &st;
     if (fhp_plan_ex(ctx_, &params, 1, &q, 1, cycles, &out) != FHP_OK) return false;
+    // The reference aborts the service call when the gait-cycle submap of its opt (NLopt) chain does not fit the map
+    // (`return false`, FP.cpp:931-934); libfhp reports that predicate for cycle 0 (FHP_STATUS_OPT_SUBMAP_FAIL).  The
+    // reference has only the four stance rows in nominalGlobalFootholdsMsg_ at that point and leaves the response alone.
+    optSubmapWouldFail_ = (st.reserved & FHP_STATUS_OPT_SUBMAP_FAIL) != 0;
+    if (optSubmapWouldFail_ && abortLikeReference) {
+      st.n_rows = 4;
+      st.success = 0;
+      st.gait_cycles_succeed = 0;
+      fill(nominalGlobalFootholdsMsg_, nom, st, nominalMarkerPoints);
+      return false;
+    }
     fill(nominalGlobalFootholdsMsg_, nom, st, nominalMarkerPoints);
     fill(centroidGlobalFootholdsMsg_, cen, st, centroidMarkerPoints);
     fill(defaultGlobalFootholds_, dfl, st, defaultMarkerPoints);
@@ -367,12 +444,185 @@ class FootholdPlannerGpu {
     getFootholdSearchGridMap(cur, 0.0, next, poly, c);
     return c;
   }
+
+  // ---- the reference's own member signatures (FootholdPlanner.hpp:51-448) ----------------------------------------------
+  // FP.hpp:71-75.  beginRow / endRow (the clear band's rows, consumed only by the opt chain's constraints) are set to 0.
+  bool checkFootholdUseCentroidMethod(const grid_map::GridMap&, PointStamped defaultFoothold, PointStamped& resultFoothold,
+                                      int& beginRow, int& endRow) {
+    beginRow = endRow = 0;
+    return checkFootholdUseCentroidMethod(defaultFoothold.point.x, defaultFoothold.point.y, resultFoothold.point);
+  }
+  // FP.hpp:94-100 (returns a default-constructed point, like the reference: FP.cpp:2008, :2035)
+  PointStamped checkFoothold(const grid_map::GridMap&, grid_map::Position center, float footRadius, float searchRadius,
+                             const grid_map::Polygon& polygon, PointStamped& footholdResult, bool& footholdValidation) {
+    const fhp_params p = with_radii(footRadius, searchRadius);
+    double rc[2];
+    rectangle_centre(polygon, p, rc);
+    const double c[2] = {center.x(), center.y()};
+    fhp_foothold out;
+    uint8_t ok = 0;
+    check(fhp_check_foothold(ctx_, &p, c, rc, 1, &out, &ok), "fhp_check_foothold");
+    footholdResult.point.x = out.x;
+    footholdResult.point.y = out.y;
+    if (ok) footholdResult.point.z = out.z;
+    footholdValidation = ok != 0;
+    return PointStamped();
+  }
+  // FP.hpp:110-112
+  bool checkDefaultFoothold(const grid_map::GridMap&, grid_map::Position center, float footRadius) {
+    const fhp_params p = with_radii(footRadius, params.search_radius);
+    const double c[2] = {center.x(), center.y()};
+    uint8_t ok = 0;
+    check(fhp_check_default(ctx_, &p, c, 1, &ok), "fhp_check_default");
+    return ok != 0;
+  }
+  // FP.hpp:124-129
+  bool checkCandidateFoothold(const grid_map::GridMap&, grid_map::Position spiralCenter, float footRadius, float searchRadius,
+                              const grid_map::Polygon& polygon, PointStamped& footholdResult) {
+    const fhp_params p = with_radii(footRadius, searchRadius);
+    double rc[2];
+    rectangle_centre(polygon, p, rc);
+    const double c[2] = {spiralCenter.x(), spiralCenter.y()};
+    fhp_foothold out;
+    uint8_t ok = 0;
+    check(fhp_check_candidate(ctx_, &p, c, rc, 1, &out, &ok), "fhp_check_candidate");
+    if (ok) {
+      footholdResult.point.x = out.x;
+      footholdResult.point.y = out.y;
+    }
+    return ok != 0;
+  }
+  // FP.hpp:140-143 (the third argument is the FOOT radius: it is what the reference's CircleIterator is given, FP.cpp:2126)
+  bool checkCirclePolygonFoothold(const grid_map::GridMap&, grid_map::Position center, float footRadius,
+                                  const grid_map::Polygon& polygon) {
+    const fhp_params p = with_radii(footRadius, params.search_radius);
+    double rc[2];
+    rectangle_centre(polygon, p, rc);
+    const double c[2] = {center.x(), center.y()};
+    uint8_t ok = 0;
+    check(fhp_check_circle_polygon(ctx_, &p, c, rc, 1, &ok), "fhp_check_circle_polygon");
+    return ok != 0;
+  }
+  // FP.hpp:262-265
+  float getFootholdMeanHeight(const grid_map::GridMap&, grid_map::Position center, float radius, double h) {
+    fhp_params p = with_radii(radius, params.search_radius);
+    p.h = h;
+    const double c[2] = {center.x(), center.y()};
+    float z = 0;
+    check(fhp_mean_height(ctx_, &p, c, 1, &z), "fhp_mean_height");
+    return z;
+  }
+  // FP.hpp:345-352.  The reference copies its arguments; the stance itself is initialize()'s (FP.cpp:350-378), which is
+  // what the four *_initialPosition arguments hold there.
+  bool setFirstGait(PointStamped RF_initialPosition, PointStamped RH_initialPosition, PointStamped LH_initialPosition,
+                    PointStamped LF_initialPosition, PointStamped& RF_currentPosition, PointStamped& RH_currentPosition,
+                    PointStamped& LH_currentPosition, PointStamped& LF_currentPosition) {
+    const PointStamped* in[4] = {&RF_initialPosition, &RH_initialPosition, &LH_initialPosition, &LF_initialPosition};
+    PointStamped* out[4] = {&RF_currentPosition, &RH_currentPosition, &LH_currentPosition, &LF_currentPosition};
+    const double hs = static_cast<double>(params.step_length / 2);  // float division (FP.cpp:2693)
+    const double hx = hs * std::cos(params.heading), hy = hs * std::sin(params.heading);
+    for (int f = 0; f < 4; ++f) {
+      out[f]->point = in[f]->point;
+      if (params.heading != 0.0) {
+        out[f]->point.x = in[f]->point.x - hx;
+        out[f]->point.y = in[f]->point.y - hy;
+      } else {
+        out[f]->point.x = in[f]->point.x - hs;
+      }
+    }
+    return true;
+  }
+  // FP.hpp:227-230
+  Point getPolygonCenter(PointStamped RF_point, PointStamped RH_point, PointStamped LH_point, PointStamped LF_point) {
+    return getPolygonCenter(RF_point.point, RH_point.point, LH_point.point, LF_point.point);
+  }
+  // FP.hpp:218-219 (z is left at 0, FP.cpp:2411-2418)
+  PointStamped getDefaultFootholdNext(Point feetCenterNext, PointStamped defaultBias) {
+    PointStamped f;
+    f.point.x = feetCenterNext.x + defaultBias.point.x;
+    f.point.y = feetCenterNext.y + defaultBias.point.y;
+    return f;
+  }
+  // FP.hpp:239-240 (vertex order leftup, rightup, rightdown, leftdown, FP.cpp:2496-2517; rotated by params.heading)
+  grid_map::Polygon getSearchPolygon(PointStamped center, float radius) {
+    const fhp_params p = with_radii(params.foot_radius, radius);
+    double v[8];
+    rectangle_vertices(p, center.point.x, center.point.y, v);
+    grid_map::Polygon poly;
+    for (int k = 0; k < 4; ++k) poly.addVertex(grid_map::Position(v[2 * k], v[2 * k + 1]));
+    return poly;
+  }
+  // FP.hpp:169-189.  The path and the eight publishers are host-side visualisation and stay untouched.
+  bool getFootholdSearchGridMap(PointStamped RF_position, PointStamped RH_position, PointStamped LH_position,
+                                PointStamped LF_position, nav_msgs::Path&, PointStamped& RF_nextPosition,
+                                PointStamped& RH_nextPosition, PointStamped& LH_nextPosition, PointStamped& LF_nextPosition,
+                                grid_map::Polygon& RF_polygon, grid_map::Polygon& RH_polygon, grid_map::Polygon& LH_polygon,
+                                grid_map::Polygon& LF_polygon, ros::Publisher, ros::Publisher, ros::Publisher, ros::Publisher,
+                                ros::Publisher, ros::Publisher, ros::Publisher, ros::Publisher) {
+    const Point cur[4] = {RF_position.point, RH_position.point, LH_position.point, LF_position.point};
+    Point next[4], poly[4][4], c;
+    getFootholdSearchGridMap(cur, ajustedPoseY_, next, poly, c);
+    PointStamped* nx[4] = {&RF_nextPosition, &RH_nextPosition, &LH_nextPosition, &LF_nextPosition};
+    grid_map::Polygon* pg[4] = {&RF_polygon, &RH_polygon, &LH_polygon, &LF_polygon};
+    for (int f = 0; f < 4; ++f) {
+      nx[f]->point = next[f];
+      *pg[f] = grid_map::Polygon();
+      for (int v = 0; v < 4; ++v) pg[f]->addVertex(grid_map::Position(poly[f][v].x, poly[f][v].y));
+    }
+    return true;
+  }
+  double ajustedPoseY_;  // ajustedPose_[1] (FP.cpp:381, :759, :1578) for the reference-signature getFootholdSearchGridMap
+
   fhp_ctx* ctx() { return ctx_; }
 
  private:
   fhp_ctx* ctx_;
   FootholdPlannerGpu(const FootholdPlannerGpu&);
   FootholdPlannerGpu& operator=(const FootholdPlannerGpu&);
+  fhp_params with_radii(float footRadius, float searchRadius) const {
+    fhp_params p = params;
+    p.foot_radius = footRadius;
+    p.search_radius = searchRadius;
+    return p;
+  }
+  // getSearchPolygon's vertices for a rectangle centre (FP.cpp:2496-2517; heading extension: rotated offsets, the same
+  // expressions as libfhp's derive_params)
+  static void rectangle_vertices(const fhp_params& p, double cx, double cy, double v[8]) {
+    const double R = p.search_radius, hR = 0.5 * p.search_radius;
+    const double ox[4] = {R, R, -R, -R}, oy[4] = {hR, -hR, -hR, hR};
+    const double c = std::cos(p.heading), s = std::sin(p.heading);
+    for (int k = 0; k < 4; ++k) {
+      const double rx = p.heading != 0.0 ? ox[k] * c - oy[k] * s : ox[k];
+      const double ry = p.heading != 0.0 ? ox[k] * s + oy[k] * c : oy[k];
+      v[2 * k] = cx + rx;
+      v[2 * k + 1] = cy + ry;
+    }
+  }
+  // The centre of a rectangle that getSearchPolygon built: libfhp takes search rectangles by their centre.  Any centre
+  // whose rectangle reproduces the four vertices bit for bit IS the rectangle (the planner only ever looks at the
+  // vertices), so the estimate vertex0 - offset0 and its floating-point neighbours are tried.
+  static void rectangle_centre(const grid_map::Polygon& polygon, const fhp_params& p, double rc[2]) {
+    if (polygon.nVertices() != 4) throw std::invalid_argument("search polygon: getSearchPolygon builds 4 vertices");
+    double off[8];
+    rectangle_vertices(p, 0.0, 0.0, off);
+    for (int axis = 0; axis < 2; ++axis) {
+      double want[4];
+      for (int k = 0; k < 4; ++k) want[k] = axis == 0 ? polygon.getVertex(k).x() : polygon.getVertex(k).y();
+      const double c0 = want[0] - off[axis];
+      const double up1 = std::nextafter(c0, 1e300), dn1 = std::nextafter(c0, -1e300);
+      const double cands[5] = {c0, up1, dn1, std::nextafter(up1, 1e300), std::nextafter(dn1, -1e300)};
+      bool found = false;
+      for (int t = 0; t < 5 && !found; ++t) {
+        bool ok = true;
+        for (int k = 0; k < 4; ++k) ok = ok && (cands[t] + off[2 * k + axis] == want[k]);
+        if (ok) {
+          rc[axis] = cands[t];
+          found = true;
+        }
+      }
+      if (!found) throw std::invalid_argument("search polygon is not a rectangle built by getSearchPolygon with these radii");
+    }
+  }
   void check(int rc, const char* what) {
     if (rc == FHP_ERR_MISSING_LAYER) throw std::out_of_range(fhp_last_error(ctx_));  // GridMap::at throws this
     if (rc != FHP_OK) throw std::runtime_error(std::string(what) + ": " + fhp_last_error(ctx_));
@@ -381,7 +631,7 @@ class FootholdPlannerGpu {
   static void fill(GlobalFootholds& msg, const std::vector<fhp_foothold>& rows, const fhp_query_status& st,
                    std::vector<Point> markers[4]) {
     for (int f = 0; f < 4; ++f) markers[f].clear();
-    msg.success = st.success != 0;
+    msg.success = st.success != 0 ? 1 : 0;
     msg.gait_cycles = st.gait_cycles;
     msg.gait_cycles_succeed = st.gait_cycles_succeed;
     msg.footholds.clear();

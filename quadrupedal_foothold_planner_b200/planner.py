@@ -463,6 +463,14 @@ class FootholdPlanner:
         cycles = int(request.gait_cycles) & 0xFF  # uint8 in the .srv
         q = make_queries([self.initialPose_])
         nom, cen, dfl, st = self.fhp.plan_ex(self.params, q, cycles)
+        # the reference aborts the call when its opt chain's gait-cycle submap does not fit the map (`return false`,
+        # FP.cpp:931-934) with only the stance rows recorded; libfhp reports that predicate for cycle 0
+        self.optSubmapWouldFail_ = bool(st[0]["reserved"] & _abi.FHP_STATUS_OPT_SUBMAP_FAIL)
+        if self.optSubmapWouldFail_:
+            st = st.copy()
+            st[0]["n_rows"], st[0]["success"], st[0]["gait_cycles_succeed"] = 4, 0, 0
+            self.nominalGlobalFootholdsMsg_ = rows_to_msg(nom[0], st[0])
+            return False
         self.nominalGlobalFootholdsMsg_ = rows_to_msg(nom[0], st[0])
         self.centroidGlobalFootholdsMsg_ = rows_to_msg(cen[0], st[0])
         # globalFootholdsResult_.defaultFootholds (FP.cpp:666-671, :1344-1348) and footholdsKPI_ (:1357-1368, :1422-1433)

@@ -11,23 +11,28 @@ from quadrupedal_foothold_planner_b200 import _abi, planner, synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
+def _build(tmp_path, ros_mode=False):
+    """ros_mode: -DFHP_WITH_ROS against tests/cpp/mock_ros (headers with the real ROS / grid_map type and field names)."""
     planner.load_lib()
-    exe = str(tmp_path / "shim_main")
+    exe = str(tmp_path / ("shim_main_ros" if ros_mode else "shim_main"))
     pkg = os.path.join(ROOT, "quadrupedal_foothold_planner_b200")
-    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "csrc"),
+    extra = ["-DFHP_WITH_ROS", "-I", os.path.join(ROOT, "tests", "cpp", "mock_ros")] if ros_mode else []
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-Werror"] + extra +
+                          ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "csrc"),
                            os.path.join(ROOT, "tests", "cpp", "shim_main.cpp"), "-o", exe, "-L", pkg, "-lfhp",
                            "-Wl,-rpath," + pkg])
     return exe
 
 
-def test_cpp_shim_links(tmp_path):
-    assert os.path.exists(_build(tmp_path))
+@pytest.mark.parametrize("ros_mode", [False, True])
+def test_cpp_shim_links(tmp_path, ros_mode):
+    assert os.path.exists(_build(tmp_path, ros_mode))
 
 
 @pytest.mark.gpu
-def test_cpp_shim_matches_oracle(tmp_path, oracle):
-    exe = _build(tmp_path)
+@pytest.mark.parametrize("ros_mode", [False, True])
+def test_cpp_shim_matches_oracle(tmp_path, oracle, ros_mode):
+    exe = _build(tmp_path, ros_mode)
     m = synth.rough_map(400, 300, 0.02, seed=13, start=(31, 250))
     path = str(tmp_path / "map.bin")
     with open(path, "wb") as f:
@@ -54,3 +59,39 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle):
             x, y, z, foot, cyc = line.split()
             assert abs(float(x) - row["x"]) <= 1e-5 and abs(float(y) - row["y"]) <= 1e-5 and abs(float(z) - row["z"]) <= 1e-5
             assert (int(foot), int(cyc)) == (row["foot_id"], row["gait_cycle_id"])
+        # marker payloads (FP.cpp:2731-2790): per chain and foot, the points of that foot's planned rows in cycle order
+        enom, ecen, edfl, _, est = oracle.plan_ex(m, _abi.yaml_params(), _abi.make_queries([pose]), 9)
+        for chain, rows in enumerate((enom, ecen, edfl)):
+            tok = out[2 + n + chain].split()
+            assert tok[0] == "markers" and int(tok[1]) == chain
+            k = 2
+            for foot in range(4):
+                exp = [r for r in rows[0][4:n] if r["foot_id"] == foot]
+                cnt = int(tok[k])
+                k += 1
+                assert cnt == len(exp) == (n - 4) // 4
+                for r in exp:
+                    got = [float(v) for v in tok[k:k + 3]]
+                    k += 3
+                    assert max(abs(got[0] - r["x"]), abs(got[1] - r["y"]), abs(got[2] - r["z"])) <= 1e-5
+            assert k == len(tok)
+        # the reference-signature overloads agree with the short forms; a foreign polygon is refused
+        assert out[5 + n].split() == ["refsig", "1", "1"]
+
+
+@pytest.mark.gpu
+def test_cpp_shim_reports_the_reference_abort(tmp_path, oracle):
+    """A pose whose opt-chain gait submap cannot fit the map: the reference's service returns false at cycle 0
+    (FP.cpp:931-934) with only the stance rows recorded; so does the shim (FHP_STATUS_OPT_SUBMAP_FAIL)."""
+    exe = _build(tmp_path)
+    m = synth.rough_map(200, 200, 0.02, seed=13, start=(0, 0))
+    path = str(tmp_path / "map.bin")
+    with open(path, "wb") as f:
+        f.write(np.asfortranarray(m.layers["traversability"]).tobytes(order="F"))
+        f.write(np.asfortranarray(m.layers["elevation"]).tobytes(order="F"))
+    pose = [2.3, 0.4, 0.0]  # the next stance centre lies outside the 4 m x 4 m map
+    st = oracle.plan(m, _abi.yaml_params(), _abi.make_queries([pose]), 3, centroid=False)[2]
+    assert st[0]["reserved"] & 0x80
+    out = subprocess.check_output([exe, path, "200", "200", "0.02", "0", "0", repr(pose[0]), repr(pose[1]), repr(pose[2]),
+                                   "3"], text=True).strip().splitlines()
+    assert out[0].split() == ["aborted", "1", "4"]
