@@ -350,6 +350,10 @@ void derive_params(const fhp_params& p, ParDev& o, bool forceHeading = false) {
     o.isosLx = longEdge + o.rectLx;
     o.isosLy = shortEdge + o.rectLy;
   }
+  for (int k = 0; k < 4; ++k) {  // edge k joins vertex k and vertex k-1 (PNPOLY's i and j)
+    const int j = (k + 3) & 3;
+    o.rectSlope[k] = (o.rectVx[j] - o.rectVx[k]) / (o.rectVy[j] - o.rectVy[k]);  // inf / nan for horizontal edges: never used
+  }
   o.halfStepX = o.halfStep * o.ch;
   o.halfStepY = o.halfStep * o.sh;
   if (o.heading)

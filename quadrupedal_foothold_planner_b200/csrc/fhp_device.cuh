@@ -1071,11 +1071,26 @@ __device__ __noinline__ bool pnpoly_point(const ParDev& P, double rx, double ry,
   return (cross & 1) != 0;
 }
 // The window rows of ONE window column (cell index u1 along y) whose cell centre is inside the polygon.  Along a column
-// p.y is fixed, so every edge that straddles it contributes ONE threshold X_e (computed exactly as upstream does) and
-// the test p.x < X_e; cell-centre x strictly decreases with the row, so "p.x < X_e" holds from first_below(X_e) on and
-// the parity of the crossings is the XOR of those suffix masks.  Exact for any polygon, ~2 divisions per column.
+// p.y is fixed, so every edge that straddles it contributes ONE threshold X_e (upstream's expression) and the test
+// p.x < X_e; cell-centre x strictly decreases with the row, so "p.x < X_e" holds from first_below(X_e) on and the
+// parity of the crossings is the XOR of those suffix masks.  Exact for any polygon.
+// The division of X_e is only PAID where it can matter: X_e is first estimated from the edge's slope (sl[i] =
+// (v[j].x - v[i].x) / (v[j].y - v[i].y) of the vertex offsets, derived once per parameter set on the host); the
+// estimate is within a few ulp (~1e-15 m) of upstream's value, so the row index it implies is the exact one unless it
+// falls within 1e-6 cell of a row boundary — then (and only then) upstream's expression and the exact walk decide.
+struct PolySlopes {
+  double s0, s1, s2, s3;  // edge i joins vertex i and vertex i-1 (PNPOLY's j)
+};
+__device__ __forceinline__ PolySlopes poly_slopes(const ParDev& P) {  // per parameter set: derived on the host
+  PolySlopes s;
+  s.s0 = P.rectSlope[0];
+  s.s1 = P.rectSlope[1];
+  s.s2 = P.rectSlope[2];
+  s.s3 = P.rectSlope[3];
+  return s;
+}
 __device__ __noinline__ uint32_t poly_col_rows(const MapDev& M, const ParDev& P, double rx, double ry, int w0, int nRows,
-                                               int u1) {
+                                               int u1, double s0, double s1, double s2, double s3) {
   const double Y = pos_axis(M.fcy, M.res, u1);
   uint32_t m = 0u;
   double jx = rx + P.rectVx[3], jy = ry + P.rectVy[3];
@@ -1083,14 +1098,65 @@ __device__ __noinline__ uint32_t poly_col_rows(const MapDev& M, const ParDev& P,
   for (int i = 0; i < 4; ++i) {
     const double ix = rx + P.rectVx[i], iy = ry + P.rectVy[i];
     if ((iy > Y) != (jy > Y)) {
-      const double X = div_rn((jx - ix) * (Y - iy), jy - iy) + ix;
-      const int a = first_below(M.fcx, M.res, M.rinv, w0, nRows, X);
+      const double sl = i == 0 ? s0 : (i == 1 ? s1 : (i == 2 ? s2 : s3));
+      const double Xe = sl * (Y - iy) + ix;  // estimate of upstream's threshold
+      const double t = (M.fcx - Xe) * M.rinv - static_cast<double>(w0);
+      const int fl = __double2int_rd(t);
+      const double fr = t - static_cast<double>(fl);
+      int a;
+      if (fr > 1e-6 && fr < 1.0 - 1e-6 && fabs(t) < 1.0e6) {
+        a = min(max(fl, -1), nRows - 1) + 1;
+      } else {  // within the guard band of a row boundary (or not finite): upstream's expression, exact predicate
+        a = first_below(M.fcx, M.res, M.rinv, w0, nRows, div_rn((jx - ix) * (Y - iy), jy - iy) + ix);
+      }
       if (a < 32) m ^= 0xffffffffu << a;
     }
     jx = ix;
     jy = iy;
   }
   return m;
+}
+
+// The same row masks for ALL window columns at once, edge by edge (mask staging path): `acc` = shared-space address of
+// WIN words, one per column, that receive the masks.  An edge straddles the contiguous run of columns between
+// first_below(v[i].y) and first_below(v[j].y) (cell-centre y decreases with the column: the straddle test
+// (v[i].y > p.y) != (v[j].y > p.y) flips exactly there), and along that run the threshold's row coordinate advances
+// by the edge's slope per column — so a column costs one multiply-add and the integer split of poly_col_rows; only an
+// estimate within 1e-6 cell of a row boundary falls back to upstream's expression and the exact walk.
+__device__ __noinline__ void poly_rows_all(const MapDev& M, const ParDev& P, double rx, double ry, int w0, int w1, int nRows,
+                                           int nCols, uint32_t acc) {
+  for (int b = 0; b < nCols; ++b) asm volatile("st.shared.u32 [%0], %1;" ::"r"(acc + static_cast<uint32_t>(b) * 4u), "r"(0u) : "memory");
+  double jx = rx + P.rectVx[3], jy = ry + P.rectVy[3];
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const double ix = rx + P.rectVx[i], iy = ry + P.rectVy[i];
+    // columns b with (iy > Y_b): b >= bi; with (jy > Y_b): b >= bj
+    const int bi = first_below(M.fcy, M.res, M.rinv, w1, nCols, iy), bj = first_below(M.fcy, M.res, M.rinv, w1, nCols, jy);
+    const int lo = min(bi, bj), hi = max(bi, bj);
+    if (lo < hi) {
+      const double sl = P.rectSlope[i];
+      const double Y0 = pos_axis(M.fcy, M.res, w1 + lo);
+      const double t0 = (M.fcx - (sl * (Y0 - iy) + ix)) * M.rinv - static_cast<double>(w0);  // row coordinate at column lo
+      for (int b = lo; b < hi; ++b) {
+        const double t = t0 + static_cast<double>(b - lo) * sl;  // Y falls by res per column: X_e by sl*res, t rises by sl
+        const int fl = __double2int_rd(t);
+        const double fr = t - static_cast<double>(fl);
+        int a;
+        if (fr > 1e-6 && fr < 1.0 - 1e-6 && fabs(t) < 1.0e6) {
+          a = min(max(fl, -1), nRows - 1) + 1;
+        } else {  // guard band of a row boundary (or not finite): upstream's expression, exact predicate
+          const double Y = pos_axis(M.fcy, M.res, w1 + b);
+          a = first_below(M.fcx, M.res, M.rinv, w0, nRows, div_rn((jx - ix) * (Y - iy), jy - iy) + ix);
+        }
+        if (a < 32) {
+          const uint32_t addr = acc + static_cast<uint32_t>(b) * 4u;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(lds_u32(addr) ^ (0xffffffffu << a)) : "memory");
+        }
+      }
+    }
+    jx = ix;
+    jy = iy;
+  }
 }
 
 // checkCirclePolygonFoothold (FP.cpp:2117-2163) for the candidate at window coordinates (qa,qb), on the planes:
@@ -1349,6 +1415,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
   const bool faithful = (P.spiralMode == FHP_SPIRAL_FAITHFUL) && !(M.start0 == 0 && M.start1 == 0);
   uint32_t rowsBox = 0, colsBox = 0, rowsIn = 0, colsIn = 0;
   Box bx = {0, 0, 0, 0};
+  PolySlopes ps = {0, 0, 0, 0};
   bool found = false;
   int fq0 = 0, fq1 = 0;
   bool pend = need && !faithful;
@@ -1356,6 +1423,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
     o.kind = FHP_KIND_CANDIDATE;
     if (HEADING) {
       bx = centre_box(rx, ry);
+      ps = poly_slopes(P);
     } else {
       bx = search_box(P, rx, ry);
       box_masks(M, G, bx, w0, w1, rowsBox, colsBox);
@@ -1372,7 +1440,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
         for (int c = 0; c < G.pack(); ++c) {
           const int b = k * G.pack() + c;
           if (b >= G.WIN()) break;
-          const uint32_t inside = poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b);
+          const uint32_t inside = poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b, ps.s0, ps.s1, ps.s2, ps.s3);
           const uint32_t bad = pl.col(PL_F, b) & (pl.col(PL_C, b) | ~inside) & rm;
           word |= bad << (c * rp);
         }
@@ -1386,6 +1454,9 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
       // registers while the loop slides over the window) — and then settles the two most common outcomes itself: no
       // acceptable cell anywhere in the spiral footprint (a stuck query), or the centre cell is valid.
       const int sh = (uc0 - w0) - G.HW();
+      // rotated rectangle: the rows inside it, per window column, into the pad words first (each is read below before the
+      // finished mask of its column — or, with the 3x3 dilation, of the column before it — overwrites it)
+      if (HEADING) poly_rows_all(M, P, rx, ry, w0, w1, G.winRows(), G.WIN(), mine + static_cast<uint32_t>(2 * G.WIN()) * 4u);
       const bool dil3 = dilated3x3(G) && pend;  // (bug-compatible spiral lanes test stencil cells one by one: raw masks)
       uint32_t anyOk = 0, okCentre = 0;
       uint32_t vPrev = 0u, vCur = 0u;  // vertically dilated masks of columns b-2 and b-1
@@ -1394,7 +1465,7 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
         uint32_t bad = 0u;
         if (b < G.WIN()) {
           const uint2 e = lds_v2(mine + static_cast<uint32_t>(b) * 8u);  // class planes (e0, e1) of column b
-          const uint32_t box = HEADING ? poly_col_rows(M, P, rx, ry, w0, G.winRows(), w1 + b)
+          const uint32_t box = HEADING ? lds_u32(mine + static_cast<uint32_t>(2 * G.WIN() + b) * 4u)  // poly_rows_all
                                        : (((colsBox >> b) & 1u) ? rowsBox : 0u);
           bad = (e.x | e.y) & ((e.x & e.y) | ~box);  // finite & (below the candidate threshold | outside the rectangle)
         }

@@ -79,6 +79,7 @@ struct ParDev {  // one per fhp_params, derived on the host exactly as FootholdP
   double ch, sh;                  // cos / sin of the heading
   double halfStepX, halfStepY;    // halfStep * ch, halfStep * sh (setFirstGait steps half a step back along u)
   double rectVx[4], rectVy[4];    // rot() of getSearchPolygon's vertex offsets (+R,+R/2) (+R,-R/2) (-R,-R/2) (-R,+R/2)
+  double rectSlope[4];            // edge slopes dx/dy of the rotated rectangle (estimates only: poly_col_rows)
   double isosLx, isosLy;          // isos_.length, isos_.width (FP.cpp:384-394): the opt chain's gait-cycle submap request
 };
 
