@@ -592,6 +592,17 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   return FHP_OK;
 }
 
+// Device alias of a page-locked, mapped host pointer (cudaHostAlloc / cudaHostRegister), or NULL for anything else.
+// (cudaPointerGetAttributes reports unregistered host memory as such instead of failing.)
+void* mapped_device_ptr(const void* h) {
+  cudaPointerAttributes at;
+  if (!h || cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 // Small batches are validated on the host before anything is launched; large ones (a walk over every query would
 // cost as much as a tenth of the plan itself) by the kernel, which reports kErrParam.
 bool param_ids_ok(const fhp_query* queries, int64_t n_queries, int32_t n_params) {
@@ -1301,15 +1312,13 @@ int fhp_plan_stream(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, co
   if (n_queries == 0) return FHP_OK;
   if ((reinterpret_cast<uintptr_t>(out_blocks) & 127u) != 0 || (reinterpret_cast<uintptr_t>(masks) & 7u) != 0)
     return fail(ctx, FHP_ERR_INVALID_ARG, "fhp_plan_stream: out_blocks must be 128-byte aligned, masks 8-byte aligned");
-  void *dSlots = nullptr, *dMask = nullptr, *dStat = nullptr;
-  if (cudaHostGetDevicePointer(&dSlots, out_blocks, 0) != cudaSuccess ||
-      cudaHostGetDevicePointer(&dStat, status, 0) != cudaSuccess ||
-      (masks && cudaHostGetDevicePointer(&dMask, masks, 0) != cudaSuccess)) {
-    cudaGetLastError();
+  void* dSlots = mapped_device_ptr(out_blocks);
+  void* dStat = mapped_device_ptr(status);
+  void* dMask = masks ? mapped_device_ptr(masks) : nullptr;
+  if (!dSlots || !dStat || (masks && !dMask))
     return fail(ctx, FHP_ERR_INVALID_ARG,
                 "fhp_plan_stream: out_blocks, masks and status must be page-locked host memory (cudaHostAlloc / "
                 "cudaHostRegister): the kernel writes them directly");
-  }
   cudaStream_t s = ctx->stream;
   int rc = prepare_params(ctx, params, n_params, s);
   if (rc != FHP_OK) return rc;
@@ -1319,11 +1328,10 @@ int fhp_plan_stream(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, co
   // the link is full duplex, so these reads do not compete with the row writes); copied first otherwise
   const fhp_query* dQueries = nullptr;
   {
-    void* dq = nullptr;
-    if (cudaHostGetDevicePointer(&dq, const_cast<fhp_query*>(queries), 0) == cudaSuccess) {
+    void* dq = mapped_device_ptr(queries);
+    if (dq) {
       dQueries = static_cast<const fhp_query*>(dq);
     } else {
-      cudaGetLastError();
       CU(ctx->dQ.reserve(sizeof(fhp_query) * n_queries));
       CU(cudaMemcpyAsync(ctx->dQ.p, queries, sizeof(fhp_query) * n_queries, cudaMemcpyHostToDevice, s));
       dQueries = static_cast<const fhp_query*>(ctx->dQ.p);
