@@ -139,7 +139,10 @@ typedef struct fhp_ctx fhp_ctx;
 int fhp_create(int device, fhp_ctx** out);
 void fhp_destroy(fhp_ctx* ctx);
 const char* fhp_last_error(const fhp_ctx* ctx); /* ctx may be NULL: message of the last failed fhp_create */
-/* Fills `p` with foothold_planner/config/foothold_planner.yaml:17-44 (trot, RF_FIRST false). */
+/* Fills `p` with foothold_planner/config/foothold_planner.yaml:17-44 (trot, RF_FIRST false).
+ * NOTE spiral_mode = FHP_SPIRAL_WRAP_CORRECT: identical to the reference while the map's start index is (0,0); on a map
+ * whose circular buffer has moved the REFERENCE's footholds need FHP_SPIRAL_FAITHFUL (upstream's SpiralIterator ignores
+ * the start index).  The reference-shaped host classes (FootholdPlannerGpu.hpp, planner.FootholdPlanner) set FAITHFUL. */
 void fhp_default_params(fhp_params* p);
 const char* fhp_version(void);
 
@@ -153,7 +156,9 @@ int fhp_set_map(fhp_ctx* ctx, const fhp_map_desc* desc, const float* const* laye
  * grid_map_ros 1.6.x fromMessage / multiArrayMessageCopyToMatrixEigen / GridMap::setGeometry:
  *   size = (int)round(length / resolution) per axis, length := size * resolution, position = info.pose.position.xy,
  *   layers.size() must equal data.size(), every data[i] must be column-major (layout.dim[0].label == "column_index",
- *   dim[0].size = cols, dim[1].label == "row_index", dim[1].size = rows), start index = (outer, inner)_start_index.
+ *   dim[0].size = cols, dim[1].size = rows; a "row_index" dim[0] is refused like upstream refuses it; any OTHER label is
+ *   read as column-major, as upstream's isRowMajor() does after logging — the call returns FHP_OK and fhp_last_error
+ *   holds upstream's log text), start index = (outer, inner)_start_index.
  * The float arrays are read IN PLACE (no Eigen copy) and streamed to the device through pinned staging buffers.
  * Unlike the reference (which ignores fromMessage's return value and keeps a half-updated map), a malformed message
  * returns FHP_ERR_INVALID_ARG with upstream's error text and leaves the previous map in place.

@@ -195,6 +195,10 @@ class FootholdPlannerGpu {
   explicit FootholdPlannerGpu(int device = 0)
       : abortLikeReference(true), optSubmapWouldFail_(false), ajustedPoseY_(0.0), ctx_(NULL) {
     fhp_default_params(&params);
+    // This class stands in for the reference class: bug-compatible grid_map::SpiralIterator (it ignores the map's
+    // circular-buffer start index) so that a moving robot-centric map gives the reference's footholds.
+    // Batch callers that want the repaired iterator set params.spiral_mode = FHP_SPIRAL_WRAP_CORRECT.
+    params.spiral_mode = FHP_SPIRAL_FAITHFUL;
     initialPose_[0] = initialPose_[1] = initialPose_[2] = 0.0;
     if (fhp_create(device, &ctx_) != FHP_OK) throw std::runtime_error(std::string("fhp_create: ") + fhp_last_error(NULL));
   }

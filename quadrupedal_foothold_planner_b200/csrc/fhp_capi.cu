@@ -788,6 +788,7 @@ int fhp_set_map_msg(fhp_ctx* ctx, const fhp_gridmap_msg* m) {
   std::vector<std::string> names;
   std::vector<const void*> ptrs;
   const std::string colLabel = "column_index", rowLabel = "row_index";
+  bool labelWarning = false;
   for (int i = 0; i < m->n_layers; ++i) {
     const fhp_multiarray& a = m->data[i];
     if (!m->layers[i].p && m->layers[i].n) return fail(ctx, FHP_ERR_INVALID_ARG, "null layer name");
@@ -797,7 +798,9 @@ int fhp_set_map_msg(fhp_ctx* ctx, const fhp_gridmap_msg* m) {
     if (l0 == rowLabel)  // isRowMajor(m) != EigenType::IsRowMajor
       return fail(ctx, FHP_ERR_INVALID_ARG,
                   "multiArrayMessageToMatrixEigen() failed because the storage order is not compatible.");
-    if (l0 != colLabel) return fail(ctx, FHP_ERR_INVALID_ARG, "isRowMajor() failed because layout label is not set correctly.");
+    // any other label: upstream's isRowMajor() logs "isRowMajor() failed because layout label is not set correctly." and
+    // answers false, i.e. the array is then read as column-major like a correctly labelled one — so it is here
+    if (l0 != colLabel) labelWarning = true;
     // getCols = dim[0].size, getRows = dim[1].size; GridMap::add asserts the size equals the geometry's
     if (static_cast<int64_t>(a.dim1_size) != d.rows || static_cast<int64_t>(a.dim0_size) != d.cols ||
         a.n != static_cast<uint64_t>(d.rows) * static_cast<uint64_t>(d.cols) || !a.data)
@@ -808,7 +811,10 @@ int fhp_set_map_msg(fhp_ctx* ctx, const fhp_gridmap_msg* m) {
   }
   if (d.start_row >= d.rows || d.start_col >= d.cols)
     return fail(ctx, FHP_ERR_INVALID_ARG, "grid map message: start index outside the map");
-  return ingest_host(ctx, d, names, ptrs);
+  const int rc = ingest_host(ctx, d, names, ptrs);
+  if (rc == FHP_OK && labelWarning)  // not an error (FHP_OK): the text upstream logs, for hosts that want to log it too
+    ctx->err = "isRowMajor() failed because layout label is not set correctly.";
+  return rc;
 }
 
 namespace {

@@ -439,7 +439,8 @@ class FootholdPlanner:
     globalFootholdPlan is the `plan_global_footholds` service body (FP.cpp:539)."""
 
     def __init__(self, params: Optional[Params] = None, initial_position=(0.0, 0.0, 0.0), device: int = 0):
-        self.params = params if params is not None else yaml_params()
+        # like the reference class: bug-compatible SpiralIterator (it ignores the map's start index, SURVEY App. C.3)
+        self.params = params if params is not None else yaml_params(spiral_mode=_abi.FHP_SPIRAL_FAITHFUL)
         self.initialPose_ = tuple(float(v) for v in initial_position)
         self.fhp = Fhp(device)
         self.nominalGlobalFootholdsMsg_ = GlobalFootholds()

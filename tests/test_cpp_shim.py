@@ -41,12 +41,12 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle, ros_mode):
     for pose, extra in (([-2.5, 0.3, 0.0], []), ([-1.0, -1.2, 0.125], ["msg"])):  # second run: message callback
         out = subprocess.check_output([exe, path, "400", "300", "0.02", "31", "250", repr(pose[0]), repr(pose[1]),
                                        repr(pose[2]), "9"] + extra, text=True).strip().splitlines()
-        nom, _, st = oracle.plan(m, _abi.yaml_params(), _abi.make_queries([pose]), 9)
+        p0 = _abi.yaml_params(spiral_mode=_abi.FHP_SPIRAL_FAITHFUL)  # the shim is the reference class: upstream's spiral
+        nom, _, st = oracle.plan(m, p0, _abi.make_queries([pose]), 9)
         s, gc, gs, n = (int(v) for v in out[0].split())
         assert (s, gc, gs, n) == (st[0]["success"], 9, st[0]["gait_cycles_succeed"], st[0]["n_rows"])
         mem = out[1 + n].split()
         assert mem[0] == "members"
-        p0 = _abi.yaml_params()
         o_init, _, o_first = oracle.initial_geometry(p0, pose)
         cur = np.concatenate([o_first, np.full((4, 1), pose[2])], axis=1)
         oc, onxt, opoly = oracle.search_geometry(p0, pose, -0.007, cur)
@@ -60,7 +60,7 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle, ros_mode):
             assert abs(float(x) - row["x"]) <= 1e-5 and abs(float(y) - row["y"]) <= 1e-5 and abs(float(z) - row["z"]) <= 1e-5
             assert (int(foot), int(cyc)) == (row["foot_id"], row["gait_cycle_id"])
         # marker payloads (FP.cpp:2731-2790): per chain and foot, the points of that foot's planned rows in cycle order
-        enom, ecen, edfl, _, est = oracle.plan_ex(m, _abi.yaml_params(), _abi.make_queries([pose]), 9)
+        enom, ecen, edfl, _, est = oracle.plan_ex(m, p0, _abi.make_queries([pose]), 9)
         for chain, rows in enumerate((enom, ecen, edfl)):
             tok = out[2 + n + chain].split()
             assert tok[0] == "markers" and int(tok[1]) == chain

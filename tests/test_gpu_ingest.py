@@ -58,6 +58,40 @@ def test_periodic_updates_reuse_buffers(fhp, oracle):
     assert len(ptrs) == 1
 
 
+def test_hand_assembled_wire_bytes_reach_the_device(fhp, oracle):
+    """The wire KAT assembled field by field in tests/test_gridmap_msg.py (no shared code with the serialiser): after
+    fhp_set_map_wire the device holds exactly that map — geometry, start index, layer order by NAME, NaN cell."""
+    from tests.test_gridmap_msg import _hand_assembled_wire
+    wire, exp = _hand_assembled_wire()
+    fhp.set_map_wire(wire)
+    d = fhp.map_info()
+    assert (d.rows, d.cols, d.start_row, d.start_col, d.n_layers) == (3, 2, 2, 1, 2)
+    assert (d.resolution, d.length_x, d.length_y, d.pos_x, d.pos_y) == (0.25, 0.75, 0.5, -1.5, 2.25)
+    p = _abi.yaml_params(foot_radius=0.05, search_radius=0.3)
+    pts = np.array([oracle.get_position(exp, r, c)[1] for r in range(3) for c in range(2)])
+    assert np.array_equal(fhp.mean_height(p, pts), oracle.mean_height(exp, p, pts))
+    assert set(np.round(fhp.mean_height(p, pts) - 0.01, 4).tolist()) == {10.0, 11.0, 12.0, 13.0, 14.0, 15.0}
+    assert np.array_equal(fhp.check_default(p, pts), oracle.check_default(exp, p, pts))
+    assert np.array_equal(fhp.check_default(_abi.yaml_params(foot_radius=0.05, search_radius=0.3, thr_default=0.65), pts),
+                          oracle.check_default(exp, _abi.yaml_params(foot_radius=0.05, search_radius=0.3, thr_default=0.65), pts))
+
+
+def test_unknown_layout_label_is_read_as_column_major_like_upstream(fhp):
+    """grid_map_ros's isRowMajor() logs an error for a label that is neither "column_index" nor "row_index" and answers
+    false: the array is then copied as column-major.  Same here (FHP_OK; the log text is left in fhp_last_error)."""
+    m = synth.rough_map(120, 90, 0.02, seed=5, start=(3, 4))
+    q = synth.uniform_queries(16, (-0.5, 0.0), (-0.4, 0.4), seed=1)
+    p = _abi.yaml_params()
+    fhp.set_map(m)
+    ref = fhp.plan(p, q, 3, centroid=True)
+    msg = GridMapMessage.from_host_map(m)
+    msg.data[1].dim[0].label = "cols"
+    fhp.set_map(synth.flat_map(64, 64, 0.02))
+    fhp.set_map_wire(msg.serialize())
+    assert b"layout label is not set correctly" in fhp.L.fhp_last_error(fhp.h)
+    _same(fhp.plan(p, q, 3, centroid=True), ref)
+
+
 def test_rejected_messages_keep_the_previous_map(fhp):
     p = _abi.yaml_params()
     good = synth.rough_map(200, 180, 0.02, seed=61, start=(7, 11))
@@ -75,9 +109,6 @@ def test_rejected_messages_keep_the_previous_map(fhp):
     msg = GridMapMessage.from_host_map(other)
     msg.data[0].dim[0].label, msg.data[0].dim[1].label = ROW_LABEL, COLUMN_LABEL  # row-major announcement
     rejected(msg.serialize(), "storage order is not compatible")
-    msg = GridMapMessage.from_host_map(other)
-    msg.data[1].dim[0].label = "cols"
-    rejected(msg.serialize(), "layout label is not set correctly")
     msg = GridMapMessage.from_host_map(other)
     msg.layers.append("extra")
     rejected(msg.serialize(), "Different number of layers and data")

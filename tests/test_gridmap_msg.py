@@ -48,6 +48,60 @@ def test_known_answer_bytes():
     assert back.data[0].data.tolist() == [1.0, 2.0] and (back.outer_start_index, back.inner_start_index) == (1, 0)
 
 
+def _hand_assembled_wire():
+    """A second known answer, assembled HERE field by field from the message definitions with struct.pack — it shares no
+    code with gridmap_msg.py's serialiser.  3x2 map, two layers in the order (elevation, traversability), empty
+    frame_id, basic_layers != layers, non-zero strides / data_offset / start indices.
+      std_msgs/Header            uint32 seq, time stamp (uint32 secs, uint32 nsecs), string frame_id
+      grid_map_msgs/GridMapInfo  Header header, float64 resolution, float64 length_x, float64 length_y, geometry_msgs/Pose pose
+      geometry_msgs/Pose         Point position (3 x float64), Quaternion orientation (4 x float64)
+      grid_map_msgs/GridMap      GridMapInfo info, string[] layers, string[] basic_layers,
+                                 std_msgs/Float32MultiArray[] data, uint16 outer_start_index, uint16 inner_start_index
+      std_msgs/Float32MultiArray MultiArrayLayout layout {MultiArrayDimension[] dim {string label, uint32 size,
+                                 uint32 stride}, uint32 data_offset}, float32[] data
+    ROS1 wire rules: little-endian, fields in definition order, uint32 length before strings and variable arrays."""
+    import struct
+
+    def string(t):
+        b = t.encode()
+        return struct.pack("<I", len(b)) + b
+
+    rows, cols, res = 3, 2, 0.25
+    elev = np.array([[10.0, 13.0], [11.0, 14.0], [12.0, 15.0]], np.float32)   # (row, col); column-major on the wire
+    trav = np.array([[0.5, 0.8], [0.6, np.nan], [0.7, 1.0]], np.float32)
+    w = struct.pack("<III", 42, 1600000000, 123456789) + string("")            # header
+    w += struct.pack("<ddd", res, rows * res, cols * res)                      # resolution, length_x, length_y
+    w += struct.pack("<ddd", -1.5, 2.25, 9.0) + struct.pack("<dddd", 0.0, 0.0, 0.0, 1.0)  # pose
+    w += struct.pack("<I", 2) + string("elevation") + string("traversability")  # layers
+    w += struct.pack("<I", 1) + string("elevation")                              # basic_layers
+    w += struct.pack("<I", 2)                                                    # data[]
+    for layer in (elev, trav):
+        w += struct.pack("<I", 2)                                                # layout.dim[]
+        w += string("column_index") + struct.pack("<II", cols, rows * cols)
+        w += string("row_index") + struct.pack("<II", rows, rows)
+        w += struct.pack("<I", 0)                                                # data_offset
+        flat = [float(layer[r, c]) for c in range(cols) for r in range(rows)]    # Eigen column-major: rows contiguous
+        w += struct.pack("<I", len(flat)) + struct.pack("<%df" % len(flat), *flat)
+    w += struct.pack("<HH", 2, 1)                                                # outer / inner start index
+    expect = _abi.HostMap(rows, cols, res, pos=(-1.5, 2.25), start=(2, 1), layers={"elevation": elev, "traversability": trav})
+    return w, expect
+
+
+def test_hand_assembled_wire_is_parsed_field_by_field():
+    wire, exp = _hand_assembled_wire()
+    msg = GridMapMessage.deserialize(wire)
+    assert (msg.seq, msg.stamp, msg.frame_id) == (42, (1600000000, 123456789), "")
+    assert (msg.resolution, msg.length_x, msg.length_y) == (0.25, 0.75, 0.5)
+    assert msg.position == (-1.5, 2.25, 9.0) and msg.orientation == (0.0, 0.0, 0.0, 1.0)
+    assert msg.layers == ["elevation", "traversability"] and msg.basic_layers == ["elevation"]
+    assert (msg.outer_start_index, msg.inner_start_index) == (2, 1)
+    got = msg.to_host_map()
+    assert (got.rows, got.cols, got.start, got.pos, got.resolution) == (3, 2, (2, 1), (-1.5, 2.25), 0.25)
+    for k in ("elevation", "traversability"):
+        assert np.array_equal(got.layers[k].view(np.uint32), exp.layers[k].view(np.uint32))
+    assert msg.serialize() == wire  # and the serialiser reproduces the hand-assembled bytes exactly
+
+
 def test_round_trip_keeps_every_bit():
     m = synth.rough_map(37, 53, 0.02, seed=9, start=(5, 50))
     wire = serialize_gridmap(m, frame_id="odom")
