@@ -523,6 +523,16 @@ def main():
     e2e_s = time_host_calls(step_e2e, e2e_steps)
     e2e_compact_s = time_host_calls(step_e2e_compact, e2e_steps)
     e2e_fixed_s = time_host_calls(step_e2e_fixed, e2e_steps) if world == 1 else None
+    e2e_pageable_s = None
+    if world == 1:  # a ROS node's std::vector is PAGEABLE memory: the same compact call on plain numpy buffers
+        p_q = wl["queries"].copy()
+        p_rows = np.empty(max(1, nq) * R, dtype=_abi.FOOTHOLD24_DTYPE)
+        p_offs = np.empty(nq + 1, dtype=np.int64)
+        p_st = np.empty(max(1, nq), dtype=_abi.STATUS_DTYPE)
+        e2e_pageable_s = time_host_calls(
+            lambda: fhp.plan_compact_raw(res.parr, res.npar, p_q, nq, cycles, p_rows, nq * R, p_offs, p_st, fmt=24),
+            max(3, e2e_steps // 2))
+        del p_q, p_rows, p_offs, p_st
     clocks = sampler.stop()
     st = res.status()
     rows_local = float(st["n_rows"].sum())
@@ -600,6 +610,10 @@ def main():
         line["e2e"]["compact24"] = {"value": total_fh / e2e_compact_s, "ms_per_step": e2e_compact_s * 1e3,
                                     "call": "fhp_plan_compact24 (rows back to back + offsets; chunked plan/scan/pack kernels, "
                                             "copy-engine D2H)"}
+        if e2e_pageable_s:
+            line["e2e"]["pageable"] = {"value": total_fh / e2e_pageable_s, "ms_per_step": e2e_pageable_s * 1e3,
+                                       "call": "fhp_plan_compact24 on PAGEABLE host buffers (what a ROS node's std::vector "
+                                               "is): the driver stages every copy through its own bounce buffers"}
         if e2e_fixed_s:
             line["e2e"]["fixed_pitch"] = {"value": total_fh / e2e_fixed_s, "d2h_bytes_per_step": int(nq * R * 40 + nq * 8),
                                           "call": "fhp_plan (every 40-byte row slot returned)"}
