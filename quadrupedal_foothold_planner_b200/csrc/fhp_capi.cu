@@ -1012,9 +1012,13 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.q = d_queries;
   A.nq = n_queries;
   A.cycles = gait_cycles;
-  {  // queries per warp: the smallest power of two that still fits the batch into one resident wave of warps
+  {  // queries per warp.  Every warp pays the same instruction stream per gait cycle whatever the number of its busy quads,
+    // but a GPU with few resident warps runs each of them faster.  Measured on C3 shards of 1,024 ... 32,768 queries
+    // (profiles/r2_experiments.md): fastest is the smallest power of two that keeps the launch at or below HALF a
+    // resident wave of warps (2,072 on a B200) — fewer queries per warp only pay while warps are what is scarce.
     const long long waveWarps = std::max<long long>(1, wave_queries(ctx, d_outC != nullptr) / 8);
-    const long long need = (n_queries + waveWarps - 1) / waveWarps;
+    const long long limit = std::max<long long>(1, waveWarps / 2);
+    const long long need = (n_queries + limit - 1) / limit;
     A.qpwShift = need <= 1 ? 0 : (need <= 2 ? 1 : (need <= 4 ? 2 : 3));
     if (ctx->qpwShiftForce >= 0) A.qpwShift = ctx->qpwShiftForce;
     if (so) A.qpwShift = 3;  // the streamed buffer format groups 8 queries per block
