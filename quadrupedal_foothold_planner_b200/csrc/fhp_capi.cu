@@ -519,6 +519,13 @@ int build_geo(fhp_ctx* ctx, float footRadius, float searchRadius, bool allowTrim
   G.stageMode = stage == kStageTma ? (G.useTma ? kStageTma : kStageLdg) : stage;
   G.winRows = G.useTma ? std::min(32 / G.pack, G.WIN + 3) : G.WIN;
   G.smemWords = G.useTma ? G.boxOff + warps * 2 * G.tmaB * G.boxWords : planesEnd;
+  // foot discs of more than four cells (footRadius > resolution): their elevation cells are fetched into shared memory by
+  // cp.async while the window is staged (plan_kernel) — 16 words per lane
+  G.elevOff = -1;
+  if (G.discK != 1) {
+    G.elevOff = (G.smemWords + 3) & ~3;
+    G.smemWords = G.elevOff + warps * 32 * 16;
+  }
   ctx->geoStage = stage;
   ctx->geoFoot = footRadius;
   ctx->geoSearch = searchRadius;

@@ -63,7 +63,7 @@ struct GeoV {
   __device__ __forceinline__ int rpShift() const { if constexpr (K::fixed) return 5; else return g.rpShift; }
 #define FHP_GEO_R(name) __device__ __forceinline__ int name() const { return g.name; }
   FHP_GEO_R(spiralWords) FHP_GEO_R(smemWords) FHP_GEO_R(stageMode) FHP_GEO_R(useTma) FHP_GEO_R(tmaB) FHP_GEO_R(tmaBShift)
-  FHP_GEO_R(boxWords) FHP_GEO_R(mbarOff) FHP_GEO_R(boxOff)
+  FHP_GEO_R(boxWords) FHP_GEO_R(mbarOff) FHP_GEO_R(boxOff) FHP_GEO_R(elevOff)
 #undef FHP_GEO_R
 };
 
@@ -786,6 +786,41 @@ __device__ __forceinline__ float mean_height_loaded(const MapDev& M, const ParDe
   if (n > 1) height_value(v.e1, iHeight, meanHeight, i);
   if (n > 2) height_value(v.e2, iHeight, meanHeight, i);
   if (n > 3) height_value(v.e3, iHeight, meanHeight, i);
+  if (i != 0) {
+    meanHeight = meanHeight / static_cast<float>(i);
+  } else {
+    meanHeight = iHeight;
+  }
+  return static_cast<float>(static_cast<double>(meanHeight) + P.h);
+}
+// Foot discs of more than four cells: the member cells' elevations travel global -> shared memory by cp.async (no
+// destination registers, so all of them are in flight at once and stay in flight while the window is staged); slot k of
+// a lane is word (k * 32 + lane) of the warp's block.  disc_elev_fetch issues them, disc_elev_mean waits and accumulates
+// in the iterator's order.  Discs with more than 16 members (or on the generic walk) take mean_height.
+__device__ __forceinline__ void disc_elev_fetch(const MapDev& M, const DiscWin& dw, uint32_t slot0) {
+  unsigned long long t = dw.small() ? dw.m : 0ull;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (t) {
+      const int bit = __ffsll(static_cast<long long>(t)) - 1;
+      t &= t - 1;
+      const int b0 = wrap_add(dw.tl0 + (bit >> 3), M.start0, M.rows), b1 = wrap_add(dw.tl1 + (bit & 7), M.start1, M.cols);
+      const float* src = M.elev + static_cast<size_t>(b1) * M.rows + b0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(slot0 + static_cast<uint32_t>(k) * 128u), "l"(src) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ float disc_elev_mean(const MapDev& M, const ParDev& P, double cx, double cy, const DiscWin& dw,
+                                                uint32_t slot0) {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  const int n = __popcll(dw.m);
+  if (!dw.small() || n > 16) return mean_height(M, P, cx, cy, dw);
+  float iHeight = 0.0f, meanHeight = 0.0f;
+  int i = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < n) height_value(lds_f32(slot0 + static_cast<uint32_t>(k) * 128u), iHeight, meanHeight, i);
   if (i != 0) {
     meanHeight = meanHeight / static_cast<float>(i);
   } else {

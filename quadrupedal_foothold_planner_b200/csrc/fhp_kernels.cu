@@ -266,7 +266,12 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     // (discs of up to four cells — footRadius <= resolution — are loaded here, in flight during the staging below;
     // larger ones are loaded in one batch where they are summed, mean_height)
     DiscElev de = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (G.discK() == 1) de = load_disc_elev(M, dw);
+    const uint32_t elevSlot = smem_u32(smem + G.elevOff()) + static_cast<uint32_t>(warpInBlock * 512 + lane) * 4u;
+    if (G.discK() == 1) {
+      de = load_disc_elev(M, dw);
+    } else {
+      disc_elev_fetch(M, dw, elevSlot);  // cp.async into shared memory, waited for where the mean is taken
+    }
     // A query that failed keeps its chains (FP.cpp:1571-1576) and only drifts 7 mm sideways per cycle, so its next
     // window is usually the SAME cells: the bit-planes are still in this lane's slot, nothing to stage.
     const bool restage = active && !(w0 == prevW0 && w1 == prevW1);
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     float zCentre = 0.0f;
     if (active) {
       Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 0 : G.pack(), G.rpShift(), G.WIN());
-      zCentre = mean_height_loaded(M, P, px, py, dw, de, G.discK() == 1);                // FP.cpp:2029 (used when the leg is valid)
+      zCentre = G.discK() == 1 ? mean_height_loaded(M, P, px, py, dw, de, true) : disc_elev_mean(M, P, px, py, dw, elevSlot);                // FP.cpp:2029 (used when the leg is valid)
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
       co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
     }

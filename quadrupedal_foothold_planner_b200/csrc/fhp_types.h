@@ -53,6 +53,7 @@ struct GeoDev {  // depends on (foot_radius, search_radius, resolution) only
   int mbarOff;      // word offset of the per-warp mbarrier pairs (from the 128-byte aligned shared base)
   int boxOff;       // word offset of the per-warp box buffers (multiple of 32 words)
   int smemWords;    // total dynamic shared memory words for a kPlanThreads block (without alignment slack)
+  int elevOff;      // word offset of the per-warp elevation staging (16 words per lane, plan_kernel), -1: none (discK == 1)
   int nCand;     // spiral table length
   int lastTwoStart;  // first rank that belongs to ring nRings-1 (distance-filtered rings)
   int nSten;
