@@ -521,6 +521,14 @@ def main():
 
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     e2e_s = time_host_calls(step_e2e, e2e_steps)
+    h_x = torch.empty(max(1, nq) * R * _abi.FOOTHOLD24_DTYPE.itemsize, dtype=torch.uint8)  # pageable: a consumer's array
+
+    def step_e2e_expanded():  # streamed response + the host-side expander into service-shaped 24-byte rows
+        step_e2e()
+        fhp._check(fhp.L.fhp_stream_expand(h_blocks.data_ptr(), h_mask.data_ptr(), h_st.data_ptr(), nq, cycles, h_x.data_ptr(),
+                                           nq * R, h_offs.data_ptr(), 0))
+
+    e2e_expanded_s = time_host_calls(step_e2e_expanded, e2e_steps)
     e2e_compact_s = time_host_calls(step_e2e_compact, e2e_steps)
     e2e_fixed_s = time_host_calls(step_e2e_fixed, e2e_steps) if world == 1 else None
     e2e_pageable_s = None
@@ -607,6 +615,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof,
         }
+        line["e2e"]["stream_plus_expander"] = {"value": total_fh / e2e_expanded_s, "ms_per_step": e2e_expanded_s * 1e3,
+                                               "call": "fhp_plan_stream, then fhp_stream_expand (host threads) into the "
+                                                       "service-shaped 24-byte rows + offsets of fhp_plan_compact24; the "
+                                                       "streamed blocks themselves need no expansion to be read (fhp_stream_row)"}
         line["e2e"]["compact24"] = {"value": total_fh / e2e_compact_s, "ms_per_step": e2e_compact_s * 1e3,
                                     "call": "fhp_plan_compact24 (rows back to back + offsets; chunked plan/scan/pack kernels, "
                                             "copy-engine D2H)"}
@@ -621,7 +633,7 @@ def main():
             line["weak_scaling"] = weak
     if res is not None:
         res.close()
-    del h_q, h_blocks, h_rows, h_st, h_offs, h_mask
+    del h_q, h_blocks, h_rows, h_st, h_offs, h_mask, h_x
 
     # ---- the other BASELINE configs, a few steps each
     if others:

@@ -301,6 +301,13 @@ int fhp_plan_stream(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, co
  * failed: rank = the successful queries before q in its group of 8.  Pure host-side function. */
 const fhp_point20* fhp_stream_row(const fhp_point20* blocks, const fhp_stream_mask* masks, int64_t n_queries,
                                   int32_t gait_cycles, int64_t q, int32_t g, int32_t f);
+/* Host-side expander of a streamed response into the service-shaped compact response of fhp_plan_compact24: query q owns
+ * out_rows[row_offsets[q] .. row_offsets[q+1]) = its 4 stance rows + 4 per successful cycle, with foot_id, gait_cycle_id
+ * and kind filled in.  Pure host function (n_threads <= 0: one per hardware thread, at most 16); for consumers that want
+ * rows rather than fhp_stream_row lookups.  capacity_rows as in fhp_plan_compact. */
+int fhp_stream_expand(const fhp_point20* blocks, const fhp_stream_mask* masks, const fhp_query_status* status,
+                      int64_t n_queries, int32_t gait_cycles, fhp_foothold24* out_rows, int64_t capacity_rows,
+                      int64_t* row_offsets, int32_t n_threads);
 /* KPIs the reference logs per successful cycle (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623): pure
  * host-side functions of ONE query's response rows (nominal or centroid chain).  feet_distance / cog_speed receive
  * 2 values per successful cycle (n_rows/4 - 1 cycles). */

@@ -1382,6 +1382,61 @@ const fhp_point20* fhp_stream_row(const fhp_point20* blocks, const fhp_stream_ma
   return blocks + ((static_cast<int64_t>(g + 1) * groups + G) * 32 + rank * 4 + f);
 }
 
+int fhp_stream_expand(const fhp_point20* blocks, const fhp_stream_mask* masks, const fhp_query_status* status,
+                      int64_t n_queries, int32_t gait_cycles, fhp_foothold24* out_rows, int64_t capacity_rows,
+                      int64_t* row_offsets, int32_t n_threads) {
+  if (n_queries < 0 || gait_cycles < 0 || gait_cycles > 255 || !row_offsets ||
+      (n_queries > 0 && (!blocks || !status || !out_rows || (gait_cycles > 0 && !masks))))
+    return FHP_ERR_INVALID_ARG;
+  row_offsets[0] = 0;
+  for (int64_t q = 0; q < n_queries; ++q) row_offsets[q + 1] = row_offsets[q] + status[q].n_rows;  // 4 + 4 per success
+  if (row_offsets[n_queries] > capacity_rows) return FHP_ERR_INVALID_ARG;
+  const int64_t groups = (n_queries + 7) / 8;
+  const int words = FHP_STREAM_MASK_WORDS(gait_cycles);
+  int nt = n_threads > 0 ? n_threads : static_cast<int>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())));
+  nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, groups / 64)));
+  auto work = [&](int64_t g0, int64_t g1) {
+    for (int64_t G = g0; G < g1; ++G) {
+      const int64_t q0 = G * 8, q1 = std::min<int64_t>(n_queries, q0 + 8);
+      for (int64_t q = q0; q < q1; ++q) {  // stance rows: block (0, G), query order
+        fhp_foothold24* o = out_rows + row_offsets[q];
+        const fhp_point20* b = blocks + (G * 32 + (q - q0) * 4);
+        for (int f = 0; f < 4; ++f) {
+          o[f].x = b[f].x;  o[f].y = b[f].y;  o[f].z = b[f].z;
+          o[f].foot_id = static_cast<uint8_t>(f);  o[f].gait_cycle_id = 0;  o[f].kind = FHP_KIND_STANCE;  o[f].reserved = 0;
+        }
+      }
+      int64_t cursor[8];
+      for (int64_t q = q0; q < q1; ++q) cursor[q - q0] = row_offsets[q] + 4;
+      for (int g = 0; g < gait_cycles; ++g) {  // cycle blocks: the group's successful queries packed to the front
+        const uint32_t bit = 1u << (g & 31);
+        const fhp_point20* b = blocks + ((static_cast<int64_t>(g) + 1) * groups + G) * 32;
+        for (int64_t q = q0; q < q1; ++q) {
+          const fhp_stream_mask* m = masks + (q * words + (g >> 5)) * 4;
+          if (!(m[0].success & bit)) continue;
+          fhp_foothold24* o = out_rows + cursor[q - q0];
+          for (int f = 0; f < 4; ++f) {
+            o[f].x = b[f].x;  o[f].y = b[f].y;  o[f].z = b[f].z;
+            o[f].foot_id = static_cast<uint8_t>(f);  o[f].gait_cycle_id = static_cast<uint8_t>(g);
+            o[f].kind = (m[f].candidate & bit) ? FHP_KIND_CANDIDATE : FHP_KIND_DEFAULT;  o[f].reserved = 0;
+          }
+          cursor[q - q0] += 4;
+          b += 4;
+        }
+      }
+    }
+  };
+  if (nt <= 1) {
+    work(0, groups);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (groups + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, std::min<int64_t>(groups, t * per), std::min<int64_t>(groups, (t + 1) * per));
+    for (std::thread& t : th) t.join();
+  }
+  return FHP_OK;
+}
+
 // KPIs of the reference's logs (getHipDistance FP.cpp:2571-2584, getCogSpeed :2587-2623, gaitCycle_ = 1.0 :332) —
 // pure functions of one query's response rows, computed on the host like the message assembly.
 int fhp_cycle_kpi(const fhp_params* params, const fhp_query* query, const fhp_foothold* rows, int32_t n_rows,

@@ -74,6 +74,7 @@ def load_lib():
     L.fhp_plan_compact_packed.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
     L.fhp_plan_compact24.argtypes = [vp, vp, i32, vp, i64, i32, vp, i64, vp, vp]
     L.fhp_plan_stream.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp]
+    L.fhp_stream_expand.argtypes = [vp, vp, vp, i64, i32, vp, i64, vp, i32]
     L.fhp_plan_device.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, vp, vp]
     L.fhp_synchronize.argtypes = [vp]
     L.fhp_check_foothold.argtypes = [vp, vp, vp, vp, i64, vp, vp]
@@ -264,6 +265,17 @@ class Fhp:
         self._stream_keep = raw
         return (blocks.numpy().view(_abi.POINT20_DTYPE).reshape(cycles + 1, groups, 32),
                 mask.numpy().view(_abi.STREAM_MASK_DTYPE).reshape(max(nq, 1), words, 4)[:nq], st.numpy().view(STATUS_DTYPE)[:nq])
+
+    def stream_expand(self, blocks, masks, status, gait_cycles: int, n_threads: int = 0):
+        """fhp_stream_expand: streamed blocks -> (rows [total] of FOOTHOLD24_DTYPE, row_offsets [nq+1])."""
+        nq = len(status)
+        rows = np.zeros(max(1, int(status["n_rows"].sum())), dtype=_abi.FOOTHOLD24_DTYPE)
+        offs = np.zeros(nq + 1, dtype=np.int64)
+        b = np.ascontiguousarray(blocks)
+        m = np.ascontiguousarray(masks)
+        self._check(self.L.fhp_stream_expand(_ptr(b), _ptr(m), _ptr(np.ascontiguousarray(status)), nq, int(gait_cycles), _ptr(rows),
+                                             len(rows), _ptr(offs), int(n_threads)))
+        return rows[: offs[nq]], offs
 
     @staticmethod
     def stream_rows_of(blocks, masks, q: int):

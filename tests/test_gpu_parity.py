@@ -397,6 +397,10 @@ def test_streamed_response_equals_plan_rows(fhp):
             assert np.array_equal(pts["z"].astype(np.float64), rows["z"])
             assert np.array_equal(foot, rows["foot_id"]) and np.array_equal(cyc, rows["gait_cycle_id"])
             assert np.array_equal(kind[4:], rows["kind"][4:])
+        # the host-side expander turns the blocks into exactly fhp_plan_compact24's response
+        xr, xo = fhp.stream_expand(blocks, masks, st2, cycles)
+        cr, co, _ = fhp.plan_compact(p, q, cycles, fmt=24)
+        assert np.array_equal(xo, co) and xr.tobytes() == cr.tobytes()
         # whole batch: the four feet agree on success, popcount == successful cycles, unwritten row slots are still zero
         succ = masks["success"]
         assert np.all(succ == succ[:, :, :1])
