@@ -214,9 +214,11 @@ int fhp_map_changed(fhp_ctx* ctx);
  *   out_centroid : NULL, or the same shape: the centroid chain rows (topic global_footholds_centroid,
  *                  FP.cpp:1448-1462) including their z.
  *   status       : n_queries entries.
- * All parameter sets of one call must share foot_radius and search_radius.  FHP_ERR_UNSUPPORTED when
- * search_radius/resolution or foot_radius/resolution exceed the kernel's window tables, or when a foot-disc
- * stencil offset lies within rounding distance of the disc boundary (see DESIGN.md "stencil classification"). */
+ * Parameter sets that differ in foot_radius / search_radius are planned in one launch per radii pair (fhp_plan /
+ * fhp_plan_ex only; the device-resident, compact and streamed calls take ONE radii pair per call and return
+ * FHP_ERR_INVALID_ARG otherwise).  FHP_ERR_UNSUPPORTED when search_radius/resolution or foot_radius/resolution exceed
+ * the kernel's window tables (windows wider than 32 cells, more than 15 spiral rings), or when a foot-disc stencil
+ * offset lies within rounding distance of the disc boundary (see DESIGN.md "Refused rather than guessed"). */
 int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
              int32_t gait_cycles, fhp_foothold* out_nominal, fhp_foothold* out_centroid, fhp_query_status* status);
 /* Extended outputs of the same plan.  default_chain: the reference's "default" chain rows —

@@ -1068,8 +1068,75 @@ int fhp_plan(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp
   return fhp_plan_ex(ctx, params, n_params, queries, n_queries, gait_cycles, &out);
 }
 
+static int plan_ex_one_geometry(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                                int64_t n_queries, int32_t gait_cycles, const fhp_plan_outputs* outp);
+
+// One call = one window geometry on the device (the tables depend on footRadius, searchRadius and the resolution).
+// Parameter sets that differ in their radii are therefore planned group by group: the queries of each (footRadius,
+// searchRadius) pair are gathered, planned in their own launch and their rows scattered back — the reference takes the
+// radii per call as well.  (Host buffers only; the device-resident, compact and streamed entry points ask for one
+// geometry per call.)
 int fhp_plan_ex(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries, int64_t n_queries,
                 int32_t gait_cycles, const fhp_plan_outputs* outp) {
+  if (!ctx) return FHP_ERR_INVALID_ARG;
+  bool mixed = false;
+  if (params && n_params > 1)
+    for (int i = 1; i < n_params; ++i)
+      mixed = mixed || params[i].foot_radius != params[0].foot_radius || params[i].search_radius != params[0].search_radius;
+  if (!mixed) return plan_ex_one_geometry(ctx, params, n_params, queries, n_queries, gait_cycles, outp);
+  if (!outp || !queries || !outp->nominal || !outp->status || n_queries < 0 || gait_cycles < 0 || gait_cycles > 255)
+    return fail(ctx, FHP_ERR_INVALID_ARG, "invalid plan arguments");
+  for (int64_t i = 0; i < n_queries; ++i)
+    if (queries[i].param_id < 0 || queries[i].param_id >= n_params) return fail(ctx, FHP_ERR_INVALID_ARG, "query.param_id out of range");
+  const size_t R = FHP_ROWS_PER_QUERY(gait_cycles);
+  std::vector<int> group(n_params, -1);  // parameter set -> geometry group
+  int nGroups = 0;
+  for (int i = 0; i < n_params; ++i) {
+    for (int j = 0; j < i && group[i] < 0; ++j)
+      if (params[j].foot_radius == params[i].foot_radius && params[j].search_radius == params[i].search_radius) group[i] = group[j];
+    if (group[i] < 0) group[i] = nGroups++;
+  }
+  for (int g = 0; g < nGroups; ++g) {
+    std::vector<fhp_params> gp;
+    std::vector<int> remap(n_params, -1);
+    for (int i = 0; i < n_params; ++i)
+      if (group[i] == g) {
+        remap[i] = static_cast<int>(gp.size());
+        gp.push_back(params[i]);
+      }
+    std::vector<int64_t> idx;
+    std::vector<fhp_query> gq;
+    for (int64_t i = 0; i < n_queries; ++i)
+      if (group[queries[i].param_id] == g) {
+        idx.push_back(i);
+        gq.push_back(queries[i]);
+        gq.back().param_id = remap[queries[i].param_id];
+      }
+    if (gq.empty()) continue;
+    const size_t n = gq.size();
+    std::vector<fhp_foothold> gn(n * R), gc(outp->centroid ? n * R : 0), gd(outp->default_chain ? n * R : 0);
+    std::vector<fhp_query_status> gs(n);
+    fhp_plan_outputs go;
+    go.nominal = gn.data();
+    go.centroid = outp->centroid ? gc.data() : nullptr;
+    go.default_chain = outp->default_chain ? gd.data() : nullptr;
+    go.status = gs.data();
+    const int rc = plan_ex_one_geometry(ctx, gp.data(), static_cast<int32_t>(gp.size()), gq.data(), static_cast<int64_t>(n),
+                                        gait_cycles, &go);
+    if (rc != FHP_OK) return rc;
+    for (size_t k = 0; k < n; ++k) {
+      const int64_t q = idx[k];
+      std::memcpy(outp->nominal + q * R, gn.data() + k * R, sizeof(fhp_foothold) * R);
+      if (outp->centroid) std::memcpy(outp->centroid + q * R, gc.data() + k * R, sizeof(fhp_foothold) * R);
+      if (outp->default_chain) std::memcpy(outp->default_chain + q * R, gd.data() + k * R, sizeof(fhp_foothold) * R);
+      outp->status[q] = gs[k];
+    }
+  }
+  return FHP_OK;
+}
+
+static int plan_ex_one_geometry(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, const fhp_query* queries,
+                                int64_t n_queries, int32_t gait_cycles, const fhp_plan_outputs* outp) {
   if (!ctx) return FHP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!outp) return fail(ctx, FHP_ERR_INVALID_ARG, "null outputs");

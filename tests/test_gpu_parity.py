@@ -350,6 +350,25 @@ def test_compact_response_equals_fixed_pitch_rows(fhp, oracle):
     assert np.array_equal(r24["x"], rb["x"]) and np.array_equal(r24["z"].astype(np.float64), rb["z"])
 
 
+def test_mixed_radii_in_one_call(fhp, oracle):
+    """Parameter sets with different foot / search radii in ONE fhp_plan call: planned per radii pair, rows scattered back
+    in query order — every query equals the oracle's plan with its own parameter set."""
+    m = synth.rough_map(600, 600, 0.02, seed=19, start=(41, 7))
+    params = [_abi.yaml_params(), _abi.yaml_params(search_radius=0.14), _abi.yaml_params(foot_radius=0.031, gait=_abi.FHP_GAIT_WALK),
+              _abi.yaml_params(step_length=0.2)]  # sets 0 and 3 share their radii
+    q = synth.uniform_queries(400, (-4.5, 2.0), (-4.5, 4.5), seed=23)
+    q["param_id"] = (np.arange(400) * 7) % 4
+    exp = oracle.plan(m, params, q, 9)
+    fhp.set_map(m)
+    got = fhp.plan(params, q, 9, centroid=True)
+    assert compare_plans(got, exp, "mixed radii") <= XYZ_TOL
+    nom, cen, dfl, st = fhp.plan_ex(params, q, 9)
+    assert compare_plans((nom, cen, st), exp, "mixed radii, plan_ex") <= XYZ_TOL
+    from quadrupedal_foothold_planner_b200.planner import FhpError
+    with pytest.raises(FhpError, match="share foot_radius"):
+        fhp.plan_compact(params, q, 9)
+
+
 def test_adopted_layer_rewritten_in_place_needs_map_changed(fhp, oracle):
     """fhp_set_map_device adopts caller-owned device buffers.  When the caller rewrites the traversability layer in place
     (e.g. re-broadcasts into the same tensors) it calls fhp_map_changed; the plan after that equals the oracle on the NEW
