@@ -402,12 +402,13 @@ def test_streamed_response_equals_plan_rows(fhp):
     m = synth.rough_map(1200, 1200, 0.02, seed=71, start=(100, 900))
     fhp.set_map(m)
     for nq, cycles, p in ((1, 8, _abi.yaml_params()), (37, 12, _abi.yaml_params(gait=_abi.FHP_GAIT_WALK)),
-                          (3000, 40, _abi.yaml_params()), (70000, 6, _abi.yaml_params(heading=0.7))):
+                          (3000, 40, _abi.yaml_params()), (70000, 6, _abi.yaml_params(heading=0.7)),
+                          (21, 0, _abi.yaml_params()), (50, 255, _abi.yaml_params())):
         q = synth.uniform_queries(nq, (-10.0, 3.0), (-10.0, 10.0), seed=nq)
         nom, _, st = fhp.plan(p, q, cycles)
         blocks, masks, st2 = fhp.plan_stream(p, q, cycles)
         assert np.array_equal(st, st2)
-        assert blocks.shape == (cycles + 1, (nq + 7) // 8, 32) and masks.shape == (nq, (cycles + 31) // 32, 4)
+        assert blocks.shape == (cycles + 1, (nq + 7) // 8, 32) and masks.shape == (nq, max(1, (cycles + 31) // 32), 4)
         for qi in range(0, nq, max(1, nq // 257)):
             rows = nom[qi][: st[qi]["n_rows"]]
             pts, foot, cyc, kind = Fhp.stream_rows_of(blocks, masks, qi)
