@@ -856,30 +856,59 @@ struct CentroidOut {
 };
 // FootholdPlanner::checkFootholdUseCentroidMethod (FP.cpp:1605-1997) on the staged planes of this lane.
 // (w0,w1): unwrapped origin of the staged window.
+// floor and "safely inside its cell" test of a fractional cell coordinate (centroid_eval's fast path)
+__device__ __forceinline__ bool cell_split(double t, int& idx) {
+  idx = __double2int_rd(t);
+  const double fr = t - static_cast<double>(idx);
+  return fr > 1e-6 && fr < 1.0 - 1e-6;
+}
 template <class GV>
 __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GV& G, const ParDev& P, const Planes& pl,
-                                                     int w0, int w1, double px, double py, unsigned& err) {
+                                                     int w0, int w1, int uc0, int uc1, double px, double py, unsigned& err) {
   CentroidOut o;
   o.x = 0.0;
   o.y = 0.0;
   o.ccase = -1;
-  // GridMap::getSubmap -> getSubmapInformation (GridMapMath.cpp)
-  const double tlx = bound_axis(px + 0.5 * P.rectLx, M.lenx, M.posx, M.halfx);
-  const double tly = bound_axis(py + 0.5 * P.rectLy, M.leny, M.posy, M.halfy);
-  if (!(within_axis(tlx, M.lenx, M.posx, M.halfx) && within_axis(tly, M.leny, M.posy, M.halfy))) return o;
-  const int tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res, M.rinv), tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res, M.rinv);
-  const double brx = bound_axis(px - 0.5 * P.rectLx, M.lenx, M.posx, M.halfx);
-  const double bry = bound_axis(py - 0.5 * P.rectLy, M.leny, M.posy, M.halfy);
-  if (!(within_axis(brx, M.lenx, M.posx, M.halfx) && within_axis(bry, M.leny, M.posy, M.halfy))) return o;
-  const int br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv), br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
-  if (!in_map(M, tl0, tl1)) return o;  // getPositionFromIndex(topLeftCorner) range check
+  // GridMap::getSubmap -> getSubmapInformation (GridMapMath.cpp): the cells that contain the two corners p +- 0.5*L.
+  // FAST PATH, the common case: the window lies well inside the map (no clamping, every range check holds, and the
+  // centre is a whole cell away from the submap's edges), so the corner cells follow from the centre's fractional cell
+  // coordinate: t(p +- d) = t(p) -+ d/res up to ~1e-12 cell, and the cell index is its floor whenever that is farther
+  // than 1e-6 from a cell boundary.  Anything else — near the border, a corner within 1e-6 of a boundary (which also
+  // covers the submaps that come out one cell larger) — takes upstream's expressions below.
+  int tl0 = 0, tl1 = 0, br0 = 0, br1 = 0;
+  bool fast = false;
+  {
+    const double hx = (0.5 * P.rectLx) * M.rinv, hy = (0.5 * P.rectLy) * M.rinv;  // half extents in cells
+    if (hx < 30.0 && hy < 30.0) {
+      const int mx = static_cast<int>(hx) + 2, my = static_cast<int>(hy) + 2;
+      if (uc0 >= mx && uc0 < M.rows - mx && uc1 >= my && uc1 < M.cols - my) {
+        const double tcx = -(((px - M.halfx) - M.posx) * M.rinv), tcy = -(((py - M.halfy) - M.posy) * M.rinv);
+        const bool a = cell_split(tcx - hx, tl0), b = cell_split(tcx + hx, br0), c = cell_split(tcy - hy, tl1),
+                   d = cell_split(tcy + hy, br1);
+        fast = a && b && c && d;
+      }
+    }
+  }
+  if (!fast) {
+    const double tlx = bound_axis(px + 0.5 * P.rectLx, M.lenx, M.posx, M.halfx);
+    const double tly = bound_axis(py + 0.5 * P.rectLy, M.leny, M.posy, M.halfy);
+    if (!(within_axis(tlx, M.lenx, M.posx, M.halfx) && within_axis(tly, M.leny, M.posy, M.halfy))) return o;
+    tl0 = raw_index_axis(tlx, M.halfx, M.posx, M.res, M.rinv);
+    tl1 = raw_index_axis(tly, M.halfy, M.posy, M.res, M.rinv);
+    const double brx = bound_axis(px - 0.5 * P.rectLx, M.lenx, M.posx, M.halfx);
+    const double bry = bound_axis(py - 0.5 * P.rectLy, M.leny, M.posy, M.halfy);
+    if (!(within_axis(brx, M.lenx, M.posx, M.halfx) && within_axis(bry, M.leny, M.posy, M.halfy))) return o;
+    br0 = raw_index_axis(brx, M.halfx, M.posx, M.res, M.rinv);
+    br1 = raw_index_axis(bry, M.halfy, M.posy, M.res, M.rinv);
+    if (!in_map(M, tl0, tl1)) return o;  // getPositionFromIndex(topLeftCorner) range check
+  }
   const double cornx = pos_axis(M.fcx, M.res, tl0) + 0.5 * M.res;
   const double corny = pos_axis(M.fcy, M.res, tl1) + 0.5 * M.res;
   const int n0 = br0 - tl0 + 1, n1 = br1 - tl1 + 1;  // submap size (rows, cols)
   const double slx = static_cast<double>(n0) * M.res, sly = static_cast<double>(n1) * M.res;
   const double shx = 0.5 * slx, shy = 0.5 * sly;
   const double spx = cornx - shx, spy = corny - shy;  // submap position
-  if (!(within_axis(px, slx, spx, shx) && within_axis(py, sly, spy, shy))) return o;  // requested centre in submap
+  if (!fast && !(within_axis(px, slx, spx, shx) && within_axis(py, sly, spy, shy))) return o;  // requested centre in submap
 
   if (n0 < 1 || n1 < 1 || n0 > 32) {
     err |= kErrWindow;

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
       Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 0 : G.pack(), G.rpShift(), G.WIN());
       zCentre = G.discK() == 1 ? mean_height_loaded(M, P, px, py, dw, de, true) : disc_elev_mean(M, P, px, py, dw, elevSlot);                // FP.cpp:2029 (used when the leg is valid)
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
-      co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);  // FP.cpp:818-821
+      co = centroid_eval(M, G, P, pl, w0, w1, uc0, uc1, px, py, err);  // FP.cpp:818-821
     }
 #if FHP_SYNC_LEVEL >= 4
     __syncthreads();
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
   }
   if (!active) return;
   if (MODE == 1) {
-    CentroidOut co = centroid_eval(M, G, P, pl, w0, w1, px, py, err);
+    CentroidOut co = centroid_eval(M, G, P, pl, w0, w1, uc0, uc1, px, py, err);
     double z = 0.0;
     if (co.ccase >= 0 && co.ccase <= 3) z = static_cast<double>(mean_height(M, G, P, co.x, co.y));
     int r0, c0;
