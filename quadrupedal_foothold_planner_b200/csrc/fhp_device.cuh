@@ -110,7 +110,14 @@ __device__ __noinline__ double div_rn(double a, double b) { return a / b; }
 // are explicit (the translation unit is built with -fmad=false); operands outside the guard band (where a residual
 // could leave the normal range) take the exact subroutine.  scratch-tested against a/3.0 on 4e8 operands.
 __device__ __forceinline__ double div3_rn(double a) {
-  if (!(fabs(a) > 1e-280 && fabs(a) < 1e280)) return div_rn(a, 3.0);
+  if (!(fabs(a) < 1e280)) {
+    // infinities and NaNs divide to themselves (a degenerate stance polygon — two feet of the centroid chain at (0,0,0) —
+    // has a zero area and a non-finite centroid for the rest of its plan: ~2 % of the lanes on C3); huge finite values
+    // take the exact routine
+    if (!(fabs(a) <= 1.7976931348623157e308)) return a * 0.33333333333333331482961625624739;
+    return div_rn(a, 3.0);
+  }
+  if (!(fabs(a) > 1e-280)) return div_rn(a, 3.0);
   const double y = 0.33333333333333331482961625624739;  // 0x3FD5555555555555
   const double q0 = a * y;
   const double q1 = __fma_rn(__fma_rn(-3.0, q0, a), y, q0);
