@@ -271,7 +271,26 @@ def run_reference(args, rank, world):
     }
     if not args.no_as_written:
         line["as_written_reference"] = as_written_reference(hmap, params, queries[1:], cycles, 1)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries ONE JSON line: anything a library prints there during the run (NCCL's version banner under
+    torchrun, for one) goes to stderr instead; emit() writes the line to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(1 if _REAL_STDOUT is None else _REAL_STDOUT, data)
 
 
 def map_update_timing(ctx, hmap, params):
@@ -331,6 +350,7 @@ def main():
     ap.add_argument("--c4-poses", type=int, default=4096, help="start poses per parameter set of C4 (config: 4096)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)  # profiling runs pass --warmup 1; the driver passes >= 3
 
@@ -704,7 +724,7 @@ def main():
             v, dt = oracle_footholds_per_s(wl["map"], wl["params"], sq, cycles, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{len(sq)} of {nq} queries x {cycles} cycles, {dt:.1f} s, all host threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     if world > 1:
         dist.barrier()
