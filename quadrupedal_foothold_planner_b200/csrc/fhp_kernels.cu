@@ -39,6 +39,34 @@ __device__ FHP_INL_PC void polygon_center(double rfx, double rfy, double rhx, do
   cy = div3_rn(div_rn(sum_y, sum_s));
 }
 
+// The same centroid for BOTH chains of a quad at once: every lane forms the six sums (cheap), then each of the quad's
+// four lanes runs ONE of the four division chains (centroid x / y, nominal x / y) and the quotients are exchanged —
+// one pass through the division subroutine per cycle instead of four.  Same operations on the same operands as
+// polygon_center, so the results are bit-identical.  WARP-COLLECTIVE.
+__device__ __forceinline__ void polygon_sums(double x1, double y1, double x2, double y2, double x3, double y3, double x4,
+                                             double y4, double& sum_x, double& sum_y, double& sum_s) {
+  const double s1 = ((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)) * 0.5;
+  const double s2 = ((x3 - x1) * (y4 - y1) - (x4 - x1) * (y3 - y1)) * 0.5;
+  sum_x = (0.0 + (x1 + x2 + x3) * s1) + (x1 + x3 + x4) * s2;
+  sum_y = (0.0 + (y1 + y2 + y3) * s1) + (y1 + y3 + y4) * s2;
+  sum_s = (0.0 + s1) + s2;
+}
+__device__ __forceinline__ void quad_centres(double cenx, double ceny, double nomx, double nomy, int quad0, int f,
+                                             double& ccx, double& ccy, double& ncx, double& ncy) {
+  double csx, csy, css, nsx, nsy, nss;
+  polygon_sums(shfl_d(cenx, quad0), shfl_d(ceny, quad0), shfl_d(cenx, quad0 + 1), shfl_d(ceny, quad0 + 1),
+               shfl_d(cenx, quad0 + 2), shfl_d(ceny, quad0 + 2), shfl_d(cenx, quad0 + 3), shfl_d(ceny, quad0 + 3), csx, csy, css);
+  polygon_sums(shfl_d(nomx, quad0), shfl_d(nomy, quad0), shfl_d(nomx, quad0 + 1), shfl_d(nomy, quad0 + 1),
+               shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3), nsx, nsy, nss);
+  const double num = (f & 2) ? ((f & 1) ? nsy : nsx) : ((f & 1) ? csy : csx);
+  const double den = (f & 2) ? nss : css;
+  const double r = div3_rn(div_rn(num, den));
+  ccx = shfl_d(r, quad0);
+  ccy = shfl_d(r, quad0 + 1);
+  ncx = shfl_d(r, quad0 + 2);
+  ncy = shfl_d(r, quad0 + 3);
+}
+
 __device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y, double z, int row, int col, int foot,
                                           int cycle, int kind) {
   double* d = reinterpret_cast<double*>(dst);
@@ -210,12 +238,16 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
 #endif
     // getFootholdSearchGridMap for both chains (FP.cpp:788, :830 -> :2166-2250)
     double ccx, ccy, ncx, ncy;
+#ifdef FHP_NO_QUAD_DIV
     polygon_center(shfl_d(cenx, quad0), shfl_d(ceny, quad0), shfl_d(cenx, quad0 + 1), shfl_d(ceny, quad0 + 1),
                    shfl_d(cenx, quad0 + 2), shfl_d(ceny, quad0 + 2), shfl_d(cenx, quad0 + 3), shfl_d(ceny, quad0 + 3),
                    ccx, ccy);
     polygon_center(shfl_d(nomx, quad0), shfl_d(nomy, quad0), shfl_d(nomx, quad0 + 1), shfl_d(nomy, quad0 + 1),
                    shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
                    ncx, ncy);
+#else
+    quad_centres(cenx, ceny, nomx, nomy, quad0, f, ccx, ccy, ncx, ncy);
+#endif
     const double nextY = qu.y + adjY;                                 // :2201
     // HEADING: next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n — forward coordinate from the stance centroid,
     // lateral coordinate pinned to the initial pose plus the drift (reduces bit-exactly to :2199-2201 at cos 1, sin 0)
