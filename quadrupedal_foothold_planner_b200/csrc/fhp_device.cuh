@@ -544,10 +544,12 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GV& G, 
 // thrC > thrD take the float paths) — split into two bit planes e0/e1 over buffer rows.  Entry (k, c) of `mask` =
 // {e0 rows 32k..32k+31, e0 rows 32k+32..32k+63, e1 same, e1 same} of buffer column c, stored k-major (index
 // k*cols + c): ONE 16-byte load holds the 32 window rows starting at any row of word k, and neighbouring columns
-// are contiguous.  Staging a window column = 1 load, 2 funnel shifts, D = e1, C = e0 & e1, F = e0 | e1, 1 store.
-// 8 lanes serve one window, two columns each per step (consecutive columns -> one or two 128-byte lines per load
-// instruction), 4 windows per pass, and write straight into the owner's slot (pack = 1 layout: 16 bytes {D, C, F, pad}
-// per column).
+// are contiguous.  Staging a window column = 1 load, 2 funnel shifts, 1 eight-byte store of the class pair (e0, e1);
+// the consumers derive D = e1, C = e0 & e1, F = e0 | e1 where they read (Planes, pack == 0 layout: pair b at words
+// 2b, 2b+1 of the lane's slot, one pad word per column behind the pairs for the finished spiral masks).  Every lane
+// stages ITS OWN window — WIN independent loads in register-sized batches, no cross-lane traffic; the 8-byte variant
+// of the entries (half the footprint, a second load when the window crosses a row word) and 8 lanes per window
+// (fewer L1 wavefronts, shuffles to route the words) both measured slower (profiles/r2_experiments.md).
 // Fast = the window lies inside the map and does not cross the circular-buffer ROW seam (the column seam is
 // handled per column); everything else takes stage_slow on the float layer, exactly like the other paths.
 template <class GV>
