@@ -81,6 +81,7 @@ struct fhp_ctx {
   // FHP_FORCE_HEADING=1 (test knob, read at fhp_create): run the heading expressions even for heading == 0, where they
   // must reduce bit-exactly to the reference's (tests/test_gpu_heading.py)
   bool noSpec = false;  // FHP_NO_SPEC=1 (test knob): never pick a geometry-specialised kernel variant (GeoK)
+  bool noOnePar = false;  // FHP_NO_ONEPAR=1 (test knob): single-parameter-set calls read the device table like the others
   bool forceHeading = false;
   bool anyHeading = false;  // some parameter set of the current call has the heading expressions in force
   bool asyncPlans = false;  // a plan was launched on a caller's stream since the last device-wide synchronisation
@@ -91,6 +92,7 @@ struct fhp_ctx {
   bool maskNegInf = false;  // the layer holds -inf cells: their raw compare differs from their class -> float paths
   long long maskBuilds = 0;
   // scratch
+  ParDev hPar0;  // derived table entry 0 of the last call (travels in the kernel arguments)
   DevBuf dPars, dQ, dOutN, dOutC, dOutD, dSt, dErr, dA, dB, dC2, dD, dCompact, dOffs;
   // zero-copy scratch for latency-bound calls (a robot's single plan): the kernel reads the queries from and writes the
   // rows to mapped pinned host memory, so the call is one launch and one stream sync with no copy engine involved
@@ -592,6 +594,7 @@ int prepare_params(fhp_ctx* ctx, const fhp_params* params, int32_t n_params, cud
   }
   std::vector<ParDev> h(n_params);
   for (int i = 0; i < n_params; ++i) derive_params(params[i], h[i], ctx->forceHeading);
+  ctx->hPar0 = h[0];
   CU(ctx->dPars.reserve(sizeof(ParDev) * n_params));
   CU(cudaMemcpyAsync(ctx->dPars.p, h.data(), sizeof(ParDev) * n_params, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));  // h goes out of scope
@@ -710,6 +713,7 @@ int fhp_create(int device, fhp_ctx** out) {
   if (const char* v = std::getenv("FHP_TMA_BOX_BUDGET")) ctx->tmaBoxBudget = std::max(1024, atoi(v));
   if (const char* v = std::getenv("FHP_FORCE_HEADING")) ctx->forceHeading = v[0] == '1';
   if (const char* v = std::getenv("FHP_NO_SPEC")) ctx->noSpec = v[0] == '1';
+  if (const char* v = std::getenv("FHP_NO_ONEPAR")) ctx->noOnePar = v[0] == '1';
   if (const char* st = std::getenv("FHP_STAGING")) {
     if (!std::strcmp(st, "mask")) ctx->stagePref = kStageMask;
     else if (!std::strcmp(st, "tma")) ctx->stagePref = kStageTma;
@@ -1016,6 +1020,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.mask = static_cast<const uint4*>(ctx->dMask.p);
   A.pars = static_cast<const ParDev*>(ctx->dPars.p);
   A.nPars = n_params;
+  A.par0 = ctx->hPar0;
   A.q = d_queries;
   A.nq = n_queries;
   A.cycles = gait_cycles;
@@ -1036,7 +1041,7 @@ static int plan_launch(fhp_ctx* ctx, int32_t n_params, const fhp_query* d_querie
   A.st = d_st;
   A.err = ctx->dErrMapped;
   {
-    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, ctx->anyHeading, ctx->noSpec, s);
+    cudaError_t e = launch_plan(A, ctx->G, d_outC != nullptr, ctx->anyHeading, ctx->noSpec, ctx->noOnePar, s);
     if (e != cudaSuccess) {
       char b[256];
       snprintf(b, sizeof b, "plan kernel launch failed: %s (queries %lld, queries/warp %d, shared memory %d B)",

@@ -18,6 +18,7 @@ struct PlanArgs {
   const uint4* mask;  // cell-class planes of the traversability layer (valid iff G.stageMode == kStageMask)
   const ParDev* pars;
   int nPars;
+  ParDev par0;  // pars[0] by value: calls with ONE parameter set read it from the constant bank (plan_kernel<..., ONEPAR>)
   const fhp_query* q;
   long long nq;
   int cycles;
@@ -47,7 +48,8 @@ struct TaskArgs {
   unsigned* err;
 };
 
-cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, bool noSpec, cudaStream_t stream);
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, bool noSpec, bool noOnePar,
+                        cudaStream_t stream);
 int geo_spec_of(const GeoDev& G);
 constexpr int kStreamWarpBytes = 32 * 20;  // shared-memory staging of one warp's rows in stream mode
 long long plan_wave_queries(const GeoDev& G, bool wantCen);

@@ -135,7 +135,11 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GV& G, uint32
 #ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
 #define FHP_PLAN_MIN_BLOCKS_MASK 7
 #endif
-template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM, int SPEC>
+template <bool ONEPAR>
+__device__ __forceinline__ const ParDev& par_of(const PlanArgs& A, int id) {
+  if constexpr (ONEPAR) return A.par0; else return A.pars[id];
+}
+template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM, int SPEC, bool ONEPAR = false>
 __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev Gd) {
   const GeoV<SPEC> G(Gd);  // SPEC > 0: the geometry's scalars are compile-time constants (fhp_device.cuh)
@@ -183,7 +187,9 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     err = kErrParam;                                                           // walked on the host
     qu.param_id = 0;
   }
-  const ParDev& P = A.pars[qu.param_id];
+  // ONEPAR (calls with one parameter set, the service's case): the derived table entry travels in the kernel arguments, so
+  // its fields are constant-bank operands instead of loads through a pointer held in registers
+  const ParDev& P = par_of<ONEPAR>(A, qu.param_id);
   const long long R = 4 + 4 * static_cast<long long>(A.cycles);
   fhp_foothold* outN = A.outN + q * R;
   fhp_foothold* outC = WANT_CEN ? A.outC + q * R : nullptr;
@@ -656,8 +662,12 @@ cudaError_t launch_compact(const fhp_foothold* rows, const fhp_query_status* st,
 typedef void (*plan_kernel_fn)(const PlanArgs, const GeoDev);
 // the default chain is only compiled into the centroid-output variants (fhp_plan_ex fills all three chains)
 template <int STAGE, bool HEADING>
-static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef, bool stream, int spec) {
+static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef, bool stream, int spec, bool onePar) {
   if (STAGE == kStageMask && !wantCen && !wantDef) {  // the response path: geometry-specialised variants (GeoK)
+    if (!HEADING && onePar) {  // ... with the single parameter set in the kernel arguments
+      if (spec == 1) return stream ? plan_kernel<false, kStageMask, false, false, true, 1, true> : plan_kernel<false, kStageMask, false, false, false, 1, true>;
+      if (spec == 2) return stream ? plan_kernel<false, kStageMask, false, false, true, 2, true> : plan_kernel<false, kStageMask, false, false, false, 2, true>;
+    }
     if (spec == 1) return stream ? plan_kernel<false, kStageMask, false, HEADING, true, 1> : plan_kernel<false, kStageMask, false, HEADING, false, 1>;
     if (spec == 2) return stream ? plan_kernel<false, kStageMask, false, HEADING, true, 2> : plan_kernel<false, kStageMask, false, HEADING, false, 2>;
   }
@@ -667,19 +677,21 @@ static plan_kernel_fn pick_plan_kernel_s(bool wantCen, bool wantDef, bool stream
 }
 // heading: some parameter set of the call carries a non-zero heading -> the variant with the rotated expressions
 // (the reference-shaped variant stays exactly what it was)
-static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading, bool stream, int spec) {
+static plan_kernel_fn pick_plan_kernel(int stage, bool wantCen, bool wantDef, bool heading, bool stream, int spec, bool onePar) {
 #ifdef FHP_BENCH_BUILD  // scratch A/B builds: only the headline variants are instantiated (seconds instead of a minute)
+  if (onePar && spec == 2) return plan_kernel<false, kStageMask, false, false, false, 2, true>;
+  if (onePar && spec == 1) return plan_kernel<false, kStageMask, false, false, false, 1, true>;
   if (spec == 2) return plan_kernel<false, kStageMask, false, false, false, 2>;
   return spec == 1 ? plan_kernel<false, kStageMask, false, false, false, 1> : plan_kernel<false, kStageMask, false, false, false, 0>;
 #else
   if (heading) {
-    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef, stream, spec);
-    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef, stream, spec);
-    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef, stream, spec);
+    if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, true>(wantCen, wantDef, stream, spec, onePar);
+    if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, true>(wantCen, wantDef, stream, spec, onePar);
+    return pick_plan_kernel_s<kStageLdg, true>(wantCen, wantDef, stream, spec, onePar);
   }
-  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef, stream, spec);
-  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef, stream, spec);
-  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef, stream, spec);
+  if (stage == kStageMask) return pick_plan_kernel_s<kStageMask, false>(wantCen, wantDef, stream, spec, onePar);
+  if (stage == kStageTma) return pick_plan_kernel_s<kStageTma, false>(wantCen, wantDef, stream, spec, onePar);
+  return pick_plan_kernel_s<kStageLdg, false>(wantCen, wantDef, stream, spec, onePar);
 #endif
 }
 
@@ -697,7 +709,8 @@ int geo_spec_of(const GeoDev& G) {
 }
 
 // ---- launchers (called from fhp_capi.cu) --------------------------------------------------------------------------
-cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, bool noSpec, cudaStream_t stream) {
+cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool heading, bool noSpec, bool noOnePar,
+                        cudaStream_t stream) {
   if (A.nq <= 0) return cudaSuccess;
   const int warps = kPlanThreads / 32;
   const int qpw = 1 << A.qpwShift;
@@ -706,7 +719,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
   const bool streamMode = A.sOut != nullptr;
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128 +  // + alignment slack
                      (streamMode ? static_cast<size_t>(warps) * kStreamWarpBytes : 0);
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading, streamMode, noSpec ? 0 : geo_spec_of(G));
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading, streamMode, noSpec ? 0 : geo_spec_of(G), A.nPars == 1 && !noOnePar);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
     if (e != cudaSuccess) return e;
@@ -719,7 +732,7 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
 // the chunk size of the host-buffer pipeline (a block runs all gait cycles sequentially, so a launch smaller than
 // a wave takes as long as a full one).
 long long plan_wave_queries(const GeoDev& G, bool wantCen) {
-  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false, false, geo_spec_of(G));
+  void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, false, false, false, geo_spec_of(G), false);
   const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128;
   if (shm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm));
   int perSm = 0, dev = 0, sms = 0;
