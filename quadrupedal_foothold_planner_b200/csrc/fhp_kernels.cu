@@ -51,7 +51,9 @@ __device__ __forceinline__ void polygon_sums(double x1, double y1, double x2, do
   sum_y = (0.0 + (y1 + y2 + y3) * s1) + (y1 + y3 + y4) * s2;
   sum_s = (0.0 + s1) + s2;
 }
-__device__ __forceinline__ void quad_centres(double cenx, double ceny, double nomx, double nomy, int quad0, int f,
+// `dead` (uniform over the quad, see plan_kernel): the quotients are not needed any more — NaN without the subroutine,
+// whose special-operand path (a zero area divides 0/0) is several times longer than the division itself.
+__device__ __forceinline__ void quad_centres(double cenx, double ceny, double nomx, double nomy, int quad0, int f, bool dead,
                                              double& ccx, double& ccy, double& ncx, double& ncy) {
   double csx, csy, css, nsx, nsy, nss;
   polygon_sums(shfl_d(cenx, quad0), shfl_d(ceny, quad0), shfl_d(cenx, quad0 + 1), shfl_d(ceny, quad0 + 1),
@@ -60,7 +62,8 @@ __device__ __forceinline__ void quad_centres(double cenx, double ceny, double no
                shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3), nsx, nsy, nss);
   const double num = (f & 2) ? ((f & 1) ? nsy : nsx) : ((f & 1) ? csy : csx);
   const double den = (f & 2) ? nss : css;
-  const double r = div3_rn(div_rn(num, den));
+  double r = __longlong_as_double(0x7ff8000000000000ll);
+  if (!dead) r = div3_rn(div_rn(num, den));
   ccx = shfl_d(r, quad0);
   ccy = shfl_d(r, quad0 + 1);
   ncx = shfl_d(r, quad0 + 2);
@@ -233,6 +236,16 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     }
     if (active && f == 0) optFail = !submap_request_ok(M, onx, ony, P.isosLx, P.isosLy);
   }
+  // A quad whose search centre has stopped being finite is DEAD for the rest of its plan: a degenerate stance polygon
+  // (two feet of the centroid chain at the (0,0,0) the centroid method returns without a case) has a zero area, the
+  // centroid is 0/0, every foothold test fails on an index of -2^30, the failed cycle leaves the chains as they are, and
+  // the next cycle starts from the same polygon (~6 % of the lane-cycles of C3).  Such lanes — and the lanes of a warp
+  // that have no query at all, whose all-zero state is the same polygon — keep taking part in the warp-collective steps
+  // but skip the work: same statuses, same rows, none of the special-operand division paths.
+  // (Not in the bug-compatible spiral mode on a shifted start index: there upstream wraps the centre's index of -2^30
+  // into the buffer and the scan goes on from that cell — such a foothold can succeed.)
+  const bool canDie = !(P.spiralMode == FHP_SPIRAL_FAITHFUL && !(M.start0 == 0 && M.start1 == 0));
+  bool dead = !active;
   double adjY = 0.0;  // ajustedPose_[1] (FP.cpp:759)
   int prevW0 = -0x7fffffff, prevW1 = -0x7fffffff;  // window staged in the previous cycle (still in this lane's slot)
   int nrows = 4, succeed = 0;
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
                    shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
                    ncx, ncy);
 #else
-    quad_centres(cenx, ceny, nomx, nomy, quad0, f, ccx, ccy, ncx, ncy);
+    quad_centres(cenx, ceny, nomx, nomy, quad0, f, dead, ccx, ccy, ncx, ncy);
 #endif
     const double nextY = qu.y + adjY;                                 // :2201
     // HEADING: next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n — forward coordinate from the stance centroid,
@@ -288,8 +301,14 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
       ry = (mulz(fwdN, P.sh) + latC) + by;
     }
 
+    dead = dead || (canDie && (!(fabs(px) <= 1.7976931348623157e308) || !(fabs(py) <= 1.7976931348623157e308)));
+    const bool live = !dead;  // (implies active)
     // stage the window around the search centre (= centroid-chain point, FP.cpp:861-862)
-    const int uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv), uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
+    int uc0 = -1073741824, uc1 = -1073741824;  // raw_index_axis of a non-finite coordinate
+    if (live) {
+      uc0 = raw_index_axis(px, M.halfx, M.posx, M.res, M.rinv);
+      uc1 = raw_index_axis(py, M.halfy, M.posy, M.res, M.rinv);
+    }
     int w0 = uc0 - G.HW();
     const int w1 = uc1 - G.HW();
     if (USE_TMA) {  // TMA needs the box's innermost (row) coordinate 16-byte aligned: shift the origin down to a
@@ -298,7 +317,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
       w0 -= c0 & 3;
     }
     DiscWin dw = {0, 0, -1, -1, 0ull, 0};  // foot disc of the centre: default test + height (FP.cpp:2048, :2529)
-    if (active) {
+    if (live) {
       dw = disc_window(M, G, px, py, uc0, uc1, P.r, P.r2);
     }
     // (discs of up to four cells — footRadius <= resolution — are loaded here, in flight during the staging below;
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     }
     // A query that failed keeps its chains (FP.cpp:1571-1576) and only drifts 7 mm sideways per cycle, so its next
     // window is usually the SAME cells: the bit-planes are still in this lane's slot, nothing to stage.
-    const bool restage = active && !(w0 == prevW0 && w1 == prevW1);
+    const bool restage = live && !(w0 == prevW0 && w1 == prevW1);
     prevW0 = w0;
     prevW1 = w1;
     if (STAGE == kStageMask)
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     double nz = 0.0, cz = 0.0;
     bool okDef = false;
     float zCentre = 0.0f;
-    if (active) {
+    if (live) {
       Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 0 : G.pack(), G.rpShift(), G.WIN());
       zCentre = G.discK() == 1 ? mean_height_loaded(M, P, px, py, dw, de, true) : disc_elev_mean(M, P, px, py, dw, elevSlot);                // FP.cpp:2029 (used when the leg is valid)
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     __syncthreads();
 #endif
     const NominalOut no =
-        nominal_eval<false, STAGE == kStageMask, HEADING>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
+        nominal_eval<false, STAGE == kStageMask, HEADING>(M, G, P, sSpiral, sw, lane, live, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
     const bool ok = no.ok;
 #if FHP_SYNC_LEVEL >= 3
     __syncthreads();
