@@ -554,8 +554,8 @@ __device__ __forceinline__ void stage_windows_tma(const MapDev& M, const GV& G, 
 // handled per column); everything else takes stage_slow on the float layer, exactly like the other paths.
 template <class GV>
 __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GV& G, const uint4* __restrict__ mask,
-                                                   uint32_t smemWarp, int lane, bool has_window, int w0, int w1,
-                                                   float thrD, float thrC) {
+                                                   uint32_t smemWarp, uint32_t mine, int lane, bool has_window, int w0,
+                                                   int w1, float thrD, float thrC) {
   const bool empty = has_window && (w0 >= M.rows || w1 >= M.cols || w0 <= -32 || w1 <= -G.WIN());
   int bb0 = w0 + M.start0, bb1 = w1 + M.start1;  // |w| <= 2^30 + HW: no overflow
   if (bb0 >= M.rows) bb0 -= M.rows;
@@ -570,13 +570,12 @@ __device__ __forceinline__ void stage_windows_mask(const MapDev& M, const GV& G,
   }
   __syncwarp();  // every lane is done reading the planes of the previous leg/cycle
   if (empty) {
-    const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
     for (int k = 0; k < G.WIN(); ++k) sts_v2(mine + static_cast<uint32_t>(k) * 8u, 0u, 0u);
   }
   if (fast) {  // every lane stages ITS OWN window: WIN independent 16-byte loads, no cross-lane traffic
     const uint4* src = mask + (bb0 >> 5) * M.cols;
     const int s = bb0 & 31;
-    const uint32_t dst = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
+    const uint32_t dst = mine;
     int col = bb1;
     for (int c = 0; c < G.WIN(); c += kStageBatch) {
       uint4 e[kStageBatch];
@@ -1461,10 +1460,11 @@ __device__ __noinline__ void spiral_scan_faithful(const MapDev& M, const GV& G, 
 // checkCandidateFoothold (:2085-2114) over grid_map::SpiralIterator with checkCirclePolygonFoothold (:2117-2163).
 // WARP-COLLECTIVE: every lane of the warp must call it (inactive lanes pass active = false).
 // (cx,cy): search centre; (rx,ry): centre of the search rectangle; (uc0,uc1): raw unwrapped index of the centre;
-// (w0,w1): unwrapped origin of the staged window (uc-HW, minus the TMA row-alignment shift).
+// (w0,w1): unwrapped origin of the staged window (uc-HW, minus the TMA row-alignment shift); mine: shared-space
+// address of this lane's plane slot (smemWarp + lane * stride words).
 template <bool DEFAULT_ONLY, bool PAD, bool HEADING, class GV>
 __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G, const ParDev& P,
-                                                   const uint16_t* sSpiral, uint32_t smemWarp, int lane,
+                                                   const uint16_t* sSpiral, uint32_t smemWarp, uint32_t mine, int lane,
                                                    bool active, int uc0, int uc1, int w0, int w1, double cx, double cy,
                                                    double rx, double ry, bool okDefault, unsigned& err) {
   NominalOut o;
@@ -1473,7 +1473,6 @@ __device__ __forceinline__ NominalOut nominal_eval(const MapDev& M, const GV& G,
   o.ok = false;
   o.kind = FHP_KIND_DEFAULT;
   o.row = o.col = -1;
-  const uint32_t mine = smemWarp + static_cast<uint32_t>(lane * G.stride()) * 4u;
   const Planes pl(mine, PAD ? 0 : G.pack(), G.rpShift(), G.WIN());  // PAD <=> mask staging: the class-pair layout
   if (active) {
     const bool centre_in_map = within_axis(cx, M.lenx, M.posx, M.halfx) && within_axis(cy, M.leny, M.posy, M.halfy) &&

@@ -162,7 +162,17 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint16_t* sSpiral = load_spiral_table(G, smem);  // ends with __syncthreads (also publishes the mbarriers)
-  const uint32_t sw = smem_u32(smem + G.spiralWords() + warpInBlock * 32 * G.stride());
+  // shared-space addresses of the warp's plane block and of this lane's slot in it.  Opaque to the compiler: under
+  // register pressure it otherwise recomputes them at every use — ten instructions each time (thread id, the shared
+  // window base from the cluster CTA id, two multiply-adds) instead of one reload
+  uint32_t sw = smem_u32(smem + G.spiralWords() + warpInBlock * 32 * G.stride());
+  uint32_t mine = sw + static_cast<uint32_t>(lane * G.stride()) * 4u;
+#ifndef FHP_NO_OPAQUE
+  asm volatile("" : "+r"(sw));
+#ifndef FHP_NO_OPAQUE_MINE
+  asm volatile("" : "+r"(mine));
+#endif
+#endif
   const long long gwarp = static_cast<long long>(blockIdx.x) * (kPlanThreads / 32) + warpInBlock;
   // A warp plans 2^qpwShift queries (its first quads).  Eight keeps every lane busy; batches too small to fill the GPU
   // spread over more warps instead, because the warp-cooperative steps (staging passes, spiral scans) serve a warp's
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     prevW0 = w0;
     prevW1 = w1;
     if (STAGE == kStageMask)
-      stage_windows_mask(M, G, A.mask, sw, lane, restage, w0, w1, P.thrD, P.thrC);
+      stage_windows_mask(M, G, A.mask, sw, mine, lane, restage, w0, w1, P.thrD, P.thrC);
     else if (USE_TMA)
       stage_windows_tma(M, G, &A.tmap, T, sw, lane, restage, w0, w1, P.thrD, P.thrC);
     else
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     bool okDef = false;
     float zCentre = 0.0f;
     if (live) {
-      Planes pl(sw + static_cast<uint32_t>(lane * G.stride()) * 4u, STAGE == kStageMask ? 0 : G.pack(), G.rpShift(), G.WIN());
+      Planes pl(mine, STAGE == kStageMask ? 0 : G.pack(), G.rpShift(), G.WIN());
       zCentre = G.discK() == 1 ? mean_height_loaded(M, P, px, py, dw, de, true) : disc_elev_mean(M, P, px, py, dw, elevSlot);                // FP.cpp:2029 (used when the leg is valid)
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
       co = centroid_eval(M, G, P, pl, w0, w1, uc0, uc1, px, py, err);  // FP.cpp:818-821
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     __syncthreads();
 #endif
     const NominalOut no =
-        nominal_eval<false, STAGE == kStageMask, HEADING>(M, G, P, sSpiral, sw, lane, live, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
+        nominal_eval<false, STAGE == kStageMask, HEADING>(M, G, P, sSpiral, sw, mine, lane, live, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
     const bool ok = no.ok;
 #if FHP_SYNC_LEVEL >= 3
     __syncthreads();
@@ -475,11 +485,11 @@ __global__ void __launch_bounds__(kPlanThreads) task_kernel(const __grid_constan
     NominalOut no;
     const bool okDef = (MODE != 4) && active && default_eval(M, G, P, pl, w0, w1, px, py, dw, err);
     if (MODE == 3)
-      no = nominal_eval<true, false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
+      no = nominal_eval<true, false, false>(M, G, P, sSpiral, sw, sw + static_cast<uint32_t>(lane * G.stride()) * 4u, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     else if (P.heading)  // uniform: one parameter set per task launch
-      no = nominal_eval<false, false, true>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
+      no = nominal_eval<false, false, true>(M, G, P, sSpiral, sw, sw + static_cast<uint32_t>(lane * G.stride()) * 4u, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     else
-      no = nominal_eval<false, false, false>(M, G, P, sSpiral, sw, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
+      no = nominal_eval<false, false, false>(M, G, P, sSpiral, sw, sw + static_cast<uint32_t>(lane * G.stride()) * 4u, lane, active, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);
     if (active) {
       if (MODE == 0) {
         double z = 0.0;
