@@ -53,6 +53,9 @@ __device__ __forceinline__ void polygon_sums(double x1, double y1, double x2, do
 }
 // `dead` (uniform over the quad, see plan_kernel): the quotients are not needed any more — NaN without the subroutine,
 // whose special-operand path (a zero area divides 0/0) is several times longer than the division itself.
+// (Without a heading only the x coordinates of the two centres are used, FP.cpp:2199-2201: lanes 0/1 and 2/3 then run
+// the same chain and the y sums are never formed.)
+template <bool HEADING>
 __device__ __forceinline__ void quad_centres(double cenx, double ceny, double nomx, double nomy, int quad0, int f, bool dead,
                                              double& ccx, double& ccy, double& ncx, double& ncy) {
   double csx, csy, css, nsx, nsy, nss;
@@ -60,14 +63,14 @@ __device__ __forceinline__ void quad_centres(double cenx, double ceny, double no
                shfl_d(cenx, quad0 + 2), shfl_d(ceny, quad0 + 2), shfl_d(cenx, quad0 + 3), shfl_d(ceny, quad0 + 3), csx, csy, css);
   polygon_sums(shfl_d(nomx, quad0), shfl_d(nomy, quad0), shfl_d(nomx, quad0 + 1), shfl_d(nomy, quad0 + 1),
                shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3), nsx, nsy, nss);
-  const double num = (f & 2) ? ((f & 1) ? nsy : nsx) : ((f & 1) ? csy : csx);
+  const double num = HEADING ? ((f & 2) ? ((f & 1) ? nsy : nsx) : ((f & 1) ? csy : csx)) : ((f & 2) ? nsx : csx);
   const double den = (f & 2) ? nss : css;
   double r = __longlong_as_double(0x7ff8000000000000ll);
   if (!dead) r = div3_rn(div_rn(num, den));
   ccx = shfl_d(r, quad0);
-  ccy = shfl_d(r, quad0 + 1);
   ncx = shfl_d(r, quad0 + 2);
-  ncy = shfl_d(r, quad0 + 3);
+  ccy = HEADING ? shfl_d(r, quad0 + 1) : 0.0;
+  ncy = HEADING ? shfl_d(r, quad0 + 3) : 0.0;
 }
 
 __device__ __forceinline__ void write_row(fhp_foothold* dst, double x, double y, double z, int row, int col, int foot,
@@ -129,8 +132,15 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GV& G, uint32
   return t;
 }
 
+// Block barriers per gait cycle: 1 = top of the cycle, 2 = + after the staging, 3 = + after the search.  They keep the
+// block's warps in the same code region; what that is worth depends on the size of the cycle's code: the 0.02 m
+// specialisation (hot loop well inside the instruction cache) is fastest with one, everything else with three
+// (profiles/r2_experiments.md, both tables).
 #ifndef FHP_SYNC_LEVEL
 #define FHP_SYNC_LEVEL 3
+#endif
+#ifndef FHP_SYNC_LEVEL_S1
+#define FHP_SYNC_LEVEL_S1 1
 #endif
 #ifndef FHP_PLAN_MIN_BLOCKS
 #define FHP_PLAN_MIN_BLOCKS 5
@@ -146,6 +156,7 @@ template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM, in
 __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev Gd) {
   const GeoV<SPEC> G(Gd);  // SPEC > 0: the geometry's scalars are compile-time constants (fhp_device.cuh)
+  constexpr int kSync = SPEC == 1 ? FHP_SYNC_LEVEL_S1 : FHP_SYNC_LEVEL;
   extern __shared__ __align__(128) uint32_t smem_raw[];  // (TMA destinations must be 128-byte aligned)
   uint32_t* const smem = smem_raw;
   constexpr bool USE_TMA = STAGE == kStageTma;
@@ -262,9 +273,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
   bool success = false;
 
   for (int g = 0; g < A.cycles; ++g) {
-#if FHP_SYNC_LEVEL >= 1
-    __syncthreads();  // keep the block's warps in the same code region (instruction-cache locality)
-#endif
+    if constexpr (kSync >= 1) __syncthreads();  // keep the block's warps in the same code region
     // getFootholdSearchGridMap for both chains (FP.cpp:788, :830 -> :2166-2250)
     double ccx, ccy, ncx, ncy;
 #ifdef FHP_NO_QUAD_DIV
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
                    shfl_d(nomx, quad0 + 2), shfl_d(nomy, quad0 + 2), shfl_d(nomx, quad0 + 3), shfl_d(nomy, quad0 + 3),
                    ncx, ncy);
 #else
-    quad_centres(cenx, ceny, nomx, nomy, quad0, f, dead, ccx, ccy, ncx, ncy);
+    quad_centres<HEADING>(cenx, ceny, nomx, nomy, quad0, f, dead, ccx, ccy, ncx, ncy);
 #endif
     const double nextY = qu.y + adjY;                                 // :2201
     // HEADING: next centre = ((c.u) + stepLength) u + ((p0.n) + adjY) n — forward coordinate from the stance centroid,
@@ -351,9 +360,7 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
     else
       stage_windows(M, G, sw, lane, restage, w0, w1, P.thrD, P.thrC);
 
-#if FHP_SYNC_LEVEL >= 2
-    __syncthreads();
-#endif
+    if constexpr (kSync >= 2) __syncthreads();
     CentroidOut co;
     co.x = co.y = 0.0;
     co.ccase = -1;
@@ -366,15 +373,11 @@ __global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_M
       okDef = default_eval(M, G, P, pl, w0, w1, px, py, dw, err);        // FP.cpp:2012
       co = centroid_eval(M, G, P, pl, w0, w1, uc0, uc1, px, py, err);  // FP.cpp:818-821
     }
-#if FHP_SYNC_LEVEL >= 4
-    __syncthreads();
-#endif
+    if constexpr (kSync >= 4) __syncthreads();
     const NominalOut no =
         nominal_eval<false, STAGE == kStageMask, HEADING>(M, G, P, sSpiral, sw, mine, lane, live, uc0, uc1, w0, w1, px, py, rx, ry, okDef, err);  // :863-903
     const bool ok = no.ok;
-#if FHP_SYNC_LEVEL >= 3
-    __syncthreads();
-#endif
+    if constexpr (kSync >= 3) __syncthreads();
     if (active) {
       if (ok) nz = static_cast<double>(zCentre);  // at the CENTRE (FP.cpp:2029)
       if (WANT_CEN && co.ccase >= 0 && co.ccase <= 3) cz = static_cast<double>(mean_height(M, G, P, co.x, co.y));
