@@ -935,6 +935,8 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GV& 
     const uint32_t rowmask = (n0 >= 32 ? 0xffffffffu : ((1u << n0) - 1u)) << a0;
     // whole-window test (FP.cpp:1649-1658) and per-row counts of cells below the threshold (:1722-1750) as a
     // bit-sliced vertical counter over the window columns (policy C.1: the phantom column is not counted)
+    // (counts are at most WIN: four counter bits are enough for windows of up to 15 columns)
+    const bool wide = G.WIN() > 15;
     uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
     any = 0;
     for (int c = c0; c <= c1; ++c) {
@@ -944,8 +946,12 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GV& 
       t = s0 & x; s0 ^= x; x = t;
       t = s1 & x; s1 ^= x; x = t;
       t = s2 & x; s2 ^= x; x = t;
-      t = s3 & x; s3 ^= x; x = t;
-      s4 ^= x;
+      if (wide) {
+        t = s3 & x; s3 ^= x; x = t;
+        s4 ^= x;
+      } else {
+        s3 ^= x;
+      }
     }
     // row is an "edge" when count > (rightCol+1)*0.5  <=>  count > floor(n1/2) for integers (:1743)
     const int T = n1 >> 1;
@@ -953,6 +959,7 @@ __device__ __forceinline__ CentroidOut centroid_eval(const MapDev& M, const GV& 
     const uint32_t sv[5] = {s0, s1, s2, s3, s4};
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
+      if (i == 4 && !wide) continue;
       const uint32_t ti = ((T >> i) & 1) ? 0xffffffffu : 0u;
       gt |= eq & sv[i] & ~ti;
       eq &= ~(sv[i] ^ ti);
