@@ -148,12 +148,20 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GV& G, uint32
 #ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
 #define FHP_PLAN_MIN_BLOCKS_MASK 7
 #endif
+// The 0.01 m specialisation runs FOUR blocks per SM (124 registers, no spills; shared memory would hold five): on a map
+// larger than the L2 the resident warps' windows and elevation discs (~0.8 KB per lane and cycle) have to survive in the
+// L2 from one gait cycle of a query to the next, and 20 warps per SM x 148 SMs push ~76 MB through it per round where 16
+// push ~60 MB — config 5 (3 GB map): 12.7 ms per launch with five blocks, 7.7 ms with four, 7.7 with three; the same
+// geometry on an L2-resident map: 2.52 / 2.19 / 2.43 ms (profiles/r2_experiments.md).
+#ifndef FHP_PLAN_MIN_BLOCKS_S2
+#define FHP_PLAN_MIN_BLOCKS_S2 4
+#endif
 template <bool ONEPAR>
 __device__ __forceinline__ const ParDev& par_of(const PlanArgs& A, int id) {
   if constexpr (ONEPAR) return A.par0; else return A.pars[id];
 }
 template <bool WANT_CEN, int STAGE, bool WANT_DEF, bool HEADING, bool STREAM, int SPEC, bool ONEPAR = false>
-__global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? FHP_PLAN_MIN_BLOCKS_MASK : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
+__global__ void __launch_bounds__(kPlanThreads, STAGE == kStageMask ? (SPEC == 2 ? FHP_PLAN_MIN_BLOCKS_S2 : FHP_PLAN_MIN_BLOCKS_MASK) : FHP_PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs A,
                                                             const __grid_constant__ GeoDev Gd) {
   const GeoV<SPEC> G(Gd);  // SPEC > 0: the geometry's scalars are compile-time constants (fhp_device.cuh)
   constexpr int kSync = SPEC == 1 ? FHP_SYNC_LEVEL_S1 : FHP_SYNC_LEVEL;
