@@ -148,11 +148,13 @@ __device__ __forceinline__ const uint16_t* load_spiral_table(const GV& G, uint32
 #ifndef FHP_PLAN_MIN_BLOCKS_MASK  // the mask path needs no box buffers: 7 blocks fit in shared memory (72 registers)
 #define FHP_PLAN_MIN_BLOCKS_MASK 7
 #endif
-// The 0.01 m specialisation runs FOUR blocks per SM (124 registers, no spills; shared memory would hold five): on a map
-// larger than the L2 the resident warps' windows and elevation discs (~0.8 KB per lane and cycle) have to survive in the
-// L2 from one gait cycle of a query to the next, and 20 warps per SM x 148 SMs push ~76 MB through it per round where 16
-// push ~60 MB — config 5 (3 GB map): 12.7 ms per launch with five blocks, 7.7 ms with four, 7.7 with three; the same
-// geometry on an L2-resident map: 2.52 / 2.19 / 2.43 ms (profiles/r2_experiments.md).
+// The 0.01 m specialisation is compiled for FOUR blocks per SM = 124 registers (shared memory would hold five).  Its
+// window is 23 columns: with 124 registers all 23 sixteen-byte column loads of a lane's window are in flight at once (92
+// destination registers), with 72-96 the compiler issues them in register-limited groups and a map larger than the L2
+// pays its DRAM latency once per group — config 5 (3 GB map): 13.7 ms per launch at 72 registers, 12.7 at 96, 7.7 at 124
+// and at 164; the same geometry on an L2-resident map: 2.67 / 2.52 / 2.19 / 2.43 ms.  It is the registers, not the
+// number of resident warps: 96 registers at 16 warps per SM (shared memory padded) runs like 96 at 20
+// (profiles/r2_experiments.md).
 #ifndef FHP_PLAN_MIN_BLOCKS_S2
 #define FHP_PLAN_MIN_BLOCKS_S2 4
 #endif
@@ -757,7 +759,10 @@ cudaError_t launch_plan(const PlanArgs& A, const GeoDev& G, bool wantCen, bool h
   const long long nWarps = (A.nq + qpw - 1) / qpw;
   const long long blocks = (nWarps + warps - 1) / warps;
   const bool streamMode = A.sOut != nullptr;
-  const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128 +  // + alignment slack
+#ifndef FHP_SMEM_PAD  // (A/B knob: extra dynamic shared memory per block, to lower the occupancy without touching registers)
+#define FHP_SMEM_PAD 0
+#endif
+  const size_t shm = static_cast<size_t>(G.smemWords) * sizeof(uint32_t) + 128 + FHP_SMEM_PAD +  // + alignment slack
                      (streamMode ? static_cast<size_t>(warps) * kStreamWarpBytes : 0);
   void (*kern)(const PlanArgs, const GeoDev) = pick_plan_kernel(G.stageMode, wantCen, A.outD != nullptr, heading, streamMode, noSpec ? 0 : geo_spec_of(G), A.nPars == 1 && !noOnePar);
   if (shm > 48 * 1024) {  // res 0.01-class windows: opt in to more than the default 48 KB of dynamic shared memory
