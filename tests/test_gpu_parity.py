@@ -604,3 +604,46 @@ def test_maps_smaller_than_a_window(fhp, oracle, shape):
     q = synth.uniform_queries(64, (0.3 - hx - 0.3, 0.3 + hx + 0.1), (-0.2 - hy - 0.2, -0.2 + hy + 0.2), seed=r + c)
     got, exp = _run_both(fhp, oracle, m, _abi.yaml_params(), q, 5)
     assert compare_plans(got, exp, f"tiny map {shape}") <= XYZ_TOL
+
+
+@pytest.mark.parametrize("res", [0.02, 0.01])
+def test_single_parameter_set_in_kernel_arguments_equals_table(oracle, res):
+    """A call with ONE parameter set runs the plan_kernel<..., ONEPAR> variants (derived parameters as constant-bank
+    operands); FHP_NO_ONEPAR=1 sends the same call through the variants that read the device table.  Same bytes from
+    both, rows and streamed response, and the rows equal the oracle's — stuck and degenerate (dead) quads included: the
+    rough map leaves centroid chains with two feet at (0,0,0)."""
+    import os
+    from quadrupedal_foothold_planner_b200.planner import Fhp
+    n = 700 if res == 0.02 else 1100
+    m = synth.rough_map(n, n, res, seed=17, start=(5, 9))
+    half = n * res / 2
+    q = synth.uniform_queries(4096, (-half + 0.8, half - 3.4), (-half + 0.8, half - 0.8), seed=3)
+    p = _abi.yaml_params()
+    N = 14
+    out = {}
+    for knob in ("0", "1"):
+        old = os.environ.get("FHP_NO_ONEPAR")
+        os.environ["FHP_NO_ONEPAR"] = knob
+        try:
+            ctx = Fhp(0)
+        finally:
+            if old is None:
+                del os.environ["FHP_NO_ONEPAR"]
+            else:
+                os.environ["FHP_NO_ONEPAR"] = old
+        try:
+            ctx.set_map(m)
+            nom, _, st = ctx.plan(p, q, N, centroid=False)
+            blocks, masks, sst = ctx.plan_stream(p, q, N)
+            rows, offs = ctx.stream_expand(blocks, masks, sst, N)
+            out[knob] = (nom.copy(), st.copy(), rows.copy(), offs.copy(), sst.copy())
+        finally:
+            ctx.close()
+    a, b = out["0"], out["1"]
+    keep = np.arange(a[0].shape[1])[None, :] < a[1]["n_rows"][:, None]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[4], b[4])
+    assert a[0][keep].tobytes() == b[0][keep].tobytes()
+    assert a[2].tobytes() == b[2].tobytes() and np.array_equal(a[3], b[3])
+    assert int((a[1]["gait_cycles_succeed"] < N).sum()) > 100  # not only clean runs
+    exp_nom, _, exp_st = oracle.plan(m, p, q, N, centroid=False)
+    assert compare_plans((a[0], None, a[1]), (exp_nom, None, exp_st), "one parameter set") == 0.0  # bit-exact
