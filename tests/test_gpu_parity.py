@@ -647,3 +647,32 @@ def test_single_parameter_set_in_kernel_arguments_equals_table(oracle, res):
     assert int((a[1]["gait_cycles_succeed"] < N).sum()) > 100  # not only clean runs
     exp_nom, _, exp_st = oracle.plan(m, p, q, N, centroid=False)
     assert compare_plans((a[0], None, a[1]), (exp_nom, None, exp_st), "one parameter set") == 0.0  # bit-exact
+
+
+@pytest.mark.parametrize("mode", [_abi.FHP_SPIRAL_WRAP_CORRECT, _abi.FHP_SPIRAL_FAITHFUL])
+@pytest.mark.parametrize("start", [(0, 0), (37, 211)])
+def test_non_finite_and_far_away_poses(fhp, oracle, start, mode):
+    """Poses that are NaN, infinite, astronomically large or simply off the map, mixed with ordinary ones in the same
+    warps: the index policy of SURVEY App. C (a non-finite / out-of-range coordinate converts to -2^30) makes every such
+    foothold fail — except in the bug-compatible spiral mode on a shifted start index, where upstream wraps that index
+    into the buffer — and the kernel's dead-quad shortcut must not change any of it."""
+    m = synth.rough_map(400, 380, 0.02, seed=23, start=start)
+    good = synth.uniform_queries(96, (-2.5, 0.5), (-2.5, 2.5), seed=8)
+    odd = [[np.nan, 0.0, 0.0], [0.0, np.nan, 0.0], [np.inf, 0.0, 0.0], [0.0, -np.inf, 0.0], [1e300, 0.0, 0.0],
+           [0.0, -1e300, 0.0], [1e12, 1e12, 0.0], [-3.0e7, 2.0, 0.0], [50.0, 0.0, 0.0], [0.0, -50.0, 0.0],
+           [3.99, 0.0, 0.0], [-4.2, 3.7, 0.0], [0.0, 0.0, np.nan], [0.0, 0.0, np.inf]]
+    q = np.concatenate([good[:40], _abi.make_queries(odd[:7]), good[40:70], _abi.make_queries(odd[7:]), good[70:]])
+    p = _abi.yaml_params(spiral_mode=mode)
+    fhp.set_map(m)
+    got = fhp.plan(p, q, 9, centroid=True)
+    exp = oracle.plan(m, p, q, 9)
+    gs, es = got[2], exp[2]
+    for f in ("success", "gait_cycles_succeed", "n_rows"):
+        assert np.array_equal(gs[f], es[f]), f
+    owned = np.arange(got[0].shape[1])[None, :] < es["n_rows"][:, None]
+    for k in (0, 1):
+        for f in ("row", "col", "foot_id", "gait_cycle_id", "kind"):
+            assert np.array_equal(got[k][f][owned], exp[k][f][owned]), f
+        for f in ("x", "y", "z"):  # NaN == NaN here: the stance rows of a NaN pose carry it
+            assert np.array_equal(got[k][f][owned], exp[k][f][owned], equal_nan=True), f
+    assert int(es["gait_cycles_succeed"][:40].max()) > 0  # the ordinary queries next to them still plan
