@@ -3,6 +3,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstddef>
 #include <cstring>
 #include <dlfcn.h>
 #include <atomic>
@@ -1454,6 +1455,16 @@ const fhp_point20* fhp_stream_row(const fhp_point20* blocks, const fhp_stream_ma
   return blocks + ((static_cast<int64_t>(g + 1) * groups + G) * 32 + rank * 4 + f);
 }
 
+// one 24-byte service row from a 20-byte streamed point: the first 20 bytes are the same {x, y, z}, the last four are
+// {foot_id, gait_cycle_id, kind, 0} as one word
+static inline void put_row(fhp_foothold24* o, const fhp_point20* b, int foot, int cycle, int kind) {
+  static_assert(sizeof(fhp_point20) == 20 && sizeof(fhp_foothold24) == 24 && offsetof(fhp_foothold24, z) == 16 &&
+                    offsetof(fhp_foothold24, foot_id) == 20 && offsetof(fhp_foothold24, kind) == 22,
+                "row layouts");
+  std::memcpy(o, b, 20);
+  const uint32_t tail = static_cast<uint32_t>(foot) | (static_cast<uint32_t>(cycle) << 8) | (static_cast<uint32_t>(kind) << 16);
+  std::memcpy(reinterpret_cast<char*>(o) + 20, &tail, 4);
+}
 int fhp_stream_expand(const fhp_point20* blocks, const fhp_stream_mask* masks, const fhp_query_status* status,
                       int64_t n_queries, int32_t gait_cycles, fhp_foothold24* out_rows, int64_t capacity_rows,
                       int64_t* row_offsets, int32_t n_threads) {
@@ -1473,10 +1484,7 @@ int fhp_stream_expand(const fhp_point20* blocks, const fhp_stream_mask* masks, c
       for (int64_t q = q0; q < q1; ++q) {  // stance rows: block (0, G), query order
         fhp_foothold24* o = out_rows + row_offsets[q];
         const fhp_point20* b = blocks + (G * 32 + (q - q0) * 4);
-        for (int f = 0; f < 4; ++f) {
-          o[f].x = b[f].x;  o[f].y = b[f].y;  o[f].z = b[f].z;
-          o[f].foot_id = static_cast<uint8_t>(f);  o[f].gait_cycle_id = 0;  o[f].kind = FHP_KIND_STANCE;  o[f].reserved = 0;
-        }
+        for (int f = 0; f < 4; ++f) put_row(o + f, b + f, f, 0, FHP_KIND_STANCE);
       }
       int64_t cursor[8];
       for (int64_t q = q0; q < q1; ++q) cursor[q - q0] = row_offsets[q] + 4;
@@ -1487,11 +1495,8 @@ int fhp_stream_expand(const fhp_point20* blocks, const fhp_stream_mask* masks, c
           const fhp_stream_mask* m = masks + (q * words + (g >> 5)) * 4;
           if (!(m[0].success & bit)) continue;
           fhp_foothold24* o = out_rows + cursor[q - q0];
-          for (int f = 0; f < 4; ++f) {
-            o[f].x = b[f].x;  o[f].y = b[f].y;  o[f].z = b[f].z;
-            o[f].foot_id = static_cast<uint8_t>(f);  o[f].gait_cycle_id = static_cast<uint8_t>(g);
-            o[f].kind = (m[f].candidate & bit) ? FHP_KIND_CANDIDATE : FHP_KIND_DEFAULT;  o[f].reserved = 0;
-          }
+          for (int f = 0; f < 4; ++f)
+            put_row(o + f, b + f, f, g, (m[f].candidate & bit) ? FHP_KIND_CANDIDATE : FHP_KIND_DEFAULT);
           cursor[q - q0] += 4;
           b += 4;
         }
