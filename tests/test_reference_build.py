@@ -15,7 +15,7 @@ import sys
 import numpy as np
 import pytest
 
-from quadrupedal_foothold_planner_b200 import _abi
+from quadrupedal_foothold_planner_b200 import _abi, synth
 from tests.parity import XYZ_TOL
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -161,3 +161,29 @@ def test_gpu_matches_reference_vectors(fhp, name):
     got = fhp.plan(p, q, n, centroid=True)
     assert np.all((got[2]["reserved"] & 0x7F) == 0)
     _compare_to_reference(got, _load(name), name, XYZ_TOL)
+
+
+@pytest.mark.parametrize("start", [(0, 0), (37, 211)])
+def test_non_finite_and_far_poses_abort_in_the_reference(oracle, start):
+    """Poses that are NaN, infinite, astronomically large or off the map: the compiled reference aborts every one of
+    them at gait cycle 0 (the opt chain's submap request fails, FP.cpp:931-934) and completes the ordinary ones; the
+    oracle raises FHP_STATUS_OPT_SUBMAP_FAIL for exactly those calls — whatever its nominal chain makes of the index
+    policy for non-finite coordinates is therefore never observable through the reference's service."""
+    if not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libfhp_ref.so")) and \
+            not os.path.isdir("/root/reference"):
+        pytest.skip("compiled reference not available in this environment")
+    odd = [[np.nan, 0.0, 0.0], [0.0, np.nan, 0.0], [np.inf, 0.0, 0.0], [0.0, -np.inf, 0.0], [1e300, 0.0, 0.0],
+           [0.0, -1e300, 0.0], [1e12, 1e12, 0.0], [-3.0e7, 2.0, 0.0], [50.0, 0.0, 0.0], [0.0, -50.0, 0.0],
+           [3.99, 0.0, 0.0], [-4.2, 3.7, 0.0], [0.0, 0.0, np.nan], [0.0, 0.0, np.inf], [-0.4, 0.3, 0.0]]
+    q = _abi.make_queries(odd)
+    m = synth.rough_map(200, 190, 0.02, seed=23, start=start)
+    p = _abi.yaml_params(spiral_mode=_abi.FHP_SPIRAL_FAITHFUL)
+    ref = oracle.ref_plan(m, p, q, 3, wrap_correct=False)
+    got = oracle.plan(m, p, q, 3, centroid=True)
+    aborted = ref[2]["reserved"] == 1
+    assert np.array_equal(aborted, (got[2]["reserved"] & 0x80) != 0)
+    assert aborted[:12].all() and not aborted[12:].any()  # a non-finite z is harmless: z never enters the geometry
+    assert np.all(ref[2]["n_rows"][aborted] == 4)
+    keep = ~aborted
+    for f in ("success", "gait_cycles_succeed", "n_rows"):
+        assert np.array_equal(got[2][f][keep], ref[2][f][keep]), f
