@@ -676,3 +676,50 @@ def test_non_finite_and_far_away_poses(fhp, oracle, start, mode):
         for f in ("x", "y", "z"):  # NaN == NaN here: the stance rows of a NaN pose carry it
             assert np.array_equal(got[k][f][owned], exp[k][f][owned], equal_nan=True), f
     assert int(es["gait_cycles_succeed"][:40].max()) > 0  # the ordinary queries next to them still plan
+
+
+def test_fuzz_kernel_vs_oracle(fhp, oracle):
+    """Random geometry the fixed tests do not visit — resolutions 0.01 / 0.02 / 0.025 / 0.04 m (windows of 23 / 11 / 9 /
+    7 columns: specialised and generic kernels), random map sizes and start indices, thresholds, step lengths, leg order,
+    gait, spiral variant, foot radius — every query against the oracle, bit for bit.  Fixed seed: a regression test,
+    not a campaign."""
+    from quadrupedal_foothold_planner_b200.planner import FhpError
+    import os
+    n_cases = int(os.environ.get("FHP_FUZZ_CASES", "28"))  # (campaigns by hand: FHP_FUZZ_SEED / FHP_FUZZ_CASES)
+    rng = np.random.default_rng(int(os.environ.get("FHP_FUZZ_SEED", "20261017")))
+    ran = 0
+    for case in range(n_cases):
+        res = float(rng.choice([0.02, 0.01, 0.025, 0.04]))
+        rows, cols = int(rng.integers(150, 420)), int(rng.integers(150, 420))
+        if res == 0.01:
+            rows += 200
+            cols += 200
+        start = (0, 0) if rng.random() < 0.3 else (int(rng.integers(0, rows)), int(rng.integers(0, cols)))
+        m = synth.rough_map(rows, cols, res, seed=int(rng.integers(1, 1 << 30)), start=start)
+        kw = {"spiral_mode": _abi.FHP_SPIRAL_FAITHFUL if rng.random() < 0.5 else _abi.FHP_SPIRAL_WRAP_CORRECT}
+        if rng.random() < 0.5:
+            kw["step_length"] = float(np.float32(rng.uniform(0.10, 0.26)))
+            kw["skew"] = float(np.float32(kw["step_length"] / 4))
+        if rng.random() < 0.3:
+            kw["rf_first"] = 1
+        if rng.random() < 0.3:
+            kw["gait"] = _abi.FHP_GAIT_WALK
+        if rng.random() < 0.3:
+            kw["thr_default"] = float(np.float32(rng.uniform(0.75, 0.95)))
+            kw["thr_candidate"] = float(np.float32(rng.uniform(0.5, 0.74)))
+        if rng.random() < 0.25:
+            kw["foot_radius"] = float(np.float32(rng.uniform(0.015, 0.045)))
+        p = _abi.yaml_params(**kw)
+        hx, hy = rows * res / 2, cols * res / 2
+        q = synth.uniform_queries(96, (-hx + 0.3, hx - 1.2), (-hy + 0.3, hy - 0.3), seed=int(rng.integers(1, 1 << 30)))
+        cycles = int(rng.integers(1, 9))
+        fhp.set_map(m)
+        try:
+            got = fhp.plan(p, q, cycles, centroid=True)
+        except FhpError as e:  # a foot-disc offset too close to the radius to classify: refused, never guessed
+            assert e.code == _abi.FHP_ERR_UNSUPPORTED, e
+            continue
+        exp = oracle.plan(m, p, q, cycles)
+        assert compare_plans(got, exp, f"fuzz case {case}: res {res} {rows}x{cols} start {start} {kw} cycles {cycles}") == 0.0
+        ran += 1
+    assert ran >= n_cases * 2 // 3

@@ -187,3 +187,14 @@ def test_non_finite_and_far_poses_abort_in_the_reference(oracle, start):
     keep = ~aborted
     for f in ("success", "gait_cycles_succeed", "n_rows"):
         assert np.array_equal(got[2][f][keep], ref[2][f][keep]), f
+
+
+def test_fuzz_oracle_vs_live_reference(oracle):
+    """A fixed-seed slice of tests/fuzz_reference.py: random maps / parameters / poses / spiral variants, the oracle against
+    the compiled reference bit for bit (the long campaigns are run by hand; their result is in the script's header)."""
+    if not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libfhp_ref.so")) and \
+            not os.path.isdir("/root/reference"):
+        pytest.skip("compiled reference not available in this environment")
+    from tests import fuzz_reference
+    cases, calls = fuzz_reference.run(oracle, seed=7, max_cases=150)
+    assert cases == 150 and calls > 600
